@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the flocking-env hot path (agent-steps/s), see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5]
+    python bench.py --impl reference ...        # CPU arm: the C oracle on the host cores
+
+A "step" is ONE fused-kernel pass of `step()` over one batch of E envs x N agents (random actions
+already resident in HBM). To keep the working set larger than the 126 MB L2, the bench cycles over
+a ring of R independent env batches (step s touches batch s % R), all on one stream, replayed from
+CUDA graphs so that Python launch overhead is not what is measured. Under torchrun every rank owns
+its own ring on its own GPU (envs shard with no data-path collective; the only collective is the
+NCCL all-reduce of the episode statistics after the timed region) -> weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE.json configs: density-scaled synthetic worlds, random actions
+WORKLOADS = {
+    # name: variant, E per GPU, N, k, collision, range_start, sensor, extra VecEnv kwargs, bytes/agent-step
+    "cfg2": dict(variant="v2", E=4096, N=10, k=4, cd=2.5, rs=(0, 50), sr=14.0, kw={}, bytes=53,
+                 desc="gym_flock_v2 batched 4096 envs x 10 agents, k=4, random actions (BASELINE configs[1])"),
+    "cfg3": dict(variant="uw", E=4096, N=32, k=3, cd=0.5, rs=(0, 200), sr=7.0, kw={}, bytes=125,
+                 desc="gym_flock_uw 4096 envs x 32 agents, k=3, random actions, materialised (N,4,k) window"),
+    "cfg4": dict(variant="uwd", E=8192, N=16, k=4, cd=0.5, rs=(0, 100), sr=7.0,
+                 kw=dict(reset_collision_distance=1.0), bytes=49,
+                 desc="gym_flock_uw_discrete 8192 envs x 16 agents, k=4, random action ids, Philox actuation noise"),
+    "cfg5": dict(variant="v2", E=64, N=2048, k=8, cd=0.05, rs=(0, 2000), sr=100.0, kw={}, bytes=69,
+                 desc="gym_flock_v2 large swarm 64 envs x 2048 agents, k=8 (tiled all-pairs path)"),
+}
+L2_BYTES = 126 * 1024 * 1024
+DT = 0.1
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.max_mhz = period_s, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (oracle/flock_oracle.c = a C port of the reference step, all host threads)
+# ---------------------------------------------------------------------------------------------------
+def cpu_run(w, steps, warmup, budget_s, nthreads=None):
+    """Time `steps` oracle steps on a bounded sample of the workload's envs; returns a dict."""
+    from oracle import flock_oracle as fo
+
+    threads = nthreads or fo.max_threads()
+    E_full = w["E"]
+    # calibrate the sample size so that warmup+steps fit the time budget
+    probe_E = min(E_full, max(threads * 4, 64))
+    env = fo.OracleEnv(w["variant"], probe_E, w["N"], w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"],
+                       seed=0x5EED, nthreads=threads, **w["kw"])
+    env.reset()
+    a = env.random_actions()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        env.step(a, DT)
+    per_env_step = (time.perf_counter() - t0) / 3 / probe_E
+    E = int(max(threads, min(E_full, budget_s / max(per_env_step * (steps + warmup), 1e-12))))
+    env = fo.OracleEnv(w["variant"], E, w["N"], w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"],
+                       seed=0x5EED, nthreads=threads, **w["kw"])
+    env.reset()
+    acts = [env.random_actions(i) for i in range(8)]
+    for i in range(warmup):
+        env.step(acts[i % 8], DT)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step(acts[i % 8], DT)
+    dt = time.perf_counter() - t0
+    return dict(value=E * w["N"] * steps / dt, seconds=dt, envs=E, threads=threads,
+                sample=f"{steps} steps of {E} of the {E_full} envs x {w['N']} agents (oracle/flock_oracle.c, OpenMP over envs)")
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 2000), min(args.warmup, 50)
+    r = cpu_run(w, steps, warmup, budget_s=60.0)
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec", "value": r["value"], "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["seconds"] / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "envs_per_step": r["envs"], "agents": w["N"], "k": w["k"]},
+        "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["threads"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference itself is Python/PyTorch and cannot travel to the GPU box; this arm times the C port "
+                "of its step (oracle/), which is FASTER than the reference's own dispatch-bound step (BASELINE.md s3)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def build_ring(w, E, ring, device, env_offset, seed=0x5EED):
+    import torch
+    from marl_range_flocking_b200 import VecEnv
+
+    envs, acts = [], []
+    for r in range(ring):
+        env = VecEnv(w["variant"], E, w["N"], w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"],
+                     seed=seed + r, env_offset=env_offset, device=device, **w["kw"])
+        env.reset()
+        envs.append(env)
+        acts.append([env.random_actions(i) for i in range(2)])
+    torch.cuda.synchronize(device)
+    return envs, acts
+
+
+def capture(envs, acts, n, start):
+    """CUDA graph of n consecutive bench steps (step s -> batch s % R)."""
+    import torch
+
+    g = torch.cuda.CUDAGraph()
+    R = len(envs)
+    with torch.cuda.graph(g):
+        for s in range(start, start + n):
+            envs[s % R].step(acts[s % R][(s // R) & 1], DT)
+    return g
+
+
+def timed_graph_steps(envs, acts, steps, warmup, device, dist_barrier):
+    import torch
+
+    chunk = min(steps, 1024)
+    full, rem = divmod(steps, chunk)
+    g_full = capture(envs, acts, chunk, 0)
+    g_rem = capture(envs, acts, rem, 0) if rem else None
+    wfull, wrem = divmod(warmup, chunk)
+    g_w = capture(envs, acts, wrem, 0) if wrem else None
+    for _ in range(wfull):
+        g_full.replay()
+    if g_w is not None:
+        g_w.replay()
+    torch.cuda.synchronize(device)
+    dist_barrier()
+    launches0 = sum(e.launch_count for e in envs)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    ev0.record()
+    for _ in range(full):
+        g_full.replay()
+    if g_rem is not None:
+        g_rem.replay()
+    ev1.record()
+    torch.cuda.synchronize(device)
+    dist_barrier()
+    # graph replays do not go through flock_step again: launches = one fused kernel per step
+    # (+ one memset node per step on the tiled path, not counted as a kernel)
+    del launches0
+    return ev0.elapsed_time(ev1), steps
+
+
+def timed_e2e(env, w, steps, warmup, device):
+    """Host buffers in / out through flock_step_host (C ABI): H2D actions, fused step, D2H results."""
+    import torch
+
+    E, N = env.num_envs, env.num_particles
+    host_acts = [env.random_actions(i).cpu().pin_memory() for i in range(4)]
+    torch.cuda.synchronize(device)
+    for i in range(warmup):
+        env.step_host(host_acts[i % 4], DT)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(steps):
+        env.step_host(host_acts[i % 4], DT)
+    ev1.record()
+    torch.cuda.synchronize(device)
+    wall = time.perf_counter() - t0
+    h2d = host_acts[0].numel() * 4
+    d2h = env._obs.numel() * 4 + E * N * 4 + E * N + E
+    return max(ev0.elapsed_time(ev1) * 1e-3, wall), h2d, d2h
+
+
+def run_gpu(args, w):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+        def barrier():
+            dist.barrier()
+    else:
+        def barrier():
+            return None
+
+    E, N = w["E"], w["N"]
+    bytes_per_batch = E * N * (w["bytes"] + 40)           # + nn_idx, velocities, episode counters
+    ring = args.ring or max(2, -(-int(1.25 * L2_BYTES) // bytes_per_batch))
+    envs, acts = build_ring(w, E, ring, device, env_offset=rank * E)
+
+    sampler = ClockSampler(local if os.environ.get("CUDA_VISIBLE_DEVICES") is None else 0)
+    # map the torch device to its NVML index through the UUID when possible
+    try:
+        import pynvml
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        pynvml.nvmlInit()
+        for i in range(pynvml.nvmlDeviceGetCount()):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            u = pynvml.nvmlDeviceGetUUID(h)
+            u = u.decode() if isinstance(u, bytes) else u
+            if uuid in u:
+                sampler.h = h
+                sampler.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+    except Exception:
+        pass
+    sampler.start()
+    ms, steps = timed_graph_steps(envs, acts, args.steps, args.warmup, device, barrier)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    agent_steps = world * E * N * steps
+    value = agent_steps / (ms_max * 1e-3)
+
+    # end-to-end through the host-buffer C ABI call (every rank, max time)
+    e2e_steps = min(args.steps, 2000)
+    e2e_s, h2d, d2h = timed_e2e(envs[0], w, e2e_steps, min(args.warmup, 20), device)
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * N * e2e_steps / float(t.item())
+
+    # the one collective of the system: all-reduce of the episode statistics (NCCL over NVLink)
+    stats = envs[0].stats_tensor().clone()
+    if use_dist:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+
+    # persistent multi-step mode (flock_step_n): state stays in registers, no per-step HBM traffic
+    extra = {}
+    if envs[0].tiled is False and rank == 0:
+        T = 256
+        envs[1].step_n(T, DT)
+        torch.cuda.synchronize(device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        envs[1].step_n(T, DT)
+        ev1.record()
+        torch.cuda.synchronize(device)
+        extra["step_n_persistent"] = {"steps_per_launch": T, "agent_steps_per_s_per_gpu": E * N * T / (ev0.elapsed_time(ev1) * 1e-3),
+                                      "note": "in-kernel Philox actions, state in registers; FP32-issue bound, no per-step HBM traffic"}
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        per_launch_s = ms_max * 1e-3 / steps
+        alg_bytes = E * N * w["bytes"]
+        achieved = alg_bytes / per_launch_s / 1e9
+        line = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + w["desc"], "envs_per_gpu": E, "agents": N, "k": w["k"],
+                       "l2_policy": f"inputs larger than L2: ring of {ring} independent env batches "
+                                    f"({ring * bytes_per_batch / 2**20:.0f} MiB), step s touches batch s % {ring}",
+                       "launch": "CUDA graph replay, one fused kernel per step, single stream"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": TRAFFIC_PER_LAUNCH.get(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "achieved = algorithmic bytes / mean launch-to-launch time of the timed region"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "VecEnv.step_host -> flock_step_host (pinned host buffers, sync per step)"},
+            "gpu_launches": steps * world,
+            "stats_allreduce": {"backend": "nccl" if use_dist else "none", "episodes": int(stats[0].item())},
+        }
+        line.update(extra)
+        if world == 1 and not args.no_cpu:
+            r = cpu_run(w, 30, 3, budget_s=12.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "agent-steps/s", "cores": r["threads"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed
+# ncu --set full captures under profiles/ (None until measured)
+TRAFFIC_PER_LAUNCH = {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20480)
+    ap.add_argument("--warmup", type=int, default=1024)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ring", type=int, default=0, help="number of env batches in the L2-defeating ring (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_gpu(args, w)
+
+
+if __name__ == "__main__":
+    main()

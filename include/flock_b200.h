@@ -1,0 +1,182 @@
+/*
+ * flock_b200.h -- C ABI of libflock_b200.so: the B200 (sm_100a) batched range-only flocking
+ * environment. Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (RetamalVictor/marl-range-flocking) has no FFI: its boundary is the Python
+ * class `MultiAgentEnv` of environments/gym_flock_v2.py, gym_flock_uw.py and
+ * gym_flock_uw_discrete.py. Each entry point below states which reference method(s) it replaces;
+ * the Python mirror of that class API lives in marl_range_flocking_b200/ and the binding a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative FLOCK_E_* code; the message is available
+ *     from flock_last_error() (thread local). Nothing throws across the ABI.
+ *   - device buffers are OWNED BY THE CALLER (torch tensors in the Python host); the library
+ *     borrows raw device pointers via flock_bind() and never frees them.
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); only the
+ *     *_host entry points synchronise that stream before returning.
+ *   - one handle per device; a handle is not thread safe.
+ *   - state layout: structure of arrays, float32, `[E][N]` row-major (E envs, N agents).
+ */
+#ifndef FLOCK_B200_H
+#define FLOCK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FLOCK_API __attribute__((visibility("default")))
+#else
+#define FLOCK_API
+#endif
+
+#define FLOCK_ABI_VERSION 1
+#define FLOCK_MAX_K 8          /* neighbours per agent (reference uses 3, 4; BASELINE cfg 5 uses 8) */
+#define FLOCK_MAX_AGENTS 8192  /* per env; whole env is staged in shared memory */
+
+enum {
+    FLOCK_OK = 0,
+    FLOCK_E_INVALID = -1,   /* bad argument / configuration */
+    FLOCK_E_UNBOUND = -2,   /* flock_bind() not called or a required pointer is NULL */
+    FLOCK_E_CUDA = -3,      /* CUDA runtime error (message has the cudaError string) */
+    FLOCK_E_NO_DEVICE = -4  /* no sm_100 device: there is NO CPU fallback */
+};
+
+enum { FLOCK_V2 = 0, FLOCK_UW = 1, FLOCK_UWD = 2 };
+
+/* Mirrors the constructor arguments of MultiAgentEnv.__init__ (gym_flock_v2.py:21-69,
+ * gym_flock_uw.py:20-67, gym_flock_uw_discrete.py:20-108) plus the per-variant constants that the
+ * reference hard-codes inside reset()/step(). */
+typedef struct flock_cfg_t {
+    int32_t variant;            /* FLOCK_V2 / FLOCK_UW / FLOCK_UWD */
+    int32_t num_envs;           /* E: env instances on this device */
+    int32_t num_agents;         /* N: `agents` */
+    int32_t k;                  /* `k` nearest neighbours, 1..FLOCK_MAX_K, N >= k+1 */
+    int32_t rigid_boundary;     /* `rigid_boundary` (check_boundary, gym_flock_v2.py:271-304) */
+    int32_t periodic;           /* 1: min-image metric in step (_computePeriodicDistances, v2:135) */
+    int32_t obs_hist;           /* 4 for uw (memory_size, gym_flock_uw.py:59), else 1 */
+    int32_t env_offset;         /* global index of local env 0 (sharding across GPUs) */
+    float boundary;             /* range_start[1] */
+    float range_lo;             /* range_start[0] */
+    float reset_hi;             /* upper end of the reset box: r1 (v2, uwd) or r1//2 (uw:87-89) */
+    float heading_hi;           /* 1.5*pi (v2:96), 2*pi (uw:92), pi/1.2 (uwd:133) */
+    float sensor_range;
+    float collision_distance;
+    float reset_collision_distance; /* uwd: 4 (gym_flock_uw_discrete.py:145); else collision_distance */
+    float max_linear_velocity;
+    float act_noise_std;        /* uwd: 0.1 (gym_flock_uw_discrete.py:333-334); else 0 */
+    float reserved0;
+    uint64_t seed;              /* Philox4x32-10 key */
+} flock_cfg_t;
+
+/* Device pointers of the caller-owned buffers. `*_alt` are the second copy of the state used by
+ * the tiled (N > 32) path, which ping-pongs between the two copies every step; they may be NULL
+ * when N <= 32. Nullable outputs are skipped by the kernels. */
+typedef struct flock_buffers_t {
+    float *x, *y, *h;               /* [E][N] positions and headings (current copy = slot 0) */
+    float *x_alt, *y_alt, *h_alt;   /* [E][N] slot 1 (tiled path only) */
+    float *prev_h;                  /* [E][N] `prev_headings` (uw reward term, gym_flock_uw.py:201) */
+    float *vx, *vy;                 /* [E][N] last displacement = reference `velocities`; nullable */
+    float *obs;                     /* [E][N][obs_hist][k] newest first (gym_flock_uw.py:120-123) */
+    int32_t *nn_idx;                /* [E][N][k] `nearest_neighbors` (v2:150); nullable */
+    float *reward;                  /* [E][N] (reference shape (N,1)) */
+    uint8_t *agent_done;            /* [E][N] `dones[0]` (v2:314) */
+    uint8_t *env_done;              /* [E]    `dones[1]` (v2:315), stays on the device */
+    uint32_t *reset_epoch;          /* [E] Philox attempt counter of reset() */
+    int64_t *ep_return_fx;          /* [E] sum over the episode of sum_i reward_i, fixed point 2^-32; nullable */
+    int32_t *ep_len;                /* [E] steps since the last reset */
+    uint64_t *stats;                /* [8] FLOCK_STAT_* accumulators flushed by reset; nullable */
+} flock_buffers_t;
+
+enum {
+    FLOCK_STAT_EPISODES = 0,     /* episodes closed by reset() (ep_len > 0) */
+    FLOCK_STAT_EP_STEPS = 1,     /* sum of their lengths */
+    FLOCK_STAT_EP_RETURN_FX = 2, /* sum of their returns (two's complement int64, 2^-32 units) */
+    FLOCK_STAT_RESET_ATTEMPTS = 3,
+    FLOCK_STAT_RESET_GAVE_UP = 4,
+    FLOCK_STAT_COUNT = 8
+};
+
+typedef struct flock_env flock_env_t;
+
+/* MultiAgentEnv.__init__ (gym_flock_v2.py:21). Validates the configuration, selects the device,
+ * allocates only the small host-call staging buffers. */
+FLOCK_API int flock_create(const flock_cfg_t *cfg, int device, flock_env_t **out);
+FLOCK_API void flock_destroy(flock_env_t *env);
+
+/* Attach the caller-owned device buffers. */
+FLOCK_API int flock_bind(flock_env_t *env, const flock_buffers_t *bufs);
+
+/* MultiAgentEnv.reset (gym_flock_v2.py:85-108, gym_flock_uw.py:83-111,
+ * gym_flock_uw_discrete.py:124-156), batched and masked.
+ *   env_mask   device uint8[E], nullable (NULL = every env). Pass the env_done buffer to reset
+ *              exactly the finished envs without a host round trip.
+ *   init_state device float[3][E][N] (x, y, heading), nullable. NULL: Philox draws with at most
+ *              `max_attempts` rejection rounds per env (the reference recurses without bound);
+ *              non-NULL: the given state is installed (parity injection), one pass.
+ *   flags      FLOCK_RESET_KEEP_OUTPUTS: auto-reset mode, leave reward / agent_done / env_done
+ *              of the step that finished the episode untouched (env_mask may then alias the
+ *              env_done buffer); 0: write reward = 0 and the done flags of the new start
+ *              (env_done = the start still collides).
+ * Always writes the state, obs and nn_idx of the reset envs and closes their episode counters. */
+#define FLOCK_RESET_KEEP_OUTPUTS 1
+FLOCK_API int flock_reset(flock_env_t *env, const uint8_t *env_mask, const float *init_state,
+                          int max_attempts, int flags, void *stream);
+
+/* MultiAgentEnv.step (gym_flock_v2.py:71-83, gym_flock_uw.py:69-81,
+ * gym_flock_uw_discrete.py:110-122): ONE fused kernel = _updateState + check_boundary +
+ * _compute(Periodic)Distances + _computeCollisions + _computeObs + _computeDone + _computeReward.
+ *   actions device float[E][N][2] (v2: linear, angular; uw: velocity direction) or float[E][N]
+ *           (uwd: float-coded action id 0..9).
+ *   noise   uwd only, nullable: device float[E][N][2] additive (linear, angular) actuation noise
+ *           replacing the in-kernel Philox N(0, act_noise_std) draw (reference: torch.normal,
+ *           gym_flock_uw_discrete.py:333-334). */
+FLOCK_API int flock_step(flock_env_t *env, const float *actions, float dt, const float *noise, void *stream);
+
+/* T consecutive steps with the canonical in-kernel random actions (action_space sampling:
+ * v2 U[-1.5,1.5)^2 gym_flock_v2.py:58, uw U[-1,1)^2 gym_flock_uw.py:57, uwd id in [0,k)
+ * gym_flock_uw_discrete.py:98). N <= 32: one persistent launch with the state in registers;
+ * N > 32: T launches. Outputs hold the last step. */
+FLOCK_API int flock_step_n(flock_env_t *env, int num_steps, float dt, void *stream);
+
+/* Fill `actions` (device, layout as in flock_step) with the canonical random actions that
+ * flock_step_n would use `step_offset` steps from now. Philox4x32-10 stream layout: key = seed,
+ * counter = (global env, agent, ep_len[env] + offset, tag + 4 * reset_epoch[env]); the epoch words
+ * are per-env device counters, so streams do not depend on the GPU count or on host state. */
+FLOCK_API int flock_random_actions(flock_env_t *env, uint32_t step_offset, float *actions, void *stream);
+
+/* Host-buffer form of step(): copies `h_actions` (pinned or pageable host memory) to the device,
+ * runs the fused step, copies obs / reward / agent_done / env_done back and synchronises the
+ * stream. Any output pointer may be NULL. This is the end-to-end path timed as `e2e`. */
+FLOCK_API int flock_step_host(flock_env_t *env, const float *h_actions, float dt, const float *h_noise,
+                    float *h_obs, float *h_reward, uint8_t *h_agent_done, uint8_t *h_env_done,
+                    void *stream);
+
+/* Which state copy is current (0: x/y/h, 1: x_alt/y_alt/h_alt). Always 0 when N <= 32. */
+FLOCK_API int flock_state_slot(const flock_env_t *env);
+
+/* Host-side count of steps issued through this handle (informational). */
+FLOCK_API uint32_t flock_get_step_index(const flock_env_t *env);
+FLOCK_API int flock_set_step_index(flock_env_t *env, uint32_t step_index);
+
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+FLOCK_API uint64_t flock_launch_count(const flock_env_t *env);
+
+/* 0: warp-per-env-group path (N <= 32), 1: tiled path (N > 32). */
+FLOCK_API int flock_path(const flock_env_t *env);
+
+FLOCK_API const char *flock_last_error(void);
+FLOCK_API int flock_abi_version(void);
+
+/* Debug / test hooks for the canonical arithmetic (device arrays, n elements). */
+FLOCK_API int flock_debug_sincos(const float *h, int n, float *sn, float *cs, void *stream);
+FLOCK_API int flock_debug_normal2(const uint32_t *words, int n_pairs, float *z, void *stream);
+FLOCK_API int flock_debug_philox(const uint32_t *ctr4_key2, int n, uint32_t *out4, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOCK_B200_H */

@@ -1,0 +1,320 @@
+// flock_api.cu -- the C ABI of libflock_b200.so (include/flock_b200.h): handle management,
+// parameter marshalling and kernel dispatch. No torch types, no exceptions across the boundary.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "flock_device.cuh"
+#include "flock_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(FLOCK_E_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+}  // namespace
+
+struct flock_env {
+    flock_cfg_t cfg;
+    flock_buffers_t b;
+    bool bound;
+    int device;
+    int sm_count;
+    int path;            // 0 small, 1 tiled
+    int slot;            // current state copy on the tiled path
+    uint32_t step_index;
+    uint64_t launches;
+    float* stage_actions;  // device staging for host-call / step_n(tiled) actions
+    float* stage_noise;
+    unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
+    size_t action_floats;
+};
+
+namespace {
+
+using flock::Params;
+
+int validate(const flock_cfg_t& c) {
+    if (c.variant < FLOCK_V2 || c.variant > FLOCK_UWD) return fail(FLOCK_E_INVALID, "variant %d not in {0,1,2}", c.variant);
+    if (c.num_envs < 1) return fail(FLOCK_E_INVALID, "num_envs must be >= 1 (got %d)", c.num_envs);
+    if (c.k < 1 || c.k > FLOCK_MAX_K) return fail(FLOCK_E_INVALID, "k must be in [1, %d] (got %d)", FLOCK_MAX_K, c.k);
+    if (c.num_agents < c.k + 1)   // the reference needs topk(k+1) <= N (gym_flock_v2.py:147)
+        return fail(FLOCK_E_INVALID, "num_agents (%d) must be >= k+1 (%d)", c.num_agents, c.k + 1);
+    if (c.num_agents > FLOCK_MAX_AGENTS)
+        return fail(FLOCK_E_INVALID, "num_agents (%d) exceeds FLOCK_MAX_AGENTS (%d)", c.num_agents, FLOCK_MAX_AGENTS);
+    const int want_h = c.variant == FLOCK_UW ? 4 : 1;
+    if (c.obs_hist != want_h) return fail(FLOCK_E_INVALID, "obs_hist must be %d for variant %d", want_h, c.variant);
+    if (c.periodic && c.variant != FLOCK_V2) return fail(FLOCK_E_INVALID, "periodic metric is only defined for v2");
+    if (!(c.boundary > 0.0f)) return fail(FLOCK_E_INVALID, "boundary must be > 0");
+    if ((long long)c.num_envs * c.num_agents > (1LL << 31) - 1) return fail(FLOCK_E_INVALID, "E*N too large");
+    return FLOCK_OK;
+}
+
+Params make_params(const flock_env* e, float dt) {
+    const flock_cfg_t& c = e->cfg;
+    const flock_buffers_t& b = e->b;
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.E = c.num_envs; p.N = c.num_agents; p.k = c.k; p.H = c.obs_hist;
+    p.rigid = c.rigid_boundary; p.env_offset = c.env_offset;
+    p.G = c.num_agents <= 32 ? 32 / c.num_agents : 0;
+    p.sstride = (c.num_agents + 3) & ~3;
+    p.B = c.boundary;
+    p.halfB = (float)((double)c.boundary / 2.0);
+    p.sensor_range = c.sensor_range;
+    p.cd = c.collision_distance;
+    p.cd4 = (float)((double)c.collision_distance * 4.0);   // gym_flock_uw.py:197
+    p.vmax = c.max_linear_velocity;
+    p.noise_std = c.act_noise_std;
+    p.dt = dt;
+    p.range_lo = c.range_lo; p.reset_hi = c.reset_hi; p.heading_hi = c.heading_hi;
+    p.reset_cd = c.reset_collision_distance;
+    p.seed_lo = (uint32_t)c.seed; p.seed_hi = (uint32_t)(c.seed >> 32);
+    p.step_offset = 0;
+    p.num_steps = 1;
+    p.max_attempts = 1;
+    const bool alt = e->path == 1 && e->slot == 1;
+    p.x = alt ? b.x_alt : b.x; p.y = alt ? b.y_alt : b.y; p.h = alt ? b.h_alt : b.h;
+    if (e->path == 1) {   // write the other copy
+        p.xo = alt ? b.x : b.x_alt; p.yo = alt ? b.y : b.y_alt; p.ho = alt ? b.h : b.h_alt;
+    } else {
+        p.xo = b.x; p.yo = b.y; p.ho = b.h;
+    }
+    p.prev_h = b.prev_h; p.vx = b.vx; p.vy = b.vy; p.obs = b.obs; p.nn = b.nn_idx;
+    p.reward = b.reward; p.agent_done = b.agent_done; p.env_done = b.env_done;
+    p.reset_epoch = b.reset_epoch;
+    p.ep_return_fx = reinterpret_cast<long long*>(b.ep_return_fx);
+    p.ep_len = b.ep_len;
+    p.stats = reinterpret_cast<unsigned long long*>(b.stats);
+    p.tile_scratch = e->tile_scratch;
+    return p;
+}
+
+int check_bound(const flock_env* e) {
+    if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
+    if (!e->bound) return fail(FLOCK_E_UNBOUND, "flock_bind() has not been called");
+    return FLOCK_OK;
+}
+
+int step_device(flock_env* e, const float* actions, float dt, const float* noise, cudaStream_t s) {
+    Params p = make_params(e, dt);
+    p.actions = actions;
+    p.noise = noise;
+    cudaError_t err;
+    if (e->path == 0) {
+        err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
+        e->launches += 1;
+    } else {
+        err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, s);
+        e->launches += 1;
+        if (err == cudaSuccess) e->slot ^= 1;
+    }
+    if (err != cudaSuccess) return cuda_fail(err, "step kernel launch");
+    e->step_index += 1;
+    return FLOCK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* flock_last_error(void) { return g_err; }
+int flock_abi_version(void) { return FLOCK_ABI_VERSION; }
+
+int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
+    if (cfg == nullptr || out == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    *out = nullptr;
+    int rc = validate(*cfg);
+    if (rc != FLOCK_OK) return rc;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(FLOCK_E_NO_DEVICE, "no CUDA device (%s); libflock_b200 has no CPU fallback",
+                    err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+    if (device < 0 || device >= count) return fail(FLOCK_E_INVALID, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    err = cudaGetDeviceProperties(&prop, device);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(FLOCK_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    err = cudaSetDevice(device);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaSetDevice");
+    flock_env* e = new (std::nothrow) flock_env();
+    if (e == nullptr) return fail(FLOCK_E_INVALID, "out of host memory");
+    memset(e, 0, sizeof(*e));
+    e->cfg = *cfg;
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    e->path = cfg->num_agents <= 32 ? 0 : 1;
+    const int aw = cfg->variant == FLOCK_UWD ? 1 : 2;
+    e->action_floats = (size_t)cfg->num_envs * cfg->num_agents * aw;
+    err = cudaMalloc(&e->stage_actions, e->action_floats * sizeof(float));
+    if (err == cudaSuccess && cfg->variant == FLOCK_UWD)
+        err = cudaMalloc(&e->stage_noise, (size_t)cfg->num_envs * cfg->num_agents * 2 * sizeof(float));
+    if (err == cudaSuccess && e->path == 1) err = flock::tiled_configure(cfg->num_agents);
+    if (err == cudaSuccess && e->path == 1) {
+        err = cudaMalloc(&e->tile_scratch, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
+        if (err == cudaSuccess) err = cudaMemset(e->tile_scratch, 0, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
+    }
+    if (err != cudaSuccess) {
+        cudaFree(e->tile_scratch);
+        cudaFree(e->stage_actions);
+        cudaFree(e->stage_noise);
+        delete e;
+        return cuda_fail(err, "flock_create");
+    }
+    *out = e;
+    return FLOCK_OK;
+}
+
+void flock_destroy(flock_env_t* e) {
+    if (e == nullptr) return;
+    cudaFree(e->stage_actions);
+    cudaFree(e->stage_noise);
+    cudaFree(e->tile_scratch);
+    delete e;
+}
+
+int flock_bind(flock_env_t* e, const flock_buffers_t* b) {
+    if (e == nullptr || b == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    if (!b->x || !b->y || !b->h || !b->prev_h || !b->obs || !b->reward || !b->agent_done || !b->env_done ||
+        !b->reset_epoch || !b->ep_len)
+        return fail(FLOCK_E_UNBOUND, "a required buffer pointer is NULL");
+    if (e->path == 1 && (!b->x_alt || !b->y_alt || !b->h_alt))
+        return fail(FLOCK_E_UNBOUND, "tiled path (N > 32) needs x_alt / y_alt / h_alt");
+    e->b = *b;
+    e->bound = true;
+    e->slot = 0;
+    return FLOCK_OK;
+}
+
+int flock_reset(flock_env_t* e, const uint8_t* env_mask, const float* init_state, int max_attempts, int flags,
+                void* stream) {
+    int rc = check_bound(e);
+    if (rc != FLOCK_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Params p = make_params(e, 0.0f);
+    p.env_mask = env_mask;
+    p.init_state = init_state;
+    p.max_attempts = max_attempts > 0 ? max_attempts : 64;
+    p.reset_flags = flags;
+    // reset installs the state into the CURRENT copy
+    p.xo = const_cast<float*>(p.x); p.yo = const_cast<float*>(p.y); p.ho = const_cast<float*>(p.h);
+    cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s) : flock::launch_reset_tiled(p, s);
+    e->launches += 1;
+    if (err != cudaSuccess) return cuda_fail(err, "reset kernel launch");
+    return FLOCK_OK;
+}
+
+int flock_step(flock_env_t* e, const float* actions, float dt, const float* noise, void* stream) {
+    int rc = check_bound(e);
+    if (rc != FLOCK_OK) return rc;
+    if (actions == nullptr) return fail(FLOCK_E_INVALID, "actions is NULL");
+    return step_device(e, actions, dt, noise, static_cast<cudaStream_t>(stream));
+}
+
+int flock_random_actions(flock_env_t* e, uint32_t step_offset, float* actions, void* stream) {
+    int rc0 = check_bound(e);
+    if (rc0 != FLOCK_OK) return rc0;
+    if (actions == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    Params p = make_params(e, 0.0f);
+    p.step_offset = step_offset;
+    cudaError_t err = flock::launch_random_actions(e->cfg.variant, p, actions, e->sm_count,
+                                                   static_cast<cudaStream_t>(stream));
+    e->launches += 1;
+    if (err != cudaSuccess) return cuda_fail(err, "random_actions kernel launch");
+    return FLOCK_OK;
+}
+
+int flock_step_n(flock_env_t* e, int num_steps, float dt, void* stream) {
+    int rc = check_bound(e);
+    if (rc != FLOCK_OK) return rc;
+    if (num_steps < 1) return fail(FLOCK_E_INVALID, "num_steps must be >= 1");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->path == 0) {
+        Params p = make_params(e, dt);
+        p.num_steps = num_steps;
+        cudaError_t err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, true, e->sm_count, s);
+        e->launches += 1;
+        if (err != cudaSuccess) return cuda_fail(err, "step_n kernel launch");
+        e->step_index += (uint32_t)num_steps;
+        return FLOCK_OK;
+    }
+    for (int t = 0; t < num_steps; ++t) {
+        rc = flock_random_actions(e, 0u, e->stage_actions, stream);
+        if (rc != FLOCK_OK) return rc;
+        rc = step_device(e, e->stage_actions, dt, nullptr, s);
+        if (rc != FLOCK_OK) return rc;
+    }
+    return FLOCK_OK;
+}
+
+int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
+                    float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done, void* stream) {
+    int rc = check_bound(e);
+    if (rc != FLOCK_OK) return rc;
+    if (h_actions == nullptr) return fail(FLOCK_E_INVALID, "h_actions is NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t EN = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+    cudaError_t err = cudaMemcpyAsync(e->stage_actions, h_actions, e->action_floats * sizeof(float),
+                                      cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return cuda_fail(err, "H2D actions");
+    const float* d_noise = nullptr;
+    if (h_noise != nullptr && e->stage_noise != nullptr) {
+        err = cudaMemcpyAsync(e->stage_noise, h_noise, EN * 2 * sizeof(float), cudaMemcpyHostToDevice, s);
+        if (err != cudaSuccess) return cuda_fail(err, "H2D noise");
+        d_noise = e->stage_noise;
+    }
+    rc = step_device(e, e->stage_actions, dt, d_noise, s);
+    if (rc != FLOCK_OK) return rc;
+    if (h_obs != nullptr && err == cudaSuccess)
+        err = cudaMemcpyAsync(h_obs, e->b.obs, EN * e->cfg.obs_hist * e->cfg.k * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (h_reward != nullptr && err == cudaSuccess)
+        err = cudaMemcpyAsync(h_reward, e->b.reward, EN * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (h_agent_done != nullptr && err == cudaSuccess)
+        err = cudaMemcpyAsync(h_agent_done, e->b.agent_done, EN, cudaMemcpyDeviceToHost, s);
+    if (h_env_done != nullptr && err == cudaSuccess)
+        err = cudaMemcpyAsync(h_env_done, e->b.env_done, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return cuda_fail(err, "D2H outputs");
+    err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) return cuda_fail(err, "stream synchronize");
+    return FLOCK_OK;
+}
+
+int flock_state_slot(const flock_env_t* e) { return e ? e->slot : 0; }
+uint32_t flock_get_step_index(const flock_env_t* e) { return e ? e->step_index : 0u; }
+int flock_set_step_index(flock_env_t* e, uint32_t step_index) {
+    if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
+    e->step_index = step_index;
+    return FLOCK_OK;
+}
+uint64_t flock_launch_count(const flock_env_t* e) { return e ? e->launches : 0ULL; }
+int flock_path(const flock_env_t* e) { return e ? e->path : 0; }
+
+int flock_debug_sincos(const float* h, int n, float* sn, float* cs, void* stream) {
+    cudaError_t err = flock::launch_debug_sincos(h, n, sn, cs, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "debug_sincos");
+}
+int flock_debug_normal2(const uint32_t* words, int n_pairs, float* z, void* stream) {
+    cudaError_t err = flock::launch_debug_normal2(words, n_pairs, z, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "debug_normal2");
+}
+int flock_debug_philox(const uint32_t* ctr4_key2, int n, uint32_t* out4, void* stream) {
+    cudaError_t err = flock::launch_debug_philox(ctr4_key2, n, out4, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "debug_philox");
+}
+
+}  // extern "C"

@@ -1,0 +1,357 @@
+// flock_device.cuh -- device-side building blocks shared by the sm_100a flocking kernels.
+//
+// Canonical arithmetic (DESIGN.md section "Canonical arithmetic"): every parity-critical
+// expression is a single IEEE binary32 operation; the translation units are compiled with
+// -fmad=false so nvcc never contracts a*b+c, and fused operations appear only as explicit
+// fmaf()/fma() calls that the CPU oracle restates one for one.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/flock_b200.h"
+
+namespace flock {
+
+constexpr int kWarp = 32;
+#define kInf (__int_as_float(0x7f800000))
+constexpr float kFltMax = 3.4028234663852886e38f;
+
+enum : uint32_t { kTagReset = 0u, kTagNoise = 1u, kTagAction = 2u };
+
+// Kernel parameters (passed by value as a __grid_constant__).
+struct Params {
+    int E, N, k, H;
+    int rigid, env_offset;
+    int G;        // envs per warp (small path)
+    int sstride;  // shared-memory stride of one env group, floats (small path)
+    float B, halfB, sensor_range, cd, cd4, vmax, noise_std, dt;
+    float range_lo, reset_hi, heading_hi, reset_cd;
+    uint32_t seed_lo, seed_hi, step_offset;   // step_offset: flock_random_actions look-ahead
+    int num_steps;      // step_n
+    int max_attempts;   // reset
+    int reset_flags;    // reset: FLOCK_RESET_*
+    const float* actions;
+    const float* noise;
+    const float* init_state;
+    const uint8_t* env_mask;
+    const float *x, *y, *h;   // state read this step
+    float *xo, *yo, *ho;      // state written this step (== x,y,h on the small path)
+    float* prev_h;
+    float *vx, *vy;
+    float* obs;
+    int32_t* nn;
+    float* reward;
+    uint8_t* agent_done;
+    uint8_t* env_done;
+    uint32_t* reset_epoch;
+    long long* ep_return_fx;
+    int32_t* ep_len;
+    unsigned long long* stats;
+    unsigned int* tile_scratch;   // tiled path: [E] CTA arrival counters, [E] collision counters (self-resetting)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Canonical transcendental functions (same DEFINITION as oracle/flock_oracle.c, separate code).
+// ---------------------------------------------------------------------------------------------
+
+// sin/cos of a binary32 angle: fp64 Cody-Waite reduction to |r| <= pi/4, fp32 polynomials with
+// explicit fmaf. Replaces torch.cos / torch.sin of gym_flock_v2.py:335-336 and
+// gym_flock_uw_discrete.py:351-352 (<= 2 ulp from the correctly rounded value).
+__device__ __forceinline__ void sincos_canon(float h, float& sn, float& cs) {
+    const double hd = (double)h;
+    if (!(fabs(hd) < 1.0e9)) {
+        sn = __int_as_float(0x7fc00000);
+        cs = sn;
+        return;
+    }
+    const double q = rint(hd * 0.63661977236758134308);
+    double r = fma(-q, 1.57079632673412561417, hd);
+    r = fma(-q, 6.07710050650619224932e-11, r);
+    const float x = (float)r;
+    const float z = x * x;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(z, ps, -1.6666654611e-1f);
+    const float xz = x * z;
+    const float s = fmaf(xz, ps, x);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(z, pc, 4.166664568298827e-2f);
+    const float zz = z * z;
+    const float c = fmaf(zz, pc, fmaf(z, -0.5f, 1.0f));
+    const int quad = (int)(__double2ll_rn(q) & 3LL);
+    const bool swap = quad & 1;
+    float so = swap ? c : s;
+    float co = swap ? s : c;
+    so = (quad & 2) ? -so : so;               // quadrants 2,3 negate sin
+    co = ((quad + 1) & 2) ? -co : co;         // quadrants 1,2 negate cos
+    sn = so;
+    cs = co;
+}
+
+// ln(m * 2^-24), m integer in [1, 2^24], fp64 with explicit fma (Box-Muller radius).
+__device__ __forceinline__ double log_u24(uint32_t m) {
+    const double u = (double)m * (1.0 / 16777216.0);
+    unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+    int e = (int)((bits >> 52) & 0x7ffULL) - 1022;
+    bits = (bits & 0x000fffffffffffffULL) | 0x3fe0000000000000ULL;
+    double f = __longlong_as_double((long long)bits);
+    if (f < 0.70710678118654752440) {
+        f = f * 2.0;
+        e -= 1;
+    }
+    const double s = (f - 1.0) / (f + 1.0);
+    const double s2 = s * s;
+    double p = 1.0 / 19.0;
+    p = fma(p, s2, 1.0 / 17.0);
+    p = fma(p, s2, 1.0 / 15.0);
+    p = fma(p, s2, 1.0 / 13.0);
+    p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, 1.0 / 3.0);
+    p = fma(p, s2, 1.0);
+    const double lnf = 2.0 * s * p;
+    return fma((double)e, 0.69314718055994530942, lnf);
+}
+
+// Philox4x32-10, counter-based (Salmon et al. SC'11).
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float u24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+
+// two standard normals from two 32-bit words (Box-Muller on the canonical log / sincos)
+__device__ __forceinline__ void normal2(uint32_t r0, uint32_t r1, float& z0, float& z1) {
+    const double ln = log_u24((r0 >> 8) + 1u);
+    const double rad = sqrt(-2.0 * ln);
+    const float theta = 6.28318530717958647692f * u24(r1);
+    float sn, cs;
+    sincos_canon(theta, sn, cs);
+    z0 = (float)(rad * (double)cs);
+    z1 = (float)(rad * (double)sn);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference semantics, per agent.
+// ---------------------------------------------------------------------------------------------
+
+// torch.clamp propagates NaN (gym_flock_v2.py:327,331)
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
+    const float t = fminf(fmaxf(v, lo), hi);
+    return (v != v) ? v : t;
+}
+
+// torch.nan_to_num defaults (gym_flock_v2.py:346)
+__device__ __forceinline__ float nan_to_num(float v) {
+    const float t = fminf(fmaxf(v, -kFltMax), kFltMax);   // fmaxf(NaN, a) = a: fixed below
+    return (v != v) ? 0.0f : t;
+}
+
+// check_boundary per coordinate (gym_flock_v2.py:271-304)
+__device__ __forceinline__ float wrap_coord(float c, float B, int rigid) {
+    if (rigid) {
+        c = (c < B) ? c : B;
+        c = (c > 0.0f) ? c : 0.0f;
+    } else {
+        c = (c < B) ? c : 0.001f;
+        c = (c > 0.0f) ? c : B;
+    }
+    return c;
+}
+
+// _updateState + check_boundary for one agent. V: 0 v2 (gym_flock_v2.py:317-350), 1 uw
+// (gym_flock_uw.py:269-302, heading=False), 2 uwd (gym_flock_uw_discrete.py:324-366).
+// a0/a1: the agent's action (uwd: a0 = float-coded id); nzu/nzw: additive actuation noise.
+template <int V>
+__device__ __forceinline__ void integrate_agent(const Params& p, float a0, float a1, float nzu, float nzw,
+                                                float& x, float& y, float& h, float& vx, float& vy) {
+    const float dt = p.dt;
+    if (V == FLOCK_V2) {
+        const float w = clamp_nan(a1, -1.57079632679489661923f, 1.57079632679489661923f);
+        const float wd = w * dt;
+        h = h + wd;
+        const float u = clamp_nan(a0, 0.005f, p.vmax);
+        float sn, cs;
+        sincos_canon(h, sn, cs);
+        vx = u * cs;
+        vy = u * sn;
+    } else if (V == FLOCK_UW) {
+        float n2 = a0 * a0;
+        const float ay2 = a1 * a1;
+        n2 = n2 + ay2;
+        const float n = __fsqrt_rn(n2);
+        vx = __fdiv_rn(a0, n);
+        vy = __fdiv_rn(a1, n);
+    } else {
+        float a = (a0 == a0) ? a0 : 0.0f;                 // int(act) with a clamp to the dictionary
+        a = fminf(fmaxf(a, 0.0f), 9.0f);
+        const int id = (int)a;
+        const float mu_u = id < 5 ? 0.2f : 0.6f;
+        const int m = id < 5 ? id : id - 5;
+        const float mu_w = m == 0 ? -1.2f : m == 1 ? -0.5f : m == 2 ? 0.0f : m == 3 ? 0.5f : 1.2f;
+        float u = mu_u + nzu;
+        float w = mu_w + nzw;
+        w = clamp_nan(w, -0.025f, 0.025f);
+        const float wd = w * dt;
+        h = h + wd;
+        u = clamp_nan(u, 5e-6f, p.vmax);
+        float sn, cs;
+        sincos_canon(h, sn, cs);
+        vx = u * cs;
+        vy = u * sn;
+        float n2 = vx * vx;
+        const float vy2 = vy * vy;
+        n2 = n2 + vy2;
+        const float n = __fsqrt_rn(n2);
+        vx = __fdiv_rn(vx, n);
+        vy = __fdiv_rn(vy, n);
+    }
+    vx = nan_to_num(vx);
+    vy = nan_to_num(vy);
+    vx = vx * dt;
+    vy = vy * dt;
+    x = x + vx;
+    y = y + vy;
+    x = wrap_coord(x, p.B, p.rigid);
+    y = wrap_coord(y, p.B, p.rigid);
+}
+
+// Philox stream layout: key = seed; counter = (global env, agent, episode step, tag + 4*reset_epoch).
+// (episode step, reset_epoch) are per-env DEVICE counters, so the stream is unique over the env's
+// life, independent of the GPU count and safe to replay from a CUDA graph.
+__device__ __forceinline__ uint32_t stream_word(uint32_t tag, uint32_t reset_epoch) { return tag + (reset_epoch << 2); }
+
+// actuation noise of uwd (gym_flock_uw_discrete.py:333-334): 2 normals * std
+__device__ __forceinline__ void act_noise(const Params& p, int env_global, int agent, uint32_t step, uint32_t repoch,
+                                          float& nzu, float& nzw) {
+    const uint4 r = philox4x32_10((uint32_t)env_global, (uint32_t)agent, step, stream_word(kTagNoise, repoch),
+                                  p.seed_lo, p.seed_hi);
+    float z0, z1;
+    normal2(r.x, r.y, z0, z1);
+    nzu = p.noise_std * z0;
+    nzw = p.noise_std * z1;
+}
+
+// canonical random action of (env, agent, episode step): tag 2
+template <int V>
+__device__ __forceinline__ void random_action(const Params& p, int env_global, int agent, uint32_t step,
+                                              uint32_t repoch, float& a0, float& a1) {
+    const uint4 r = philox4x32_10((uint32_t)env_global, (uint32_t)agent, step, stream_word(kTagAction, repoch),
+                                  p.seed_lo, p.seed_hi);
+    if (V == FLOCK_V2) {
+        const float t0 = u24(r.x) * 3.0f, t1 = u24(r.y) * 3.0f;
+        a0 = t0 - 1.5f;
+        a1 = t1 - 1.5f;
+    } else if (V == FLOCK_UW) {
+        const float t0 = u24(r.x) * 2.0f, t1 = u24(r.y) * 2.0f;
+        a0 = t0 - 1.0f;
+        a1 = t1 - 1.0f;
+    } else {
+        a0 = (float)__umulhi(r.x, (uint32_t)p.k);
+        a1 = 0.0f;
+    }
+}
+
+// squared pair distance: min-image (gym_flock_v2.py:140-144) or Euclidean (v2:166-168).
+// For wrapped coordinates |dx| is in [0, B], where (dx > B/2 ? B - dx : dx) == fminf(dx, B - dx)
+// bit for bit (B/2 is exact).
+template <bool PER>
+__device__ __forceinline__ float pair_d2(float xi, float yi, float xj, float yj, float B) {
+    float dx = fabsf(xi - xj);
+    float dy = fabsf(yi - yj);
+    if (PER) {
+        dx = fminf(dx, B - dx);
+        dy = fminf(dy, B - dy);
+    }
+    const float a = dx * dx;
+    const float b = dy * dy;
+    return a + b;
+}
+
+// Per-row running k-smallest list, ascending by (d2, j). Candidates must be offered in
+// ascending j, so a strict `<` keeps the lower index on equal d2.
+template <int K>
+struct TopK {
+    float d[K];
+    int idx[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            d[s] = kInf;
+            idx[s] = -1;
+        }
+    }
+    // branch-free sorted insertion: values by a min/max network, indices by selects
+    __device__ __forceinline__ void insert(float c, int j) {
+#pragma unroll
+        for (int s = K - 1; s > 0; --s) {
+            const bool lt_prev = c < d[s - 1];
+            const bool lt_cur = c < d[s];
+            idx[s] = lt_prev ? idx[s - 1] : (lt_cur ? j : idx[s]);
+            d[s] = fminf(d[s], fmaxf(d[s - 1], c));
+        }
+        idx[0] = (c < d[0]) ? j : idx[0];
+        d[0] = fminf(d[0], c);
+    }
+    __device__ __forceinline__ float worst() const { return d[K - 1]; }
+};
+
+// sqrt + clamp(0, sensor_range) of the k winners (gym_flock_v2.py:151) and the collision flag
+// (gym_flock_v2.py:212-215, 314).
+template <int K>
+__device__ __forceinline__ bool finish_row(const TopK<K>& t, int k, float sensor_range, float cd, float* dist) {
+    bool coll = false;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        float d = __fsqrt_rn(t.d[s]);
+        d = fminf(fmaxf(d, 0.0f), sensor_range);
+        dist[s] = d;
+        coll = coll || (s < k && d < cd);
+    }
+    return coll;
+}
+
+// reward of one agent (v2: gym_flock_v2.py:217-220,268; uw: gym_flock_uw.py:186-221;
+// uwd: gym_flock_uw_discrete.py:234-276). prev_h is the value BEFORE this step's update.
+template <int V>
+__device__ __forceinline__ float agent_reward(const Params& p, bool coll, float x, float y, float h,
+                                              float prev_h, float comx, float comy, float hmean) {
+    if (V == FLOCK_V2) {
+        return coll ? -5.0f : 0.01f;
+    } else if (V == FLOCK_UW) {
+        const float pen = coll ? -5.0f : 0.01f;
+        const float ddx = x - comx, ddy = y - comy;
+        float q = ddx * ddx;
+        const float q2 = ddy * ddy;
+        q = q + q2;
+        const float dc = __fsqrt_rn(q);
+        const float rcom = dc < p.cd4 ? 0.01f : 0.0f;
+        const float diff = fabsf(prev_h - h);
+        const float rang = diff > 0.27f ? -0.01f : 0.001f;
+        float r = pen + rcom;
+        r = r + rang;
+        return r;
+    } else {
+        const float pen = coll ? -9.0f : 0.0f;
+        const float err = fabsf(hmean - h);
+        const float ral = err > 0.20f ? 0.0f : 0.1f;
+        return pen + ral;
+    }
+}
+
+// reward in 2^-32 fixed point (order-free integer accumulation of episode returns)
+__device__ __forceinline__ long long reward_fx(float r) { return __double2ll_rn((double)r * 4294967296.0); }
+
+}  // namespace flock

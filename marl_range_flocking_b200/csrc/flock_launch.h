@@ -1,0 +1,22 @@
+// flock_launch.h -- host-side launch entry points of the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace flock {
+struct Params;
+
+// flock_small.cu (N <= 32)
+cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool multi, int sm_count, cudaStream_t s);
+cudaError_t launch_reset_small(const Params& p, int sm_count, cudaStream_t s);
+cudaError_t launch_random_actions(int variant, const Params& p, float* out, int sm_count, cudaStream_t s);
+cudaError_t launch_debug_sincos(const float* h, int n, float* sn, float* cs, cudaStream_t s);
+cudaError_t launch_debug_normal2(const uint32_t* w, int n, float* z, cudaStream_t s);
+cudaError_t launch_debug_philox(const uint32_t* ck, int n, uint32_t* out, cudaStream_t s);
+
+// flock_tiled.cu (N > 32)
+cudaError_t tiled_configure(int num_agents);   // opt in to the dynamic shared memory the env needs
+size_t tiled_smem_bytes(int num_agents);
+cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, cudaStream_t s);
+cudaError_t launch_reset_tiled(const Params& p, cudaStream_t s);
+}  // namespace flock

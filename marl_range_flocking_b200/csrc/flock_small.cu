@@ -1,0 +1,467 @@
+// flock_small.cu -- warp-per-env-group kernels for small swarms (N <= 32).
+//
+// Mapping: lane = agent; a warp owns G = floor(32 / N) consecutive envs (N = 10 -> 3 envs, 30
+// live lanes; N = 16 -> 2; N = 32 -> 1), so the warp's slice of every SoA array is one contiguous
+// run of G*N floats -> fully coalesced loads/stores. New positions are staged in shared memory
+// and the all-pairs loop reads them back as broadcast float4 (4 neighbours per LDS.128 pair);
+// the per-row k-smallest list lives in registers. One launch = one env step
+// (integrate -> wrap -> all-pairs range -> k-NN -> collisions/dones -> reward -> obs).
+#include "flock_device.cuh"
+#include "flock_launch.h"
+
+namespace flock {
+
+constexpr int kSmallThreads = 128;
+constexpr int kSmallWarps = kSmallThreads / kWarp;
+constexpr int kSlots = 64;  // floats per staged array per warp: G * roundup(N,4) <= 64
+
+struct LaneMap {
+    int g, a;
+    bool lane_ok;
+    unsigned gmask;
+};
+
+__device__ __forceinline__ LaneMap lane_map(int lane, int N, int G) {
+    LaneMap m;
+    m.lane_ok = lane < G * N;
+    m.g = m.lane_ok ? lane / N : 0;
+    m.a = m.lane_ok ? lane - m.g * N : 0;
+    const unsigned ones = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+    m.gmask = m.lane_ok ? (ones << (m.g * N)) : (1u << lane);
+    return m;
+}
+
+// vectorised row store: n 4-byte values per agent, rows contiguous in memory (dst = base + row*n)
+template <typename T, int MAXN>
+__device__ __forceinline__ void store_row(T* dst, const T (&v)[MAXN], int n) {
+    static_assert(sizeof(T) == 4, "4-byte elements");
+    struct alignas(16) Vec4 { T a, b, c, d; };
+    if constexpr (MAXN >= 8) {
+        if (n == 8) {
+            reinterpret_cast<Vec4*>(dst)[0] = Vec4{v[0], v[1], v[2], v[3]};
+            reinterpret_cast<Vec4*>(dst)[1] = Vec4{v[4], v[5], v[6], v[7]};
+            return;
+        }
+    }
+    if constexpr (MAXN >= 4) {
+        if (n == 4) {
+            reinterpret_cast<Vec4*>(dst)[0] = Vec4{v[0], v[1], v[2], v[3]};
+            return;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < MAXN; ++s)
+        if (s < n) dst[s] = v[s];
+}
+
+// obs row(s) of one agent. H == 1: obs[idx][k]. H == 4 (uw): shift the window by one slot and put
+// the new ranges first (gym_flock_uw.py:120-123); `fresh` = window is all zeros (reset).
+template <int K>
+__device__ __forceinline__ void write_obs(const Params& p, size_t idx, const float (&dist)[K], bool fresh) {
+    const int k = p.k;
+    if (p.H == 1) {
+        store_row<float, K>(p.obs + idx * k, dist, k);
+        return;
+    }
+    float* o = p.obs + idx * (size_t)(p.H * k);
+    const int keep = (p.H - 1) * k;
+    if (k == 3 && p.H == 4) {  // 12 floats = 3 x float4, the reference's configuration
+        float4* o4 = reinterpret_cast<float4*>(o);
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+        if (!fresh) {
+            r0 = o4[0];
+            r1 = o4[1];
+            r2 = o4[2];
+        }
+        o4[0] = make_float4(dist[0], dist[1], dist[2 % K], r0.x);
+        o4[1] = make_float4(r0.y, r0.z, r0.w, r1.x);
+        o4[2] = make_float4(r1.y, r1.z, r1.w, r2.x);
+        return;
+    }
+    for (int t = keep - 1; t >= 0; --t) o[t + k] = fresh ? 0.0f : o[t];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+        if (s < k) o[s] = dist[s];
+}
+
+// sum of the episode-return increments of one env group (integer, order free) via REDUX
+__device__ __forceinline__ long long group_sum_fx(unsigned gmask, long long fx) {
+    const unsigned lo = (unsigned)fx & 0xffffu;
+    const unsigned mid = (unsigned)(fx >> 16) & 0xffffu;
+    const int hi = (int)(fx >> 32);
+    const unsigned slo = __reduce_add_sync(gmask, lo);
+    const unsigned smid = __reduce_add_sync(gmask, mid);
+    const int shi = __reduce_add_sync(gmask, hi);
+    return ((long long)shi << 32) + ((long long)smid << 16) + (long long)slo;
+}
+
+// all-pairs range + k-NN of row `a` against the staged positions of its env group
+template <int K, bool PER>
+__device__ __forceinline__ void knn_small(const float* sxg, const float* syg, int a, int sstride, float x, float y,
+                                          float B, TopK<K>& t) {
+    t.init();
+    const float4* px = reinterpret_cast<const float4*>(sxg);
+    const float4* py = reinterpret_cast<const float4*>(syg);
+    const int n4 = sstride >> 2;
+    for (int j4 = 0; j4 < n4; ++j4) {
+        const float4 X = px[j4];
+        const float4 Y = py[j4];
+        const int j = j4 << 2;
+        float d;
+        d = pair_d2<PER>(x, y, X.x, Y.x, B); d = (j == a) ? kInf : d; t.insert(d, j);
+        d = pair_d2<PER>(x, y, X.y, Y.y, B); d = (j + 1 == a) ? kInf : d; t.insert(d, j + 1);
+        d = pair_d2<PER>(x, y, X.z, Y.z, B); d = (j + 2 == a) ? kInf : d; t.insert(d, j + 2);
+        d = pair_d2<PER>(x, y, X.w, Y.w, B); d = (j + 3 == a) ? kInf : d; t.insert(d, j + 3);
+    }
+}
+
+// stage one value per lane plus +inf / 0 padding up to the group stride
+__device__ __forceinline__ void stage_xy(float* sx, float* sy, const LaneMap& m, int N, int sstride, bool live,
+                                         float x, float y) {
+    if (m.lane_ok) {
+        sx[m.g * sstride + m.a] = live ? x : kInf;
+        sy[m.g * sstride + m.a] = live ? y : 0.0f;
+        if (m.a < sstride - N) {
+            sx[m.g * sstride + N + m.a] = kInf;
+            sy[m.g * sstride + N + m.a] = 0.0f;
+        }
+    }
+}
+
+// sequential float32 sum over the env's agents (canonical order 0..N-1)
+__device__ __forceinline__ float seq_sum(const float* s, int N) {
+    float acc = 0.0f;
+    for (int j = 0; j < N; ++j) acc = acc + s[j];
+    return acc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// step: MultiAgentEnv.step of the three variants (gym_flock_v2.py:71-83, gym_flock_uw.py:69-81,
+// gym_flock_uw_discrete.py:110-122). NSTEPS > 1 (flock_step_n) keeps the state in registers and
+// draws the canonical random actions in-kernel.
+// -------------------------------------------------------------------------------------------------
+template <int V, int K, bool PER, bool MULTI>
+__global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const __grid_constant__ Params p) {
+    __shared__ __align__(16) float s_stage[kSmallWarps][3][kSlots];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* sx = s_stage[wib][0];
+    float* sy = s_stage[wib][1];
+    float* sh = s_stage[wib][2];
+    const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
+    const LaneMap m = lane_map(lane, N, G);
+    const int num_tasks = (p.E + G - 1) / G;
+    const int warps_total = gridDim.x * kSmallWarps;
+    const int nsteps = MULTI ? p.num_steps : 1;
+
+    for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
+        const int env = task * G + m.g;
+        const bool live = m.lane_ok && env < p.E;
+        const size_t idx = (size_t)(live ? env : 0) * N + m.a;
+        float x = 0.f, y = 0.f, h = 0.f, prev_h = 0.f;
+        float prev_h_in = 0.f;
+        uint32_t ep0 = 0u, repoch = 0u;   // per-env Philox epoch (episode step, reset epoch)
+        if (live) {
+            if (MULTI || V == FLOCK_UWD) {
+                ep0 = (uint32_t)p.ep_len[env];
+                repoch = p.reset_epoch[env];
+            }
+            x = p.x[idx];
+            y = p.y[idx];
+            h = p.h[idx];
+            if (V == FLOCK_UW) prev_h = prev_h_in = p.prev_h[idx];
+        }
+        float vx = 0.f, vy = 0.f, rew = 0.f;
+        float dist[K];
+        TopK<K> t;
+        bool coll = false, env_coll = false;
+        long long ret_fx = 0;
+        float hist[(V == FLOCK_UW) ? 3 * K : 1];
+        if (MULTI && V == FLOCK_UW && live) {
+            const float* o = p.obs + idx * (size_t)(4 * k);
+#pragma unroll
+            for (int s = 0; s < 3 * K; ++s) hist[s] = (s % K < k) ? o[(s / K) * k + (s % K)] : 0.0f;
+        }
+
+        for (int st = 0; st < nsteps; ++st) {
+            float a0 = 0.f, a1 = 0.f, nzu = 0.f, nzw = 0.f;
+            if (live) {
+                const uint32_t step = ep0 + (uint32_t)st;
+                if (MULTI) {
+                    random_action<V>(p, p.env_offset + env, m.a, step, repoch, a0, a1);
+                } else if (V == FLOCK_UWD) {
+                    a0 = p.actions[idx];
+                } else {
+                    const float2 act = reinterpret_cast<const float2*>(p.actions)[idx];
+                    a0 = act.x;
+                    a1 = act.y;
+                }
+                if (V == FLOCK_UWD) {
+                    if (!MULTI && p.noise != nullptr) {
+                        const float2 nz = reinterpret_cast<const float2*>(p.noise)[idx];
+                        nzu = nz.x;
+                        nzw = nz.y;
+                    } else if (p.noise_std > 0.0f) {
+                        act_noise(p, p.env_offset + env, m.a, step, repoch, nzu, nzw);
+                    }
+                }
+                integrate_agent<V>(p, a0, a1, nzu, nzw, x, y, h, vx, vy);
+            }
+            __syncwarp();
+            stage_xy(sx, sy, m, N, sstride, live, x, y);
+            if (V == FLOCK_UWD && m.lane_ok) sh[m.g * sstride + m.a] = h;
+            __syncwarp();
+            if (live) {
+                const float* sxg = sx + m.g * sstride;
+                const float* syg = sy + m.g * sstride;
+                float comx = 0.f, comy = 0.f, hmean = 0.f;
+                if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
+                    comx = __fdiv_rn(seq_sum(sxg, N), (float)N);
+                    comy = __fdiv_rn(seq_sum(syg, N), (float)N);
+                }
+                if (V == FLOCK_UWD) hmean = __fdiv_rn(seq_sum(sh + m.g * sstride, N), (float)N);  // uwd:256
+                knn_small<K, PER>(sxg, syg, m.a, sstride, x, y, p.B, t);
+                coll = finish_row<K>(t, k, p.sensor_range, p.cd, dist);
+                rew = agent_reward<V>(p, coll, x, y, h, prev_h, comx, comy, hmean);
+                if (V == FLOCK_UW) prev_h = h;
+                env_coll = (__ballot_sync(m.gmask, coll) & m.gmask) != 0u;
+                ret_fx += group_sum_fx(m.gmask, reward_fx(rew));
+                if (MULTI && V == FLOCK_UW && st + 1 < nsteps) {
+#pragma unroll
+                    for (int s = 3 * K - 1; s >= K; --s) hist[s] = hist[s - K];   // K-strided copy of the window
+#pragma unroll
+                    for (int s = 0; s < K; ++s) hist[s] = dist[s];
+                }
+            }
+        }
+
+        if (live) {
+            p.xo[idx] = x;
+            p.yo[idx] = y;
+            if (V != FLOCK_UW) p.ho[idx] = h;
+            if (V == FLOCK_UW && !(prev_h == prev_h_in)) p.prev_h[idx] = prev_h;   // constant after the first step
+            if (p.vx != nullptr) {
+                p.vx[idx] = vx;
+                p.vy[idx] = vy;
+            }
+            if (MULTI && V == FLOCK_UW && nsteps > 1) {
+                // window after nsteps: newest first = dist, then the K-strided register history
+                float* o = p.obs + idx * (size_t)(4 * k);
+                for (int s = 0; s < k; ++s) o[s] = dist[s];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int s = 0; s < K; ++s)
+                        if (s < k) o[(r + 1) * k + s] = hist[r * K + s];
+            } else {
+                write_obs<K>(p, idx, dist, false);
+            }
+            if (p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
+            p.reward[idx] = rew;
+            p.agent_done[idx] = coll ? 1 : 0;
+            if (m.a == 0) {
+                p.env_done[env] = env_coll ? 1 : 0;
+                if (p.ep_return_fx != nullptr) p.ep_return_fx[env] += ret_fx;
+                p.ep_len[env] += nsteps;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// reset: MultiAgentEnv.reset (gym_flock_v2.py:85-108, gym_flock_uw.py:83-111,
+// gym_flock_uw_discrete.py:124-156) with a BOUNDED rejection loop, masked and batched.
+// -------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const __grid_constant__ Params p) {
+    __shared__ __align__(16) float s_stage[kSmallWarps][2][kSlots];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* sx = s_stage[wib][0];
+    float* sy = s_stage[wib][1];
+    const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
+    const LaneMap m = lane_map(lane, N, G);
+    const int num_tasks = (p.E + G - 1) / G;
+    const int warps_total = gridDim.x * kSmallWarps;
+    const size_t EN = (size_t)p.E * N;
+
+    for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
+        const int env = task * G + m.g;
+        bool live = m.lane_ok && env < p.E;
+        if (live && p.env_mask != nullptr) live = p.env_mask[env] != 0;
+        const size_t idx = (size_t)(live ? env : 0) * N + m.a;
+        float x = 0.f, y = 0.f, h = 0.f;
+        uint32_t epoch = live ? p.reset_epoch[env] : 0u;
+        uint32_t attempts = 0;
+        bool need = live;       // group still needs a (re)draw
+        bool coll = false, env_coll = false;
+        float dist[K];
+        TopK<K> t;
+        const int max_att = p.init_state != nullptr ? 1 : p.max_attempts;
+        while (__any_sync(0xffffffffu, need)) {
+            if (need) {
+                if (p.init_state != nullptr) {
+                    x = p.init_state[idx];
+                    y = p.init_state[EN + idx];
+                    h = p.init_state[2 * EN + idx];
+                } else {
+                        const uint4 r = philox4x32_10((uint32_t)(p.env_offset + env), (uint32_t)m.a, epoch + attempts,
+                                                  kTagReset, p.seed_lo, p.seed_hi);
+                    const float span = p.range_lo - p.reset_hi;      // (r0 - r1) * U + r1, gym_flock_v2.py:87-89
+                    const float tx = span * u24(r.x);
+                    x = tx + p.reset_hi;
+                    const float ty = span * u24(r.y);
+                    y = ty + p.reset_hi;
+                    const float th = (0.0f - p.heading_hi) * u24(r.z);  // gym_flock_v2.py:96
+                    h = th + p.heading_hi;
+                }
+                x = wrap_coord(x, p.B, p.rigid);                      // check_boundary, v2:99
+                y = wrap_coord(y, p.B, p.rigid);
+                attempts += 1;
+            }
+            __syncwarp();
+            stage_xy(sx, sy, m, N, sstride, live, x, y);
+            __syncwarp();
+            if (need) {   // whole group shares `need`
+                knn_small<K, false>(sx + m.g * sstride, sy + m.g * sstride, m.a, sstride, x, y, p.B, t);  // Euclidean, v2:100
+                coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
+                env_coll = (__ballot_sync(m.gmask, coll) & m.gmask) != 0u;
+                need = env_coll && (int)attempts < max_att;
+            }
+        }
+        if (live) {
+            p.xo[idx] = x;
+            p.yo[idx] = y;
+            p.ho[idx] = h;
+            p.prev_h[idx] = 0.0f;                                     // v2:95
+            if (p.vx != nullptr) {
+                p.vx[idx] = 0.0f;                                     // v2:94
+                p.vy[idx] = 0.0f;
+            }
+            write_obs<K>(p, idx, dist, true);
+            if (p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
+            const bool keep = (p.reset_flags & FLOCK_RESET_KEEP_OUTPUTS) != 0;
+            if (!keep) {
+                p.reward[idx] = 0.0f;
+                p.agent_done[idx] = coll ? 1 : 0;
+            }
+            if (m.a == 0) {
+                if (!keep) p.env_done[env] = env_coll ? 1 : 0;
+                if (p.init_state == nullptr) p.reset_epoch[env] = epoch + attempts;
+                const int len = p.ep_len[env];
+                if (p.stats != nullptr) {
+                    if (len > 0) {
+                        atomicAdd(&p.stats[FLOCK_STAT_EPISODES], 1ULL);
+                        atomicAdd(&p.stats[FLOCK_STAT_EP_STEPS], (unsigned long long)len);
+                        if (p.ep_return_fx != nullptr)
+                            atomicAdd(&p.stats[FLOCK_STAT_EP_RETURN_FX], (unsigned long long)p.ep_return_fx[env]);
+                    }
+                    if (p.init_state == nullptr) {
+                        atomicAdd(&p.stats[FLOCK_STAT_RESET_ATTEMPTS], (unsigned long long)attempts);
+                        if (env_coll) atomicAdd(&p.stats[FLOCK_STAT_RESET_GAVE_UP], 1ULL);
+                    }
+                }
+                p.ep_len[env] = 0;
+                if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = 0;
+            }
+        }
+    }
+}
+
+// canonical random actions into a buffer (flock_random_actions)
+template <int V>
+__global__ void flock_random_actions_kernel(const __grid_constant__ Params p, float* out) {
+    const size_t n = (size_t)p.E * p.N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int env = (int)(i / p.N), a = (int)(i - (size_t)env * p.N);
+        float a0, a1;
+        random_action<V>(p, p.env_offset + env, a, (uint32_t)p.ep_len[env] + p.step_offset, p.reset_epoch[env], a0, a1);
+        if (V == FLOCK_UWD) out[i] = a0;
+        else reinterpret_cast<float2*>(out)[i] = make_float2(a0, a1);
+    }
+}
+
+__global__ void flock_debug_sincos_kernel(const float* h, int n, float* sn, float* cs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sincos_canon(h[i], sn[i], cs[i]);
+}
+__global__ void flock_debug_normal2_kernel(const uint32_t* w, int n, float* z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) normal2(w[2 * i], w[2 * i + 1], z[2 * i], z[2 * i + 1]);
+}
+__global__ void flock_debug_philox_kernel(const uint32_t* ck, int n, uint32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint4 r = philox4x32_10(ck[6 * i], ck[6 * i + 1], ck[6 * i + 2], ck[6 * i + 3], ck[6 * i + 4], ck[6 * i + 5]);
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side dispatch
+// -------------------------------------------------------------------------------------------------
+static int small_grid(const Params& p, int sm_count) {
+    const int tasks = (p.E + p.G - 1) / p.G;
+    const int blocks = (tasks + kSmallWarps - 1) / kSmallWarps;
+    const int cap = sm_count * 16;     // 16 resident 128-thread CTAs per SM
+    return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+}
+
+template <int V, int K, bool PER>
+static cudaError_t launch_step_small_vkp(const Params& p, bool multi, int sm_count, cudaStream_t s) {
+    const int grid = small_grid(p, sm_count);
+    if (multi) flock_step_small_kernel<V, K, PER, true><<<grid, kSmallThreads, 0, s>>>(p);
+    else flock_step_small_kernel<V, K, PER, false><<<grid, kSmallThreads, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int V, bool PER>
+static cudaError_t launch_step_small_vp(const Params& p, bool multi, int sm_count, cudaStream_t s) {
+    if (p.k <= 3) return launch_step_small_vkp<V, 3, PER>(p, multi, sm_count, s);
+    if (p.k == 4) return launch_step_small_vkp<V, 4, PER>(p, multi, sm_count, s);
+    return launch_step_small_vkp<V, 8, PER>(p, multi, sm_count, s);
+}
+
+cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool multi, int sm_count, cudaStream_t s) {
+    switch (variant) {
+        case FLOCK_V2:
+            return periodic ? launch_step_small_vp<FLOCK_V2, true>(p, multi, sm_count, s)
+                            : launch_step_small_vp<FLOCK_V2, false>(p, multi, sm_count, s);
+        case FLOCK_UW:
+            return launch_step_small_vp<FLOCK_UW, false>(p, multi, sm_count, s);
+        default:
+            return launch_step_small_vp<FLOCK_UWD, false>(p, multi, sm_count, s);
+    }
+}
+
+cudaError_t launch_reset_small(const Params& p, int sm_count, cudaStream_t s) {
+    const int grid = small_grid(p, sm_count);
+    if (p.k <= 3) flock_reset_small_kernel<3><<<grid, kSmallThreads, 0, s>>>(p);
+    else if (p.k == 4) flock_reset_small_kernel<4><<<grid, kSmallThreads, 0, s>>>(p);
+    else flock_reset_small_kernel<8><<<grid, kSmallThreads, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_random_actions(int variant, const Params& p, float* out, int sm_count, cudaStream_t s) {
+    const size_t n = (size_t)p.E * p.N;
+    int grid = (int)((n + 255) / 256);
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    if (grid < 1) grid = 1;
+    if (variant == FLOCK_V2) flock_random_actions_kernel<FLOCK_V2><<<grid, 256, 0, s>>>(p, out);
+    else if (variant == FLOCK_UW) flock_random_actions_kernel<FLOCK_UW><<<grid, 256, 0, s>>>(p, out);
+    else flock_random_actions_kernel<FLOCK_UWD><<<grid, 256, 0, s>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_debug_sincos(const float* h, int n, float* sn, float* cs, cudaStream_t s) {
+    flock_debug_sincos_kernel<<<(n + 255) / 256, 256, 0, s>>>(h, n, sn, cs);
+    return cudaGetLastError();
+}
+cudaError_t launch_debug_normal2(const uint32_t* w, int n, float* z, cudaStream_t s) {
+    flock_debug_normal2_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, n, z);
+    return cudaGetLastError();
+}
+cudaError_t launch_debug_philox(const uint32_t* ck, int n, uint32_t* out, cudaStream_t s) {
+    flock_debug_philox_kernel<<<(n + 255) / 256, 256, 0, s>>>(ck, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace flock

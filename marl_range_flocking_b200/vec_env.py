@@ -1,0 +1,329 @@
+"""Device-resident batched flocking environment (`VecEnv`).
+
+E independent instances of the reference's `MultiAgentEnv` (environments/gym_flock_v2.py,
+gym_flock_uw.py, gym_flock_uw_discrete.py) live in HBM as float32 structure-of-arrays `[E][N]`
+tensors owned by torch; every `step()` is ONE fused sm_100a kernel launched through the C ABI of
+libflock_b200.so (include/flock_b200.h). No host synchronisation happens in `reset`/`step`:
+`env_done` (the reference's python bool `dones[1]`, gym_flock_v2.py:315) stays on the device.
+
+PyTorch is used for device memory, streams and (in `dist.py`) NCCL plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FlockBuffers, FlockCfg, VARIANT_IDS, check
+
+# reference per-variant constants
+_HEADING_HI = {"v2": math.pi * 1.5, "uw": math.pi * 2, "uwd": math.pi / 1.2}   # v2:96, uw:92, uwd:133
+_OBS_HIST = {"v2": 1, "uw": 4, "uwd": 1}                                         # uw: memory_size, :59
+
+
+def _f32(v: float) -> float:
+    return float(torch.tensor(v, dtype=torch.float32).item())
+
+
+class VecEnv:
+    """Batched, device-resident version of the reference `MultiAgentEnv`.
+
+    Constructor arguments up to `desired_distance` mirror `MultiAgentEnv.__init__`
+    (gym_flock_v2.py:21-32; `normalize_distance` / `desired_distance` are accepted and ignored
+    exactly as the reference's live code path ignores them). Keyword-only arguments
+    are the batched extensions.
+    """
+
+    def __init__(self, variant: str, num_envs: int, agents: int, k: int = 4, collision_distance: float = 3,
+                 normalize_distance: bool = False, rigid_boundary: bool = False, range_start=(0, 100),
+                 sensor_range: float = 7, max_linear_velocity: float = 2.5, desired_distance: float = 15, *,
+                 device=None, seed: int = 0, env_offset: int = 0, auto_reset: bool = False,
+                 max_reset_attempts: int = 64, reset_collision_distance: Optional[float] = None,
+                 act_noise_std: Optional[float] = None, periodic: Optional[bool] = None,
+                 track_velocities: bool = True, track_neighbors: bool = True):
+        if variant not in VARIANT_IDS:
+            raise ValueError(f"variant must be one of {sorted(VARIANT_IDS)}, got {variant!r}")
+        if normalize_distance:
+            raise NotImplementedError("normalize_distance=True is never enabled by the reference (make_env passes "
+                                      "False, gym_flock_v2.py:424) and is not implemented")
+        self.lib = _lib.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("marl_range_flocking_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"VecEnv lives on a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.variant = variant
+        self.num_envs, self.num_particles, self.k = int(num_envs), int(agents), int(k)
+        self.rigid_boundary = bool(rigid_boundary)
+        self.range_start = tuple(range_start)
+        self.boundary = range_start[1]
+        self.sensor_range = sensor_range
+        self.max_linear_velocity = max_linear_velocity
+        self.collision_distance = collision_distance
+        self.desired_distance = desired_distance
+        self.memory_size = 4
+        self.obs_hist = _OBS_HIST[variant]
+        self.auto_reset = bool(auto_reset)
+        self.max_reset_attempts = int(max_reset_attempts)
+        r0, r1 = range_start
+        reset_hi = (r1 // 2) if variant == "uw" else r1                       # gym_flock_uw.py:87-89
+        if reset_collision_distance is None:
+            reset_collision_distance = 4.0 if variant == "uwd" else collision_distance   # uwd:145
+        if act_noise_std is None:
+            act_noise_std = 0.1 if variant == "uwd" else 0.0                  # uwd:333-334
+        if periodic is None:
+            periodic = variant == "v2"                                        # gym_flock_v2.py:76
+        self.cfg = FlockCfg(VARIANT_IDS[variant], self.num_envs, self.num_particles, self.k,
+                            int(self.rigid_boundary), int(bool(periodic)), self.obs_hist, int(env_offset),
+                            float(r1), float(r0), float(reset_hi), _f32(_HEADING_HI[variant]), float(sensor_range),
+                            float(collision_distance), float(reset_collision_distance), float(max_linear_velocity),
+                            float(act_noise_std), 0.0, int(seed) & 0xFFFFFFFFFFFFFFFF)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.flock_create(ctypes.byref(self.cfg), self.device.index, ctypes.byref(handle)))
+        self._h = handle
+        self.tiled = self.lib.flock_path(self._h) == 1
+        E, N, H = self.num_envs, self.num_particles, self.obs_hist
+        f32 = dict(dtype=torch.float32, device=self.device)
+        z = lambda *shape, **kw: torch.zeros(*shape, **{**f32, **kw})
+        self._x = [z(E, N)] + ([z(E, N)] if self.tiled else [])
+        self._y = [z(E, N)] + ([z(E, N)] if self.tiled else [])
+        self._hd = [z(E, N)] + ([z(E, N)] if self.tiled else [])
+        self._prev_h = z(E, N)
+        self._vx = z(E, N) if track_velocities else None
+        self._vy = z(E, N) if track_velocities else None
+        self._obs = z(E, N, H, self.k)
+        self._nn = z(E, N, self.k, dtype=torch.int32) if track_neighbors else None
+        self._reward = z(E, N, 1)
+        self._agent_done = z(E, N, dtype=torch.bool)
+        self._env_done = z(E, dtype=torch.bool)
+        self._reset_epoch = z(E, dtype=torch.int32)          # uint32 counter, int32 storage
+        self._ep_return_fx = z(E, dtype=torch.int64)
+        self._ep_len = z(E, dtype=torch.int32)
+        self._stats = z(8, dtype=torch.int64)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        bufs = FlockBuffers(
+            ptr(self._x[0]), ptr(self._y[0]), ptr(self._hd[0]),
+            ptr(self._x[1]) if self.tiled else None, ptr(self._y[1]) if self.tiled else None,
+            ptr(self._hd[1]) if self.tiled else None,
+            ptr(self._prev_h), ptr(self._vx), ptr(self._vy), ptr(self._obs), ptr(self._nn), ptr(self._reward),
+            ptr(self._agent_done), ptr(self._env_done), ptr(self._reset_epoch), ptr(self._ep_return_fx),
+            ptr(self._ep_len), ptr(self._stats))
+        check(self.lib.flock_bind(self._h, ctypes.byref(bufs)))
+        self._host = None   # pinned host mirrors for step_host
+
+    # ------------------------------------------------------------------------------------------
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self.lib.flock_destroy(h)
+            except Exception:
+                pass
+
+    def close(self):
+        self.__del__()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _slot(self) -> int:
+        return self.lib.flock_state_slot(self._h) if self.tiled else 0
+
+    def _dev_guard(self):
+        return torch.cuda.device(self.device)
+
+    def _as_input(self, t, shape, name) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        t = t.to(device=self.device, dtype=torch.float32)
+        if t.numel() != math.prod(shape):
+            raise ValueError(f"{name} has {t.numel()} elements, expected shape {tuple(shape)}")
+        return t.reshape(shape).contiguous()
+
+    # ---- views of the device state (zero copy; overwritten by the next step) ------------------
+    @property
+    def x(self) -> torch.Tensor:
+        return self._x[self._slot()]
+
+    @property
+    def y(self) -> torch.Tensor:
+        return self._y[self._slot()]
+
+    @property
+    def headings(self) -> torch.Tensor:
+        return self._hd[self._slot()]
+
+    @property
+    def positions(self) -> torch.Tensor:
+        """(E, N, 2), the reference's `positions` layout (a stacked copy of the SoA state)."""
+        return torch.stack((self.x, self.y), dim=-1)
+
+    @property
+    def velocities(self) -> torch.Tensor:
+        """(E, N, 2) displacement of the last step = reference `velocities` (gym_flock_v2.py:349)."""
+        if self._vx is None:
+            raise RuntimeError("VecEnv was built with track_velocities=False")
+        return torch.stack((self._vx, self._vy), dim=-1)
+
+    @property
+    def prev_headings(self) -> torch.Tensor:
+        if self.variant == "uwd":   # uwd copies headings every step (gym_flock_uw_discrete.py:249-252)
+            return torch.where(self._ep_len[:, None] > 0, self.headings, self._prev_h)
+        return self._prev_h
+
+    @property
+    def nearest_neighbors(self) -> torch.Tensor:
+        if self._nn is None:
+            raise RuntimeError("VecEnv was built with track_neighbors=False")
+        return self._nn
+
+    @property
+    def distances_to_nearest_neighbors(self) -> torch.Tensor:
+        return self._obs[:, :, 0, :]
+
+    @property
+    def collisions(self) -> torch.Tensor:
+        """(E, N, k) int64 0/1, `_computeCollisions` (gym_flock_v2.py:212-215)."""
+        return (self.distances_to_nearest_neighbors < self.collision_distance).long()
+
+    @property
+    def observation(self) -> torch.Tensor:
+        """(E, N, k) for v2 / uwd, (E, N, 4, k) newest first for uw."""
+        return self._obs if self.obs_hist > 1 else self._obs[:, :, 0, :]
+
+    @property
+    def reward(self) -> torch.Tensor:
+        return self._reward
+
+    @property
+    def dones(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._agent_done, self._env_done
+
+    @property
+    def step_index(self) -> int:
+        return int(self.lib.flock_get_step_index(self._h))
+
+    @step_index.setter
+    def step_index(self, v: int):
+        check(self.lib.flock_set_step_index(self._h, int(v) & 0xFFFFFFFF))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.flock_launch_count(self._h))
+
+    # ---- the environment API -----------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None, init_state: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Batched `reset()`. `mask`: (E,) bool, only those envs; `init_state`: (3, E, N) x/y/heading
+        to install instead of drawing (parity injection)."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device).reshape(self.num_envs)
+            m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+            m = m.contiguous()
+        ini = None if init_state is None else self._as_input(init_state, (3, self.num_envs, self.num_particles), "init_state")
+        with self._dev_guard():
+            check(self.lib.flock_reset(self._h, None if m is None else m.data_ptr(),
+                                       None if ini is None else ini.data_ptr(), self.max_reset_attempts, 0,
+                                       self._stream()))
+        return self.observation
+
+    def step(self, actions, dt: float = 0.1, noise=None):
+        """Batched `step(action, dt)`: actions (E, N, 2) [v2, uw] or (E, N) float ids [uwd].
+
+        Returns `(obs, reward (E,N,1), (agent_done (E,N) bool, env_done (E,) bool), {})`; all are
+        views of env-owned device tensors."""
+        E, N = self.num_envs, self.num_particles
+        a = self._as_input(actions, (E, N) if self.variant == "uwd" else (E, N, 2), "actions")
+        nz = None if noise is None else self._as_input(noise, (E, N, 2), "noise")
+        with self._dev_guard():
+            check(self.lib.flock_step(self._h, a.data_ptr(), float(dt), None if nz is None else nz.data_ptr(),
+                                      self._stream()))
+            info: Dict = {}
+            if self.auto_reset:
+                # finished envs restart in place; reward / dones of the finishing step are kept and
+                # the returned obs of those envs is the first observation of the new episode
+                check(self.lib.flock_reset(self._h, self._env_done.data_ptr(), None, self.max_reset_attempts,
+                                           _lib.FLOCK_RESET_KEEP_OUTPUTS, self._stream()))
+        return self.observation, self._reward, (self._agent_done, self._env_done), info
+
+    def step_n(self, num_steps: int, dt: float = 0.1):
+        """`num_steps` steps with the canonical in-kernel random actions (one persistent launch when N <= 32)."""
+        with self._dev_guard():
+            check(self.lib.flock_step_n(self._h, int(num_steps), float(dt), self._stream()))
+        return self.observation, self._reward, (self._agent_done, self._env_done), {}
+
+    def random_actions(self, step_offset: int = 0) -> torch.Tensor:
+        """The canonical random actions `step_n` would apply `step_offset` steps from now."""
+        E, N = self.num_envs, self.num_particles
+        out = torch.empty((E, N) if self.variant == "uwd" else (E, N, 2), dtype=torch.float32, device=self.device)
+        with self._dev_guard():
+            check(self.lib.flock_random_actions(self._h, int(step_offset) & 0xFFFFFFFF, out.data_ptr(), self._stream()))
+        return out
+
+    def step_host(self, actions_cpu: torch.Tensor, dt: float = 0.1, noise_cpu: Optional[torch.Tensor] = None):
+        """End-to-end host form: host actions in, host obs / reward / dones out (pinned mirrors are
+        reused between calls). The call synchronises the stream."""
+        E, N = self.num_envs, self.num_particles
+        if self._host is None:
+            pin = dict(pin_memory=True)
+            self._host = dict(
+                obs=torch.empty(self._obs.shape, dtype=torch.float32, **pin),
+                reward=torch.empty((E, N, 1), dtype=torch.float32, **pin),
+                agent_done=torch.empty((E, N), dtype=torch.bool, **pin),
+                env_done=torch.empty((E,), dtype=torch.bool, **pin))
+        if actions_cpu.device.type != "cpu" or actions_cpu.dtype != torch.float32 or not actions_cpu.is_contiguous():
+            raise ValueError("step_host wants a contiguous float32 CPU tensor")
+        want = E * N * (1 if self.variant == "uwd" else 2)
+        if actions_cpu.numel() != want:
+            raise ValueError(f"actions has {actions_cpu.numel()} elements, expected {want}")
+        hb = self._host
+        with self._dev_guard():
+            check(self.lib.flock_step_host(self._h, actions_cpu.data_ptr(), float(dt),
+                                           None if noise_cpu is None else noise_cpu.data_ptr(),
+                                           hb["obs"].data_ptr(), hb["reward"].data_ptr(), hb["agent_done"].data_ptr(),
+                                           hb["env_done"].data_ptr(), self._stream()))
+        obs = hb["obs"] if self.obs_hist > 1 else hb["obs"][:, :, 0, :]
+        return obs, hb["reward"], (hb["agent_done"], hb["env_done"]), {}
+
+    # ---- checkpoint / injection --------------------------------------------------------------
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        return dict(x=self.x.clone(), y=self.y.clone(), headings=self.headings.clone(), prev_headings=self._prev_h.clone(),
+                    obs=self._obs.clone(), reset_epoch=self._reset_epoch.clone(), ep_len=self._ep_len.clone(),
+                    ep_return_fx=self._ep_return_fx.clone(), stats=self._stats.clone(),
+                    step_index=torch.tensor(self.step_index, dtype=torch.int64))
+
+    def set_state(self, state: Dict[str, torch.Tensor]) -> None:
+        s = self._slot()
+        self._x[s].copy_(state["x"]); self._y[s].copy_(state["y"]); self._hd[s].copy_(state["headings"])
+        if "prev_headings" in state:
+            self._prev_h.copy_(state["prev_headings"])
+        if "obs" in state:
+            self._obs.copy_(state["obs"].reshape(self._obs.shape))
+        for key, buf in (("reset_epoch", self._reset_epoch), ("ep_len", self._ep_len),
+                         ("ep_return_fx", self._ep_return_fx), ("stats", self._stats)):
+            if key in state:
+                buf.copy_(state[key])
+        if "step_index" in state:
+            self.step_index = int(state["step_index"])
+
+    # ---- logging statistics ------------------------------------------------------------------
+    def stats_tensor(self) -> torch.Tensor:
+        """(8,) int64 device tensor of episode statistics flushed by reset (see FLOCK_STAT_*)."""
+        return self._stats
+
+    def episode_returns(self) -> torch.Tensor:
+        """(E,) float64 running return of the open episodes: sum_t sum_i reward / N (main.py:44)."""
+        return self._ep_return_fx.double() / 4294967296.0 / self.num_particles
+
+    def stats(self) -> Dict[str, float]:
+        s = self._stats.tolist()      # one device->host read
+        n = max(s[0], 1)
+        return dict(episodes=s[0], mean_episode_length=s[1] / n,
+                    mean_episode_return=s[2] / 4294967296.0 / self.num_particles / n,
+                    reset_attempts=s[3], reset_gave_up=s[4])

@@ -140,8 +140,9 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* Stream layout (canonical, GPU-count invariant): key = seed; counter =
- * (global env id, agent id, epoch, tag). tag 0: reset draw (epoch = per-env attempt counter),
- * tag 1: actuation noise (epoch = step index), tag 2: random actions (epoch = step index). */
+ * (global env id, agent id, epoch, tag word). tag 0: reset draw (epoch = per-env attempt counter
+ * reset_epoch, tag word 0); tag 1: actuation noise, tag 2: random actions (epoch = ep_len[env] =
+ * steps since the env's last reset, tag word = tag + 4 * reset_epoch[env]). */
 enum { TAG_RESET = 0, TAG_NOISE = 1, TAG_ACTION = 2 };
 
 static float u24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); } /* [0,1), torch.rand grid */
@@ -231,9 +232,12 @@ static void integrate_agent(const orc_cfg_t *c, const float *act, float nzu, flo
         vy = ay / n;
     } else {
         float a = act[0];
-        int id = (a == a) ? (int)a : 0;            /* int(act): truncation (uwd :329) */
-        if (id < 0) id = 0;
-        if (id > 9) id = 9;
+        /* int(act): truncation (uwd :329). Ids outside the dictionary (KeyError upstream) are
+         * clamped to it, NaN -> 0; the clamp happens in float so the conversion is always defined. */
+        a = (a == a) ? a : 0.0f;
+        a = a < 0.0f ? 0.0f : a;
+        a = a > 9.0f ? 9.0f : a;
+        int id = (int)a;
         float mu_u = id < 5 ? 0.2f : 0.6f;
         float mu_w = UWD_MU_W[id % 5];
         float u = mu_u + nzu;                      /* torch.normal(mean, 0.1) = mean + noise */
@@ -378,13 +382,16 @@ typedef struct {
     uint8_t *agent_done;           /* [E][N] */
     uint8_t *env_done;             /* [E] */
     uint32_t *reset_epoch;         /* [E] Philox attempt counter */
+    int64_t *ep_return_fx;         /* [E] episode return, sum_i reward_i in 2^-32 fixed point (logging, main.py:44) */
+    int32_t *ep_len;               /* [E] steps since reset */
+    uint64_t *stats;               /* [8] episodes, ep steps, ep return fx, reset attempts, gave up */
 } orc_buf_t;
 
 /* step(): gym_flock_v2.py:71-83, gym_flock_uw.py:69-81, gym_flock_uw_discrete.py:110-122.
  * actions: [E][N][2] (v2/uw) or [E][N] (uwd). noise: NULL -> Philox (tag 1, epoch step_index)
  * when act_noise_std > 0; else [E][N][2] additive (n_u, n_w). */
 void orc_step(const orc_cfg_t *c, orc_buf_t *b, const float *actions, const float *noise,
-              float dt, uint32_t step_index, int nthreads)
+              float dt, int nthreads)
 {
     const int E = c->num_envs, N = c->num_agents, k = c->k, H = c->obs_hist;
     const int aw = c->variant == 2 ? 1 : 2;
@@ -400,7 +407,8 @@ void orc_step(const orc_cfg_t *c, orc_buf_t *b, const float *actions, const floa
                 if (noise) { nzu = noise[(o + i) * 2]; nzw = noise[(o + i) * 2 + 1]; }
                 else if (c->act_noise_std > 0.0f) {
                     uint32_t r[4];
-                    philox4x32_10((uint32_t)(c->env_offset + e), (uint32_t)i, step_index, TAG_NOISE,
+                    philox4x32_10((uint32_t)(c->env_offset + e), (uint32_t)i, (uint32_t)b->ep_len[e],
+                                  TAG_NOISE + (b->reset_epoch[e] << 2),
                                   (uint32_t)c->seed, (uint32_t)(c->seed >> 32), r);
                     float z0, z1;
                     flock_normal2(r[0], r[1], &z0, &z1);
@@ -414,18 +422,22 @@ void orc_step(const orc_cfg_t *c, orc_buf_t *b, const float *actions, const floa
         b->env_done[e] = (uint8_t)sense_env(c, 0, b->x + o, b->y + o, b->h + o, b->prev_h + o,
                                             b->obs + o * H * k, b->nn + o * k, b->reward + o,
                                             b->agent_done + o);
+        for (int i = 0; i < N; ++i)
+            b->ep_return_fx[e] += (int64_t)llrint((double)b->reward[o + i] * 4294967296.0);
+        b->ep_len[e] += 1;
     }
 }
 
 /* canonical random actions for step_n (tag 2): v2 U[-1.5,1.5)^2 (action_space v2:58),
  * uw U[-1,1)^2 (uw:57), uwd id = floor(U*k) (Discrete(k) uwd:98). */
-void orc_random_actions(const orc_cfg_t *c, uint32_t step_index, float *actions)
+void orc_random_actions(const orc_cfg_t *c, const orc_buf_t *b, uint32_t step_offset, float *actions)
 {
     const int E = c->num_envs, N = c->num_agents;
     for (int e = 0; e < E; ++e)
         for (int i = 0; i < N; ++i) {
             uint32_t r[4];
-            philox4x32_10((uint32_t)(c->env_offset + e), (uint32_t)i, step_index, TAG_ACTION,
+            philox4x32_10((uint32_t)(c->env_offset + e), (uint32_t)i, (uint32_t)b->ep_len[e] + step_offset,
+                          TAG_ACTION + (b->reset_epoch[e] << 2),
                           (uint32_t)c->seed, (uint32_t)(c->seed >> 32), r);
             size_t a = (size_t)e * N + i;
             if (c->variant == 0) {
@@ -446,19 +458,23 @@ void orc_random_actions(const orc_cfg_t *c, uint32_t step_index, float *actions)
  * env_done reports whether the accepted/injected start still collides. Returns #envs that
  * exhausted max_attempts. */
 int orc_reset(const orc_cfg_t *c, orc_buf_t *b, const uint8_t *mask, const float *init,
-              int max_attempts, int nthreads)
+              int max_attempts, int keep_outputs, int nthreads)
 {
     const int E = c->num_envs, N = c->num_agents, k = c->k, H = c->obs_hist;
     int gave_up = 0;
-#ifdef _OPENMP
-    if (nthreads > 0) omp_set_num_threads(nthreads);
-#pragma omp parallel for schedule(static) reduction(+:gave_up)
-#endif
+    (void)nthreads;
     for (int e = 0; e < E; ++e) {
         if (mask && !mask[e]) continue;
         size_t o = (size_t)e * N;
         int done = 1;
-        for (int att = 0; att < (init ? 1 : max_attempts) && done; ++att) {
+        int att = 0;
+        /* auto-reset mode keeps reward / dones of the step that ended the episode */
+        float *keep_r = NULL; uint8_t *keep_d = NULL;
+        if (keep_outputs) {
+            keep_r = (float *)malloc(sizeof(float) * N); keep_d = (uint8_t *)malloc(N);
+            memcpy(keep_r, b->reward + o, sizeof(float) * N); memcpy(keep_d, b->agent_done + o, N);
+        }
+        for (; att < (init ? 1 : max_attempts) && done; ++att) {
             for (int i = 0; i < N; ++i) {
                 float px, py, ph;
                 if (init) {
@@ -485,8 +501,24 @@ int orc_reset(const orc_cfg_t *c, orc_buf_t *b, const uint8_t *mask, const float
             done = sense_env(c, 1, b->x + o, b->y + o, b->h + o, b->prev_h + o,
                              b->obs + o * H * k, b->nn + o * k, b->reward + o, b->agent_done + o);
         }
-        b->env_done[e] = (uint8_t)done;
+        if (keep_outputs) {
+            memcpy(b->reward + o, keep_r, sizeof(float) * N); memcpy(b->agent_done + o, keep_d, N);
+            free(keep_r); free(keep_d);
+        } else {
+            b->env_done[e] = (uint8_t)done;
+        }
         if (done && !init) gave_up += 1;
+        if (b->ep_len[e] > 0) {                    /* close the running episode (logging only) */
+            b->stats[0] += 1;
+            b->stats[1] += (uint64_t)b->ep_len[e];
+            b->stats[2] += (uint64_t)b->ep_return_fx[e];
+        }
+        if (!init) {
+            b->stats[3] += (uint64_t)att;
+            if (done) b->stats[4] += 1;
+        }
+        b->ep_len[e] = 0;
+        b->ep_return_fx[e] = 0;
     }
     return gave_up;
 }

@@ -51,7 +51,7 @@ class _Cfg(ctypes.Structure):
 class _Buf(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("x", "y", "h", "prev_h", "vx", "vy", "obs", "nn", "reward", "agent_done", "env_done",
-                 "reset_epoch")]
+                 "reset_epoch", "ep_return_fx", "ep_len", "stats")]
 
 
 _lib = None
@@ -122,10 +122,13 @@ class OracleEnv:
         self.obs = np.zeros((E, N, H, k), f32); self.nn = np.zeros((E, N, k), np.int32)
         self.reward = np.zeros((E, N), f32); self.agent_done = np.zeros((E, N), np.uint8)
         self.env_done = np.zeros((E,), np.uint8); self.reset_epoch = np.zeros((E,), np.uint32)
+        self.ep_return_fx = np.zeros((E,), np.int64); self.ep_len = np.zeros((E,), np.int32)
+        self.stats = np.zeros((8,), np.uint64)
         self.step_index = 0
         self._buf = _Buf(*[_ptr(a).value for a in (self.x, self.y, self.h, self.prev_h, self.vx, self.vy,
                                                     self.obs, self.nn, self.reward, self.agent_done,
-                                                    self.env_done, self.reset_epoch)])
+                                                    self.env_done, self.reset_epoch, self.ep_return_fx,
+                                                    self.ep_len, self.stats)])
         self._lib = _load()
 
     # -- state injection ------------------------------------------------------------------
@@ -136,14 +139,15 @@ class OracleEnv:
         if obs is not None:
             self.obs[...] = np.asarray(obs, np.float32).reshape(self.obs.shape)
 
-    def reset(self, mask=None, init=None, max_attempts: int = 64) -> int:
+    def reset(self, mask=None, init=None, max_attempts: int = 64, keep_outputs: bool = False) -> int:
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         ini = None if init is None else np.ascontiguousarray(init, np.float32)
         if ini is not None:
             assert ini.shape == (3, self.E, self.N)
         return self._lib.orc_reset(ctypes.byref(self.cfg), ctypes.byref(self._buf),
                                    None if m is None else _ptr(m), None if ini is None else _ptr(ini),
-                                   ctypes.c_int(max_attempts), ctypes.c_int(self.nthreads))
+                                   ctypes.c_int(max_attempts), ctypes.c_int(int(keep_outputs)),
+                                   ctypes.c_int(self.nthreads))
 
     def step(self, actions, dt: float = 0.1, noise=None):
         aw = 1 if self.variant == "uwd" else 2
@@ -151,15 +155,14 @@ class OracleEnv:
         assert a.size == self.E * self.N * aw
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
         self._lib.orc_step(ctypes.byref(self.cfg), ctypes.byref(self._buf), _ptr(a),
-                           None if nz is None else _ptr(nz), ctypes.c_float(dt),
-                           ctypes.c_uint32(self.step_index), ctypes.c_int(self.nthreads))
+                           None if nz is None else _ptr(nz), ctypes.c_float(dt), ctypes.c_int(self.nthreads))
         self.step_index += 1
 
-    def random_actions(self, step_index=None) -> np.ndarray:
+    def random_actions(self, step_offset: int = 0) -> np.ndarray:
         aw = 1 if self.variant == "uwd" else 2
         a = np.zeros((self.E, self.N, aw) if aw == 2 else (self.E, self.N), np.float32)
-        si = self.step_index if step_index is None else step_index
-        self._lib.orc_random_actions(ctypes.byref(self.cfg), ctypes.c_uint32(si), _ptr(a))
+        self._lib.orc_random_actions(ctypes.byref(self.cfg), ctypes.byref(self._buf), ctypes.c_uint32(step_offset),
+                                     _ptr(a))
         return a
 
 

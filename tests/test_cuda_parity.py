@@ -1,0 +1,303 @@
+"""GPU: the sm_100a kernels (through the C ABI / VecEnv) against the CPU oracle -- BIT-EXACT.
+
+Integer outputs (k-NN index lists, dones, episode counters) and every float32 buffer (positions,
+headings, displacements, ranges, rewards) must be identical to oracle/flock_oracle.c, which is
+itself pinned to the reference by tests/test_oracle_golden.py. Tolerance: 0 ulp.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.cuda_util import assert_same, compare_all, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from marl_range_flocking_b200 import load_library
+    return load_library()
+
+
+def test_philox_known_answers_and_stream():
+    lib = _lib()
+    from oracle import flock_oracle as fo
+    rng = np.random.default_rng(0)
+    ck = rng.integers(0, 2**32, (4096, 6), dtype=np.uint64).astype(np.uint32)
+    ck[0] = 0
+    ck[1] = 0xFFFFFFFF
+    ck[2] = [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0]
+    d = torch.from_numpy(ck.view(np.int32)).cuda()
+    out = torch.zeros(4096, 4, dtype=torch.int32, device="cuda")
+    assert lib.flock_debug_philox(d.data_ptr(), 4096, out.data_ptr(), None) == 0
+    got = out.cpu().numpy().view(np.uint32)
+    # Random123 known-answer vectors for philox4x32-10
+    assert got[0].tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert got[1].tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert got[2].tolist() == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    want = np.stack([fo.philox4x32_10(r[:4], r[4:]) for r in ck[:256]])
+    assert np.array_equal(got[:256], want)
+
+
+def test_canonical_sincos_and_normal_bit_exact():
+    lib = _lib()
+    from oracle import flock_oracle as fo
+    rng = np.random.default_rng(1)
+    h = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e4, 1e4, 100000), rng.uniform(-1e8, 1e8, 20000),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 2e9, 1e-30, np.pi / 4, -np.pi / 4]]).astype(np.float32)
+    d = torch.from_numpy(h).cuda()
+    s = torch.empty_like(d)
+    c = torch.empty_like(d)
+    assert lib.flock_debug_sincos(d.data_ptr(), h.size, s.data_ptr(), c.data_ptr(), None) == 0
+    ws, wc = fo.sincosf(h)
+    assert_same("sin", s, ws)
+    assert_same("cos", c, wc)
+    w = rng.integers(0, 2**32, 400000, dtype=np.uint64).astype(np.uint32)
+    w[:4] = [0, 0, 0xFFFFFFFF, 0xFFFFFFFF]
+    dw = torch.from_numpy(w.view(np.int32)).cuda()
+    z = torch.empty(w.size, dtype=torch.float32, device="cuda")
+    assert lib.flock_debug_normal2(dw.data_ptr(), w.size // 2, z.data_ptr(), None) == 0
+    assert_same("normal2", z, fo.normal2(w))
+
+
+SMALL = [
+    # variant, E, N, k, cd, range_start, sensor_range
+    ("v2", 100, 10, 4, 2.5, (0, 50), 14.0),      # BASELINE config 1/2 parameters
+    ("v2", 37, 32, 8, 0.5, (0, 100), 30.0),
+    ("v2", 64, 5, 4, 1.0, (0, 20), 9.0),         # k = N-1
+    ("v2", 50, 2, 1, 1.0, (0, 20), 9.0),
+    ("v2", 31, 7, 3, 1.0, (0, 20), 9.0),
+    ("v2", 20, 17, 5, 1.0, (0, 40), 9.0),        # one env per warp, 17 live lanes
+    ("uw", 64, 32, 3, 0.5, (0, 200), 7.0),       # BASELINE config 3 parameters
+    ("uw", 50, 8, 3, 3.0, (0, 50), 7.0),         # shared-critic trainer parameters
+    ("uw", 33, 12, 4, 1.0, (0, 60), 7.0),        # k=4 history (generic obs path)
+    ("uwd", 64, 16, 4, 0.5, (0, 100), 7.0),      # BASELINE config 4 parameters
+    ("uwd", 33, 8, 4, 3.0, (0, 50), 7.0),        # VDN trainer parameters
+    ("uwd", 20, 25, 6, 0.5, (0, 100), 7.0),
+]
+TILED = [
+    ("v2", 5, 64, 8, 0.5, (0, 200), 30.0),       # TMA path (N % 4 == 0)
+    ("v2", 3, 67, 4, 0.5, (0, 200), 30.0),       # plain-load path
+    ("v2", 2, 300, 8, 0.3, (0, 400), 50.0),      # 3 tiles per env, ragged last tile
+    ("uw", 4, 48, 3, 0.5, (0, 300), 7.0),
+    ("uwd", 3, 40, 4, 0.5, (0, 300), 7.0),
+    ("v2", 2, 33, 3, 0.5, (0, 200), 30.0),
+]
+
+
+def _run_parity(variant, E, N, k, cd, rs, sr, T, rigid=False):
+    env, orc = make_pair(variant, E, N, k, cd, rs, sr, rigid=rigid)
+    env.reset()
+    orc.reset()
+    compare_all(env, orc, tag="reset:")
+    for t in range(T):
+        a = orc.random_actions()
+        dt = 0.1 if t % 3 else 0.25
+        orc.step(a, dt)
+        env.step(torch.from_numpy(a).cuda(), dt)
+        compare_all(env, orc, tag=f"step{t}:")
+    # masked reset of the finished envs + a second full reset (closes episodes -> stats)
+    mask = orc.env_done.copy()
+    mask[::3] = 1
+    orc.reset(mask=mask)
+    env.reset(mask=torch.from_numpy(mask).cuda().bool())
+    compare_all(env, orc, tag="masked reset:")
+    a = orc.random_actions()
+    orc.step(a, 0.1)
+    env.step(torch.from_numpy(a).cuda(), 0.1)
+    compare_all(env, orc, tag="after masked reset:")
+
+
+@pytest.mark.parametrize("case", SMALL, ids=[f"{c[0]}-E{c[1]}-N{c[2]}-k{c[3]}" for c in SMALL])
+def test_small_path_bit_exact(case):
+    _run_parity(*case, T=40)
+
+
+@pytest.mark.parametrize("case", TILED, ids=[f"{c[0]}-E{c[1]}-N{c[2]}-k{c[3]}" for c in TILED])
+def test_tiled_path_bit_exact(case):
+    _run_parity(*case, T=12)
+
+
+def test_rigid_boundary_bit_exact():
+    _run_parity("v2", 40, 10, 4, 1.0, (0, 6), 9.0, T=60, rigid=True)
+    _run_parity("v2", 2, 64, 4, 0.1, (0, 6), 9.0, T=30, rigid=True)
+
+
+def test_dense_world_wraps_and_collides():
+    # tiny world: constant wrapping, many collisions, clamped ranges (sensor_range < typical distance)
+    _run_parity("v2", 64, 10, 4, 2.5, (0, 8), 2.0, T=80)
+    _run_parity("uw", 64, 10, 3, 2.5, (0, 8), 2.0, T=80)
+    _run_parity("uwd", 64, 10, 4, 2.5, (0, 8), 2.0, T=80)
+
+
+@pytest.mark.parametrize("variant,N,k", [("v2", 10, 4), ("uw", 32, 3), ("uwd", 16, 4), ("v2", 32, 8), ("uw", 9, 4)])
+def test_step_n_persistent_matches_step_by_step(variant, N, k):
+    E, T = 50, 37
+    env, orc = make_pair(variant, E, N, k, 0.5, (0, 100), 9.0, seed=77)
+    env.reset()
+    orc.reset()
+    env.step_n(T, 0.1)
+    for _ in range(T):
+        orc.step(orc.random_actions(), 0.1)
+    compare_all(env, orc, tag="step_n:")
+    # and once more from a non-zero step index, single step
+    env.step_n(1, 0.2)
+    orc.step(orc.random_actions(), 0.2)
+    compare_all(env, orc, tag="step_n(1):")
+
+
+def test_step_n_tiled_matches():
+    env, orc = make_pair("v2", 2, 64, 4, 0.5, (0, 200), 30.0, seed=5)
+    env.reset()
+    orc.reset()
+    env.step_n(5, 0.1)
+    for _ in range(5):
+        orc.step(orc.random_actions(), 0.1)
+    compare_all(env, orc, tag="step_n tiled:")
+
+
+def test_random_actions_match_oracle():
+    for variant, N, k in (("v2", 10, 4), ("uw", 32, 3), ("uwd", 16, 4)):
+        env, orc = make_pair(variant, 20, N, k, 0.5, (0, 100), 9.0, seed=9, env_offset=1000)
+        for si in (0, 1, 12345):
+            assert_same("actions", env.random_actions(si), orc.random_actions(si))
+
+
+def test_uwd_injected_noise_and_nan_inf_actions():
+    env, orc = make_pair("uwd", 16, 8, 4, 1.0, (0, 50), 7.0)
+    env.reset()
+    orc.reset()
+    rng = np.random.default_rng(3)
+    for t in range(10):
+        a = rng.integers(0, 10, (16, 8)).astype(np.float32) + rng.uniform(0, 0.9, (16, 8)).astype(np.float32)
+        nz = (rng.standard_normal((16, 8, 2)) * 0.1).astype(np.float32)
+        orc.step(a, 0.1, noise=nz)
+        env.step(torch.from_numpy(a).cuda(), 0.1, noise=torch.from_numpy(nz).cuda())
+        compare_all(env, orc, tag=f"uwd noise {t}:")
+    env, orc = make_pair("v2", 8, 6, 3, 1.0, (0, 20), 9.0)
+    env.reset()
+    orc.reset()
+    a = orc.random_actions()
+    a[0, 0] = [np.nan, 0.1]
+    a[1, 1] = [0.5, np.nan]
+    a[2, 2] = [np.inf, -np.inf]
+    a[3, 3] = [-np.inf, 1e30]
+    for t in range(3):
+        orc.step(a, 0.1)
+        env.step(torch.from_numpy(a).cuda(), 0.1)
+        compare_all(env, orc, tag=f"bad actions {t}:")
+    env, orc = make_pair("uw", 8, 6, 3, 1.0, (0, 20), 9.0)
+    env.reset()
+    orc.reset()
+    a = orc.random_actions()
+    a[0, 0] = [0.0, 0.0]          # zero action -> 0/0 -> nan_to_num -> 0 (gym_flock_uw.py:298)
+    a[1, 1] = [np.nan, 1.0]
+    a[2, 2] = [3e30, 1e30]
+    orc.step(a, 0.1)
+    env.step(torch.from_numpy(a).cuda(), 0.1)
+    compare_all(env, orc, tag="uw bad actions:")
+
+
+def test_ties_and_coincident_agents_lower_index_wins():
+    # symmetric layout: agent 0 in the middle of a square -> four exactly equal distances
+    N, k = 6, 3
+    x = np.array([[10, 9, 11, 10, 10, 10]], np.float32)
+    y = np.array([[10, 10, 10, 9, 11, 10]], np.float32)   # agent 5 coincides with agent 0
+    h = np.zeros((1, N), np.float32)
+    for variant in ("v2", "uw", "uwd"):
+        env, orc = make_pair(variant, 1, N, k, 0.5, (0, 20), 9.0)
+        init = np.stack([x, y, h])
+        orc.reset(init=init)
+        env.reset(init_state=torch.from_numpy(init).cuda())
+        compare_all(env, orc, tag="ties reset:")
+        nn = env.nearest_neighbors[0].cpu().numpy()
+        assert nn[0].tolist() == [5, 1, 2]        # d=0 (coincident) first, then the lowest indices of the tie
+        assert nn[5].tolist() == [0, 1, 2]
+        assert not (nn == np.arange(N)[:, None]).any()   # never itself
+
+
+def test_env_sharding_is_invariant():
+    """Splitting the env range over two handles (as two GPUs would) reproduces the single-handle
+    results bit for bit: the Philox streams are keyed by the GLOBAL env index."""
+    for variant, N, k in (("v2", 10, 4), ("uwd", 16, 4)):
+        E = 64
+        full, _ = make_pair(variant, E, N, k, 0.5, (0, 100), 9.0, seed=42)
+        lo, _ = make_pair(variant, E // 2, N, k, 0.5, (0, 100), 9.0, seed=42, env_offset=0)
+        hi, _ = make_pair(variant, E // 2, N, k, 0.5, (0, 100), 9.0, seed=42, env_offset=E // 2)
+        for e in (full, lo, hi):
+            e.reset()
+            e.step_n(25, 0.1)
+        torch.cuda.synchronize()
+        for name in ("x", "y", "headings", "observation", "reward"):
+            want = getattr(full, name)
+            got = torch.cat([getattr(lo, name), getattr(hi, name)], dim=0)
+            assert torch.equal(want, got), name
+
+
+def test_step_host_matches_device_path():
+    env, orc = make_pair("v2", 128, 10, 4, 2.5, (0, 50), 14.0)
+    env.reset()
+    orc.reset()
+    for t in range(5):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        obs, rew, (ad, ed), _ = env.step_host(torch.from_numpy(a).pin_memory(), 0.1)
+        assert_same("host obs", obs, orc.obs[:, :, 0, :])
+        assert_same("host reward", rew[..., 0], orc.reward)
+        assert_same("host agent_done", ad.to(torch.uint8), orc.agent_done)
+        assert_same("host env_done", ed.to(torch.uint8), orc.env_done)
+    compare_all(env, orc, tag="host:")
+
+
+def test_auto_reset_resets_exactly_the_done_envs():
+    env, orc = make_pair("v2", 256, 10, 4, 2.5, (0, 30), 14.0, auto_reset=True)
+    env.reset()
+    orc.reset()
+    for t in range(30):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        orc.reset(mask=orc.env_done.copy(), keep_outputs=True)
+        env.step(torch.from_numpy(a).cuda(), 0.1)
+        compare_all(env, orc, tag=f"auto reset {t}:")
+    s = env.stats()
+    assert s["episodes"] == int(orc.stats[0]) and s["episodes"] > 0
+
+
+FULL = [
+    ("v2", 4096, 10, 4, 2.5, (0, 50), 14.0, 20),      # BASELINE config 2
+    ("uw", 4096, 32, 3, 0.5, (0, 200), 7.0, 10),      # BASELINE config 3
+    ("uwd", 8192, 16, 4, 0.5, (0, 100), 7.0, 10),     # BASELINE config 4
+]
+
+
+@pytest.mark.parametrize("case", FULL, ids=[f"{c[0]}-E{c[1]}-N{c[2]}" for c in FULL])
+def test_full_size_configs_bit_exact(case):
+    variant, E, N, k, cd, rs, sr, T = case
+    env, orc = make_pair(variant, E, N, k, cd, rs, sr, seed=0x5EED,
+                         **({"reset_collision_distance": 1.0} if variant == "uwd" else {}))
+    env.reset()
+    orc.reset()
+    compare_all(env, orc, tag="reset:")
+    for t in range(T):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        env.step(torch.from_numpy(a).cuda(), 0.1)
+    compare_all(env, orc, tag="final:")
+    # domain properties at full size: ranges ascending, clamped, self never a neighbour
+    d = env.distances_to_nearest_neighbors
+    assert bool((d[..., 1:] >= d[..., :-1]).all()) and bool((d >= 0).all()) and bool((d <= sr).all())
+    nn = env.nearest_neighbors
+    assert not bool((nn == torch.arange(N, device=nn.device)[None, :, None]).any())
+    assert bool(((nn >= 0) & (nn < N)).all())
+
+
+def test_large_swarm_config5_bit_exact():
+    # BASELINE config 5 shape (E reduced to keep the CPU oracle fast): 2048 agents, k = 8
+    env, orc = make_pair("v2", 4, 2048, 8, 0.05, (0, 2000), 100.0, seed=0x5EED)
+    env.reset()
+    orc.reset()
+    compare_all(env, orc, tag="reset:")
+    for t in range(3):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        env.step(torch.from_numpy(a).cuda(), 0.1)
+        compare_all(env, orc, tag=f"step{t}:")
