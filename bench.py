@@ -199,7 +199,6 @@ def timed_graph_steps(envs, acts, steps, warmup, device, dist_barrier):
         g_w.replay()
     torch.cuda.synchronize(device)
     dist_barrier()
-    launches0 = sum(e.launch_count for e in envs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(device)
     ev0.record()
@@ -210,9 +209,7 @@ def timed_graph_steps(envs, acts, steps, warmup, device, dist_barrier):
     ev1.record()
     torch.cuda.synchronize(device)
     dist_barrier()
-    # graph replays do not go through flock_step again: launches = one fused kernel per step
-    # (+ one memset node per step on the tiled path, not counted as a kernel)
-    del launches0
+    # graph replays do not go through flock_step again: launches = one fused kernel node per step
     return ev0.elapsed_time(ev1), steps
 
 
@@ -317,6 +314,33 @@ def run_gpu(args, w):
         extra["step_n_persistent"] = {"steps_per_launch": T, "agent_steps_per_s_per_gpu": E * N * T / (ev0.elapsed_time(ev1) * 1e-3),
                                       "note": "in-kernel Philox actions, state in registers; FP32-issue bound, no per-step HBM traffic"}
 
+    # the same kernel on ONE big batch (as many envs as the whole ring): shows what the kernel
+    # sustains once a launch carries enough bytes to leave the launch-latency regime
+    if rank == 0 and not args.no_sweep:
+        from marl_range_flocking_b200 import VecEnv
+        peak_, _ = _peaks()
+        big_E = E * ring
+        big = VecEnv(w["variant"], big_E, N, w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"], seed=1,
+                     device=device, **w["kw"])
+        big.reset()
+        big_act = [big.random_actions(i) for i in range(2)]
+        for i in range(3):
+            big.step(big_act[i & 1], DT)
+        torch.cuda.synchronize(device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20 if not big.tiled else 3
+        ev0.record()
+        for i in range(reps):
+            big.step(big_act[i & 1], DT)
+        ev1.record()
+        torch.cuda.synchronize(device)
+        t_big = ev0.elapsed_time(ev1) * 1e-3 / reps
+        gbs = big_E * N * w["bytes"] / t_big / 1e9
+        extra["large_batch"] = {"envs": big_E, "ms_per_step": t_big * 1e3, "agent_steps_per_s": big_E * N / t_big,
+                                "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak_,
+                                "note": "one launch over envs = E x ring; working set > L2, same fused kernel"}
+        del big, big_act
+
     if rank == 0:
         peak, peak_src = _peaks()
         per_launch_s = ms_max * 1e-3 / steps
@@ -365,6 +389,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--ring", type=int, default=0, help="number of env batches in the L2-defeating ring (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the large-batch roofline leg")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

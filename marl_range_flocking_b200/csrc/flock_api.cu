@@ -280,14 +280,32 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
     }
     rc = step_device(e, e->stage_actions, dt, d_noise, s);
     if (rc != FLOCK_OK) return rc;
-    if (h_obs != nullptr && err == cudaSuccess)
-        err = cudaMemcpyAsync(h_obs, e->b.obs, EN * e->cfg.obs_hist * e->cfg.k * sizeof(float), cudaMemcpyDeviceToHost, s);
-    if (h_reward != nullptr && err == cudaSuccess)
-        err = cudaMemcpyAsync(h_reward, e->b.reward, EN * sizeof(float), cudaMemcpyDeviceToHost, s);
-    if (h_agent_done != nullptr && err == cudaSuccess)
-        err = cudaMemcpyAsync(h_agent_done, e->b.agent_done, EN, cudaMemcpyDeviceToHost, s);
-    if (h_env_done != nullptr && err == cudaSuccess)
-        err = cudaMemcpyAsync(h_env_done, e->b.env_done, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s);
+    // When the caller laid obs | reward | agent_done | env_done out back to back on BOTH sides (the
+    // Python host does), the four results travel as one D2H copy instead of four.
+    const size_t obs_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float);
+    const size_t rew_bytes = EN * sizeof(float);
+    const char* d0 = reinterpret_cast<const char*>(e->b.obs);
+    char* h0 = reinterpret_cast<char*>(h_obs);
+    const bool packed = h_obs && h_reward && h_agent_done && h_env_done &&
+                        reinterpret_cast<const char*>(e->b.reward) == d0 + obs_bytes &&
+                        reinterpret_cast<const char*>(e->b.agent_done) == d0 + obs_bytes + rew_bytes &&
+                        reinterpret_cast<const char*>(e->b.env_done) == d0 + obs_bytes + rew_bytes + EN &&
+                        reinterpret_cast<char*>(h_reward) == h0 + obs_bytes &&
+                        reinterpret_cast<char*>(h_agent_done) == h0 + obs_bytes + rew_bytes &&
+                        reinterpret_cast<char*>(h_env_done) == h0 + obs_bytes + rew_bytes + EN;
+    if (packed) {
+        err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes + rew_bytes + EN + (size_t)e->cfg.num_envs,
+                              cudaMemcpyDeviceToHost, s);
+    } else {
+        if (h_obs != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes, cudaMemcpyDeviceToHost, s);
+        if (h_reward != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_reward, e->b.reward, rew_bytes, cudaMemcpyDeviceToHost, s);
+        if (h_agent_done != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_agent_done, e->b.agent_done, EN, cudaMemcpyDeviceToHost, s);
+        if (h_env_done != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_env_done, e->b.env_done, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s);
+    }
     if (err != cudaSuccess) return cuda_fail(err, "D2H outputs");
     err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) return cuda_fail(err, "stream synchronize");

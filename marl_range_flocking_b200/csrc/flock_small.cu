@@ -160,15 +160,41 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
         float x = 0.f, y = 0.f, h = 0.f, prev_h = 0.f;
         float prev_h_in = 0.f;
         uint32_t ep0 = 0u, repoch = 0u;   // per-env Philox epoch (episode step, reset epoch)
+        // Every global load of the step is issued here, up front, so the warp pays ONE DRAM round
+        // trip: the read-modify-write operands of the epilogue (episode counters, uw obs window)
+        // are prefetched into registers together with the state and the actions.
+        long long ep_ret0 = 0;
+        float act0 = 0.f, act1 = 0.f, nz0 = 0.f, nz1 = 0.f;
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0;   // uw window (k = 3 fast path)
+        const bool fast_win = (V == FLOCK_UW) && !MULTI && k == 3 && p.H == 4;
         if (live) {
-            if (MULTI || V == FLOCK_UWD) {
-                ep0 = (uint32_t)p.ep_len[env];
-                repoch = p.reset_epoch[env];
-            }
+            ep0 = (uint32_t)p.ep_len[env];
+            if (MULTI || V == FLOCK_UWD) repoch = p.reset_epoch[env];
+            if (m.a == 0 && p.ep_return_fx != nullptr) ep_ret0 = p.ep_return_fx[env];
             x = p.x[idx];
             y = p.y[idx];
             h = p.h[idx];
             if (V == FLOCK_UW) prev_h = prev_h_in = p.prev_h[idx];
+            if (!MULTI) {
+                if (V == FLOCK_UWD) {
+                    act0 = p.actions[idx];
+                    if (p.noise != nullptr) {
+                        const float2 nz = reinterpret_cast<const float2*>(p.noise)[idx];
+                        nz0 = nz.x;
+                        nz1 = nz.y;
+                    }
+                } else {
+                    const float2 act = reinterpret_cast<const float2*>(p.actions)[idx];
+                    act0 = act.x;
+                    act1 = act.y;
+                }
+                if (fast_win) {
+                    const float4* o4 = reinterpret_cast<const float4*>(p.obs + idx * 12);
+                    w0 = o4[0];
+                    w1 = o4[1];
+                    w2 = o4[2];
+                }
+            }
         }
         float vx = 0.f, vy = 0.f, rew = 0.f;
         float dist[K];
@@ -188,18 +214,14 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 const uint32_t step = ep0 + (uint32_t)st;
                 if (MULTI) {
                     random_action<V>(p, p.env_offset + env, m.a, step, repoch, a0, a1);
-                } else if (V == FLOCK_UWD) {
-                    a0 = p.actions[idx];
                 } else {
-                    const float2 act = reinterpret_cast<const float2*>(p.actions)[idx];
-                    a0 = act.x;
-                    a1 = act.y;
+                    a0 = act0;
+                    a1 = act1;
                 }
                 if (V == FLOCK_UWD) {
                     if (!MULTI && p.noise != nullptr) {
-                        const float2 nz = reinterpret_cast<const float2*>(p.noise)[idx];
-                        nzu = nz.x;
-                        nzw = nz.y;
+                        nzu = nz0;
+                        nzw = nz1;
                     } else if (p.noise_std > 0.0f) {
                         act_noise(p, p.env_offset + env, m.a, step, repoch, nzu, nzw);
                     }
@@ -252,6 +274,11 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
 #pragma unroll
                     for (int s = 0; s < K; ++s)
                         if (s < k) o[(r + 1) * k + s] = hist[r * K + s];
+            } else if (fast_win) {
+                float4* o4 = reinterpret_cast<float4*>(p.obs + idx * 12);   // shift by one row of 3, newest first
+                o4[0] = make_float4(dist[0], dist[1], dist[2 % K], w0.x);
+                o4[1] = make_float4(w0.y, w0.z, w0.w, w1.x);
+                o4[2] = make_float4(w1.y, w1.z, w1.w, w2.x);
             } else {
                 write_obs<K>(p, idx, dist, false);
             }
@@ -260,8 +287,8 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             p.agent_done[idx] = coll ? 1 : 0;
             if (m.a == 0) {
                 p.env_done[env] = env_coll ? 1 : 0;
-                if (p.ep_return_fx != nullptr) p.ep_return_fx[env] += ret_fx;
-                p.ep_len[env] += nsteps;
+                if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = ep_ret0 + ret_fx;
+                p.ep_len[env] = (int)ep0 + nsteps;
             }
         }
     }

@@ -97,11 +97,10 @@ class VecEnv:
         self._prev_h = z(E, N)
         self._vx = z(E, N) if track_velocities else None
         self._vy = z(E, N) if track_velocities else None
-        self._obs = z(E, N, H, self.k)
+        # obs | reward | agent_done | env_done share one allocation so that the host-call path moves
+        # the step results with a single device->host copy
+        self._out_slab, (self._obs, self._reward, self._agent_done, self._env_done) = self._alloc_outputs(self.device)
         self._nn = z(E, N, self.k, dtype=torch.int32) if track_neighbors else None
-        self._reward = z(E, N, 1)
-        self._agent_done = z(E, N, dtype=torch.bool)
-        self._env_done = z(E, dtype=torch.bool)
         self._reset_epoch = z(E, dtype=torch.int32)          # uint32 counter, int32 storage
         self._ep_return_fx = z(E, dtype=torch.int64)
         self._ep_len = z(E, dtype=torch.int32)
@@ -118,6 +117,18 @@ class VecEnv:
         self._host = None   # pinned host mirrors for step_host
 
     # ------------------------------------------------------------------------------------------
+    def _alloc_outputs(self, device, pin: bool = False):
+        E, N, H, k = self.num_envs, self.num_particles, self.obs_hist, self.k
+        n_obs, n_rew = E * N * H * k * 4, E * N * 4
+        total = n_obs + n_rew + E * N + E
+        slab = (torch.zeros(total, dtype=torch.uint8, pin_memory=True) if pin
+                else torch.zeros(total, dtype=torch.uint8, device=device))
+        obs = slab[:n_obs].view(torch.float32).view(E, N, H, k)
+        reward = slab[n_obs:n_obs + n_rew].view(torch.float32).view(E, N, 1)
+        agent_done = slab[n_obs + n_rew:n_obs + n_rew + E * N].view(torch.bool).view(E, N)
+        env_done = slab[n_obs + n_rew + E * N:].view(torch.bool).view(E)
+        return slab, (obs, reward, agent_done, env_done)
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
@@ -271,12 +282,8 @@ class VecEnv:
         reused between calls). The call synchronises the stream."""
         E, N = self.num_envs, self.num_particles
         if self._host is None:
-            pin = dict(pin_memory=True)
-            self._host = dict(
-                obs=torch.empty(self._obs.shape, dtype=torch.float32, **pin),
-                reward=torch.empty((E, N, 1), dtype=torch.float32, **pin),
-                agent_done=torch.empty((E, N), dtype=torch.bool, **pin),
-                env_done=torch.empty((E,), dtype=torch.bool, **pin))
+            slab, (o, r, ad, ed) = self._alloc_outputs(None, pin=True)
+            self._host = dict(slab=slab, obs=o, reward=r, agent_done=ad, env_done=ed)
         if actions_cpu.device.type != "cpu" or actions_cpu.dtype != torch.float32 or not actions_cpu.is_contiguous():
             raise ValueError("step_host wants a contiguous float32 CPU tensor")
         want = E * N * (1 if self.variant == "uwd" else 2)
