@@ -117,7 +117,7 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
         e->launches += 1;
     } else {
-        err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, s);
+        err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, e->sm_count, s);
         e->launches += 1;
         if (err == cudaSuccess) e->slot ^= 1;
     }

@@ -1,18 +1,20 @@
 // flock_tiled.cu -- tiled all-pairs kernels for large swarms (32 < N <= FLOCK_MAX_AGENTS).
 //
-// One CTA = one 128-row i-tile of one env. The env's whole old state (x, y, heading) and its
-// actions are pulled into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier); every
-// CTA of the env re-integrates all N agents in shared memory (about 3 % of the pair work at
-// N = 2048, and it removes any grid-wide dependency), writes back only its own rows to the OTHER
-// state copy (ping-pong, so concurrent CTAs of the same env still read the old state), then runs
-// its rows against all j as broadcast float4 shared-memory reads with a register-resident
-// k-smallest list per row. One launch = one env step, as on the small path.
+// One CTA = one i-tile (R = blockDim.x rows, chosen per launch for SM balance) of one env. The
+// env's old positions are pulled into shared memory with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier); every CTA of the env re-integrates all N agents in place in shared memory (headings
+// and actions stream straight from global; ~5 % of the pair work at N = 2048, and it removes any
+// grid-wide dependency), writes back only its own rows to the OTHER state copy (ping-pong, so
+// concurrent CTAs of the same env still read the old state), then runs its rows against all j as
+// broadcast 128-bit shared-memory reads with a register-resident k-smallest list per row.
+// One launch = one env step, as on the small path.
 #include "flock_device.cuh"
 #include "flock_launch.h"
 
 namespace flock {
 
-constexpr int kTileThreads = 128;
+constexpr int kMaxTileThreads = 256;   // upper bound of rows per CTA
+constexpr int kCandCap = 8;         // deferred k-NN candidates per row between two merges
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,73 +46,131 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  : "memory");
 }
 
-__host__ __device__ __forceinline__ int padded_agents(int N) { return ((N + 3) & ~3) + 4; }
-
-size_t tiled_smem_bytes(int num_agents) { return (size_t)padded_agents(num_agents) * 5 * sizeof(float); }
-
-// shared-memory carve-up: sx | sy | sh | sa (actions, 2 floats per agent)
-struct TileSmem {
-    float *sx, *sy, *sh, *sa;
-};
-__device__ __forceinline__ TileSmem carve(float* base, int N) {
-    const int P = padded_agents(N);
-    return TileSmem{base, base + P, base + 2 * P, base + 3 * P};
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    // volatile + memory clobber: must stay after the __syncthreads() that publishes the staged env
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
 }
 
-__device__ __forceinline__ void stage_env(const Params& p, const TileSmem& sm, uint64_t* bar, int env, int aw,
-                                          bool with_actions) {
+__host__ __device__ __forceinline__ int padded_agents(int N) { return ((N + 3) & ~3) + 4; }
+
+// shared-memory carve-up: sx | sy | [sh] | candidate buffer. sh (headings) exists only where the
+// kernel needs every agent's heading afterwards (uwd mean heading, reset).
+size_t tiled_smem_bytes(int num_agents, int rows, bool need_sh) {
+    return (size_t)padded_agents(num_agents) * (need_sh ? 3 : 2) * sizeof(float) +
+           (size_t)kCandCap * rows * sizeof(uint2);
+}
+
+struct TileSmem {
+    float *sx, *sy, *sh;
+    uint2* cand;   // [kCandCap][rows] (d2 bits, j), column = thread
+};
+__device__ __forceinline__ TileSmem carve(float* base, int N, bool need_sh) {
+    const int P = padded_agents(N);
+    float* after = base + (need_sh ? 3 : 2) * P;
+    return TileSmem{base, base + P, need_sh ? base + 2 * P : nullptr, reinterpret_cast<uint2*>(after)};
+}
+
+// stage the env's old positions: TMA bulk copies when rows are 16-byte multiples, plain loads otherwise
+__device__ __forceinline__ void stage_xy(const Params& p, const TileSmem& sm, uint64_t* bar, int env) {
     const int N = p.N;
     const size_t base = (size_t)env * N;
-    if ((N & 3) == 0) {  // rows are 16-byte multiples and 16-byte aligned: TMA bulk path
+    if ((N & 3) == 0) {
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             const uint32_t row = (uint32_t)N * 4u;
-            const uint32_t act = with_actions ? row * (uint32_t)aw : 0u;
-            mbar_expect_tx(bar, 3u * row + act);
+            mbar_expect_tx(bar, 2u * row);
             tma_load_1d(sm.sx, p.x + base, row, bar);
             tma_load_1d(sm.sy, p.y + base, row, bar);
-            tma_load_1d(sm.sh, p.h + base, row, bar);
-            if (with_actions) tma_load_1d(sm.sa, p.actions + base * aw, act, bar);
         }
         __syncthreads();          // barrier initialised and armed before anyone polls it
         mbar_wait(bar, 0);
     } else {
-        for (int a = threadIdx.x; a < N; a += kTileThreads) {
+        for (int a = threadIdx.x; a < N; a += blockDim.x) {
             sm.sx[a] = p.x[base + a];
             sm.sy[a] = p.y[base + a];
-            sm.sh[a] = p.h[base + a];
-            if (with_actions)
-                for (int c = 0; c < aw; ++c) sm.sa[a * aw + c] = p.actions[(base + a) * aw + c];
         }
         __syncthreads();
     }
 }
 
+// All-pairs scan of one row against the staged env, ALL 32 lanes of the warp must call it.
+//
+// The hot loop is 9 FP32 instructions per pair plus a warp-uniform threshold vote per 4 pairs;
+// candidates with d2 <= thr are only APPENDED (predicated) to a per-thread shared-memory buffer and
+// merged into the register-resident sorted k-list in batches, so the 40-instruction sorted insert
+// is off the hot path. `thr` is any upper bound of the row's k-th smallest d2 (the caller derives
+// it from the previous step's neighbour list; FLT_MAX = no bound; negative = dummy row, never
+// hits). Candidates reach the list in ascending j and the insert is strict, so ties keep the lower
+// index; the row's own index is dropped at merge time, which keeps the j == i test out of the loop.
 template <int K, bool PER>
-__device__ __forceinline__ void knn_tiled(const float* sx, const float* sy, int i, int N, float x, float y, float B,
-                                          TopK<K>& t) {
+__device__ __forceinline__ void knn_tiled(const float* sx, const float* sy, uint2* cand, int i, int N, float x,
+                                          float y, float B, float thr, TopK<K>& t) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int cstride = blockDim.x;
     t.init();
-    const float4* px = reinterpret_cast<const float4*>(sx);
-    const float4* py = reinterpret_cast<const float4*>(sy);
+    int cnt = 0;
+    auto merge = [&]() {
+#pragma unroll 1
+        for (int c = 0; c < kCandCap; ++c) {
+            if (!__any_sync(kFull, c < cnt)) break;
+            const uint2 e = cand[c * cstride];
+            const bool ok = c < cnt && (int)e.y != i;
+            t.insert(ok ? __uint_as_float(e.x) : kInf, (int)e.y);
+        }
+        cnt = 0;
+        thr = fminf(thr, t.worst());
+    };
+    // explicit shared-window addresses: one register per array, bumped by 16 bytes per iteration
+    uint32_t ax = smem_u32(sx), ay = smem_u32(sy);
     const int n4 = (N + 3) >> 2;
 #pragma unroll 2
-    for (int j4 = 0; j4 < n4; ++j4) {
-        const float4 X = px[j4];
-        const float4 Y = py[j4];
-        const int j = j4 << 2;
-        float d0 = pair_d2<PER>(x, y, X.x, Y.x, B);
-        float d1 = pair_d2<PER>(x, y, X.y, Y.y, B);
-        float d2 = pair_d2<PER>(x, y, X.z, Y.z, B);
-        float d3 = pair_d2<PER>(x, y, X.w, Y.w, B);
-        d0 = (j == i) ? kInf : d0;
-        d1 = (j + 1 == i) ? kInf : d1;
-        d2 = (j + 2 == i) ? kInf : d2;
-        d3 = (j + 3 == i) ? kInf : d3;
-        if (d0 < t.worst()) t.insert(d0, j);
-        if (d1 < t.worst()) t.insert(d1, j + 1);
-        if (d2 < t.worst()) t.insert(d2, j + 2);
-        if (d3 < t.worst()) t.insert(d3, j + 3);
+    for (int j4 = 0; j4 < n4; ++j4, ax += 16u, ay += 16u) {
+        const float4 X = lds128(ax);
+        const float4 Y = lds128(ay);
+        const float d0 = pair_d2<PER>(x, y, X.x, Y.x, B);
+        const float d1 = pair_d2<PER>(x, y, X.y, Y.y, B);
+        const float d2 = pair_d2<PER>(x, y, X.z, Y.z, B);
+        const float d3 = pair_d2<PER>(x, y, X.w, Y.w, B);
+        const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (__any_sync(kFull, m <= thr)) {
+            const int j = j4 << 2;
+            if (d0 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d0), (unsigned)j); ++cnt; }
+            if (d1 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d1), (unsigned)(j + 1)); ++cnt; }
+            if (d2 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d2), (unsigned)(j + 2)); ++cnt; }
+            if (d3 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d3), (unsigned)(j + 3)); ++cnt; }
+            if (__any_sync(kFull, cnt > kCandCap - 4)) merge();
+        }
     }
+    merge();
+}
+
+// Upper bound of the k-th smallest d2 of row i from a previous neighbour list (any k distinct valid
+// indices != i bound it): max over their CURRENT distances. Returns FLT_MAX when the list is not a
+// set of k distinct in-range indices (first use, foreign data), so a bad hint can never change the
+// result, only the speed.
+template <int K, bool PER>
+__device__ __forceinline__ float hint_bound(const int (&hint)[K], int k, int i, int N, const float* sx,
+                                            const float* sy, float x, float y, float B) {
+    bool ok = true;
+    float bound = 0.0f;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        if (s < k) {
+            const int j = hint[s];
+            const bool in = j >= 0 && j < N && j != i;
+            ok = ok && in;
+#pragma unroll
+            for (int u = 0; u < s; ++u) ok = ok && (hint[u] != j);
+            const int jj = in ? j : 0;
+            bound = fmaxf(bound, pair_d2<PER>(x, y, sx[jj], sy[jj], B));
+        }
+    }
+    return ok ? bound : kFltMax;
 }
 
 template <typename T, int MAXN>
@@ -148,25 +208,43 @@ __device__ __forceinline__ void write_obs_t(const Params& p, size_t idx, const f
         if (s < k) o[s] = dist[s];
 }
 
-// step, grid = (tiles per env, E).
+// step, grid = (tiles per env, E), blockDim.x = rows per tile.
 template <int V, int K, bool PER>
-__global__ void __launch_bounds__(kTileThreads) flock_step_tiled_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
     const int N = p.N, k = p.k;
     const int env = blockIdx.y, tile = blockIdx.x;
-    const int aw = (V == FLOCK_UWD) ? 1 : 2;
-    const TileSmem sm = carve(smem, N);
-    stage_env(p, sm, &bar, env, aw, true);
-
-    // integrate every agent of the env in shared memory; keep this thread's own row in registers
-    const int i = tile * kTileThreads + threadIdx.x;
+    const int rows = blockDim.x;
+    const TileSmem sm = carve(smem, N, V == FLOCK_UWD);
+    const int i = tile * rows + threadIdx.x;
     const bool has_row = i < N;
     const size_t base = (size_t)env * N;
+    // last step's neighbour list of this thread's row: the hint that bounds this step's k-th distance
+    int hint[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) hint[s] = (p.nn != nullptr && has_row && s < k) ? p.nn[(base + i) * k + s] : -1;
+    uint32_t ep = 0u, repoch = 0u;
+    if (V == FLOCK_UWD) {
+        ep = (uint32_t)p.ep_len[env];
+        repoch = p.reset_epoch[env];
+    }
+    stage_xy(p, sm, &bar, env);
+
+    // integrate every agent of the env in place in shared memory (headings / actions come straight
+    // from global, coalesced); keep this thread's own row in registers
     float x = 0.f, y = 0.f, h = 0.f, vx = 0.f, vy = 0.f;
-    for (int a = threadIdx.x; a < N; a += kTileThreads) {
-        float ax = sm.sx[a], ay = sm.sy[a], ah = sm.sh[a];
-        const float a0 = sm.sa[a * aw], a1 = (aw == 2) ? sm.sa[a * aw + 1] : 0.0f;
+#pragma unroll 4
+    for (int a = threadIdx.x; a < N; a += rows) {
+        float ax = sm.sx[a], ay = sm.sy[a], ah = p.h[base + a];
+        float a0, a1 = 0.0f;
+        if (V == FLOCK_UWD) {
+            a0 = p.actions[base + a];
+        } else {
+            const float2 act = reinterpret_cast<const float2*>(p.actions)[base + a];
+            a0 = act.x;
+            a1 = act.y;
+        }
         float nzu = 0.f, nzw = 0.f;
         if (V == FLOCK_UWD) {
             if (p.noise != nullptr) {
@@ -174,14 +252,14 @@ __global__ void __launch_bounds__(kTileThreads) flock_step_tiled_kernel(const __
                 nzu = nz.x;
                 nzw = nz.y;
             } else if (p.noise_std > 0.0f) {
-                act_noise(p, p.env_offset + env, a, (uint32_t)p.ep_len[env], p.reset_epoch[env], nzu, nzw);
+                act_noise(p, p.env_offset + env, a, ep, repoch, nzu, nzw);
             }
         }
         float avx, avy;
         integrate_agent<V>(p, a0, a1, nzu, nzw, ax, ay, ah, avx, avy);
         sm.sx[a] = ax;
         sm.sy[a] = ay;
-        sm.sh[a] = ah;
+        if (V == FLOCK_UWD) sm.sh[a] = ah;
         if (a == i) {
             x = ax; y = ay; h = ah; vx = avx; vy = avy;
         }
@@ -210,9 +288,11 @@ __global__ void __launch_bounds__(kTileThreads) flock_step_tiled_kernel(const __
 
     long long fx = 0;
     bool coll = false;
+    float thr = -1.0f;                      // rows past N never hit
+    if (has_row) thr = hint_bound<K, PER>(hint, k, i, N, sm.sx, sm.sy, x, y, p.B);
+    TopK<K> t;
+    knn_tiled<K, PER>(sm.sx, sm.sy, sm.cand + threadIdx.x, i, N, x, y, p.B, thr, t);
     if (has_row) {
-        TopK<K> t;
-        knn_tiled<K, PER>(sm.sx, sm.sy, i, N, x, y, p.B, t);
         float dist[K];
         coll = finish_row<K>(t, k, p.sensor_range, p.cd, dist);
         const size_t idx = base + i;
@@ -268,12 +348,12 @@ __global__ void __launch_bounds__(kTileThreads) flock_step_tiled_kernel(const __
 
 // reset, grid = E, one CTA per env, bounded rejection loop (gym_flock_v2.py:85-108)
 template <int K>
-__global__ void __launch_bounds__(kTileThreads) flock_reset_tiled_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, k = p.k;
     const int env = blockIdx.x;
     if (p.env_mask != nullptr && p.env_mask[env] == 0) return;
-    const TileSmem sm = carve(smem, N);
+    const TileSmem sm = carve(smem, N, true);
     const size_t base = (size_t)env * N;
     const size_t EN = (size_t)p.E * N;
     const uint32_t epoch = p.reset_epoch[env];
@@ -287,7 +367,7 @@ __global__ void __launch_bounds__(kTileThreads) flock_reset_tiled_kernel(const _
     }
     while (env_coll && attempts < max_att) {
         __syncthreads();
-        for (int a = threadIdx.x; a < N; a += kTileThreads) {
+        for (int a = threadIdx.x; a < N; a += blockDim.x) {
             float x, y, h;
             if (p.init_state != nullptr) {
                 x = p.init_state[base + a];
@@ -311,10 +391,13 @@ __global__ void __launch_bounds__(kTileThreads) flock_reset_tiled_kernel(const _
         attempts += 1;
         __syncthreads();
         int coll_any = 0;
-        for (int i = threadIdx.x; i < N; i += kTileThreads) {
+        for (int i0 = 0; i0 < N; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            const bool has_row = i < N;
             TopK<K> t;
-            const float x = sm.sx[i], y = sm.sy[i];
-            knn_tiled<K, false>(sm.sx, sm.sy, i, N, x, y, p.B, t);
+            const float x = sm.sx[has_row ? i : 0], y = sm.sy[has_row ? i : 0];
+            knn_tiled<K, false>(sm.sx, sm.sy, sm.cand + threadIdx.x, i, N, x, y, p.B, has_row ? kFltMax : -1.0f, t);
+            if (!has_row) continue;
             float dist[K];
             const bool coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
             coll_any |= coll ? 1 : 0;
@@ -358,35 +441,54 @@ __global__ void __launch_bounds__(kTileThreads) flock_reset_tiled_kernel(const _
 }
 
 // -------------------------------------------------------------------------------------------------
+// rows per CTA: balance the most loaded SM (its CTAs x rows), prefer larger tiles on ties
+static int choose_rows(int N, int E, int sm_count) {
+    int best = kMaxTileThreads;
+    long long best_cost = -1;
+    for (int r = kMaxTileThreads; r >= 128; r -= 32) {
+        const long long ctas = (long long)((N + r - 1) / r) * E;
+        const long long cost = ((ctas + sm_count - 1) / sm_count) * r;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = r;
+        }
+    }
+    if (N < best) best = (N + 31) & ~31;
+    return best;
+}
+
 template <int V, int K, bool PER>
-static cudaError_t launch_tiled_vkp(const Params& p, cudaStream_t s) {
-    const dim3 grid((p.N + kTileThreads - 1) / kTileThreads, p.E);
-    flock_step_tiled_kernel<V, K, PER><<<grid, kTileThreads, tiled_smem_bytes(p.N), s>>>(p);
+static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, cudaStream_t s) {
+    const int rows = choose_rows(p.N, p.E, sm_count);
+    const dim3 grid((p.N + rows - 1) / rows, p.E);
+    flock_step_tiled_kernel<V, K, PER><<<grid, rows, tiled_smem_bytes(p.N, rows, V == FLOCK_UWD), s>>>(p);
     return cudaGetLastError();
 }
 template <int V, bool PER>
-static cudaError_t launch_tiled_vp(const Params& p, cudaStream_t s) {
-    if (p.k <= 3) return launch_tiled_vkp<V, 3, PER>(p, s);
-    if (p.k == 4) return launch_tiled_vkp<V, 4, PER>(p, s);
-    return launch_tiled_vkp<V, 8, PER>(p, s);
+static cudaError_t launch_tiled_vp(const Params& p, int sm_count, cudaStream_t s) {
+    if (p.k <= 3) return launch_tiled_vkp<V, 3, PER>(p, sm_count, s);
+    if (p.k == 4) return launch_tiled_vkp<V, 4, PER>(p, sm_count, s);
+    return launch_tiled_vkp<V, 8, PER>(p, sm_count, s);
 }
 
-cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, cudaStream_t s) {
+cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int sm_count, cudaStream_t s) {
     switch (variant) {
         case FLOCK_V2:
-            return periodic ? launch_tiled_vp<FLOCK_V2, true>(p, s) : launch_tiled_vp<FLOCK_V2, false>(p, s);
+            return periodic ? launch_tiled_vp<FLOCK_V2, true>(p, sm_count, s)
+                            : launch_tiled_vp<FLOCK_V2, false>(p, sm_count, s);
         case FLOCK_UW:
-            return launch_tiled_vp<FLOCK_UW, false>(p, s);
+            return launch_tiled_vp<FLOCK_UW, false>(p, sm_count, s);
         default:
-            return launch_tiled_vp<FLOCK_UWD, false>(p, s);
+            return launch_tiled_vp<FLOCK_UWD, false>(p, sm_count, s);
     }
 }
 
 cudaError_t launch_reset_tiled(const Params& p, cudaStream_t s) {
-    const size_t smem = tiled_smem_bytes(p.N);
-    if (p.k <= 3) flock_reset_tiled_kernel<3><<<p.E, kTileThreads, smem, s>>>(p);
-    else if (p.k == 4) flock_reset_tiled_kernel<4><<<p.E, kTileThreads, smem, s>>>(p);
-    else flock_reset_tiled_kernel<8><<<p.E, kTileThreads, smem, s>>>(p);
+    const int rows = kMaxTileThreads;
+    const size_t smem = tiled_smem_bytes(p.N, rows, true);
+    if (p.k <= 3) flock_reset_tiled_kernel<3><<<p.E, rows, smem, s>>>(p);
+    else if (p.k == 4) flock_reset_tiled_kernel<4><<<p.E, rows, smem, s>>>(p);
+    else flock_reset_tiled_kernel<8><<<p.E, rows, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -396,7 +498,7 @@ static cudaError_t opt_in(Kern kern, size_t bytes) {
 }
 
 cudaError_t tiled_configure(int num_agents) {
-    const size_t b = tiled_smem_bytes(num_agents);
+    const size_t b = tiled_smem_bytes(num_agents, kMaxTileThreads, true);
     if (b <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaSuccess;
 #define FLOCK_OPT(V, K, PER) \
