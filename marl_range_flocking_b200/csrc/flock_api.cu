@@ -71,6 +71,8 @@ Params make_params(const flock_env* e, float dt) {
     p.rigid = c.rigid_boundary; p.env_offset = c.env_offset;
     p.G = c.num_agents <= 32 ? 32 / c.num_agents : 0;
     p.sstride = (c.num_agents + 3) & ~3;
+    p.g_magic = (65536 + c.num_agents - 1) / c.num_agents;
+    p.num_tasks = p.G > 0 ? (c.num_envs + p.G - 1) / p.G : 0;
     p.B = c.boundary;
     p.halfB = (float)((double)c.boundary / 2.0);
     p.sensor_range = c.sensor_range;

@@ -23,6 +23,8 @@ struct Params {
     int E, N, k, H;
     int rigid, env_offset;
     int G;        // envs per warp (small path)
+    int g_magic;  // ceil(65536 / N): lane / N == (lane * g_magic) >> 16 for lane < 32
+    int num_tasks;  // ceil(E / G)
     int sstride;  // shared-memory stride of one env group, floats (small path)
     float B, halfB, sensor_range, cd, cd4, vmax, noise_std, dt;
     float range_lo, reset_hi, heading_hi, reset_cd;
@@ -49,6 +51,13 @@ struct Params {
     unsigned long long* stats;
     unsigned int* tile_scratch;   // tiled path: [E] CTA arrival counters, [E] collision counters (self-resetting)
 };
+
+// Programmatic dependent launch (PDL): a step kernel lets the NEXT kernel of the stream start
+// launching immediately (its index prologue overlaps our execution) and itself waits for the
+// previous kernel's memory before the first global access. No-ops when the launch does not carry
+// the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // Canonical transcendental functions (same DEFINITION as oracle/flock_oracle.c, separate code).
@@ -323,32 +332,54 @@ __device__ __forceinline__ bool finish_row(const TopK<K>& t, int k, float sensor
     return coll;
 }
 
-// reward of one agent (v2: gym_flock_v2.py:217-220,268; uw: gym_flock_uw.py:186-221;
-// uwd: gym_flock_uw_discrete.py:234-276). prev_h is the value BEFORE this step's update.
+// Reward as a function of the agent's threshold flags, so that the per-agent value and the
+// per-class constants used by the episode-return sum come from the same float operations.
+//   v2  (gym_flock_v2.py:217-220,268):           coll ? -5 : 0.01
+//   uw  (gym_flock_uw.py:186-221):  f1 = near the centre of mass, f2 = heading changed > 0.27
+//   uwd (gym_flock_uw_discrete.py:234-276):      f1 = heading farther than 0.20 from the mean
 template <int V>
-__device__ __forceinline__ float agent_reward(const Params& p, bool coll, float x, float y, float h,
-                                              float prev_h, float comx, float comy, float hmean) {
+__device__ __forceinline__ float reward_from_flags(bool coll, bool f1, bool f2) {
     if (V == FLOCK_V2) {
         return coll ? -5.0f : 0.01f;
     } else if (V == FLOCK_UW) {
         const float pen = coll ? -5.0f : 0.01f;
-        const float ddx = x - comx, ddy = y - comy;
-        float q = ddx * ddx;
-        const float q2 = ddy * ddy;
-        q = q + q2;
-        const float dc = __fsqrt_rn(q);
-        const float rcom = dc < p.cd4 ? 0.01f : 0.0f;
-        const float diff = fabsf(prev_h - h);
-        const float rang = diff > 0.27f ? -0.01f : 0.001f;
+        const float rcom = f1 ? 0.01f : 0.0f;
+        const float rang = f2 ? -0.01f : 0.001f;
         float r = pen + rcom;
         r = r + rang;
         return r;
     } else {
         const float pen = coll ? -9.0f : 0.0f;
-        const float err = fabsf(hmean - h);
-        const float ral = err > 0.20f ? 0.0f : 0.1f;
+        const float ral = f1 ? 0.0f : 0.1f;
         return pen + ral;
     }
+}
+
+// threshold flags of one agent; prev_h is the value BEFORE this step's update
+template <int V>
+__device__ __forceinline__ void reward_flags(const Params& p, float x, float y, float h, float prev_h, float comx,
+                                             float comy, float hmean, bool& f1, bool& f2) {
+    f1 = false;
+    f2 = false;
+    if (V == FLOCK_UW) {
+        const float ddx = x - comx, ddy = y - comy;
+        float q = ddx * ddx;
+        const float q2 = ddy * ddy;
+        q = q + q2;
+        const float dc = __fsqrt_rn(q);
+        f1 = dc < p.cd4;
+        f2 = fabsf(prev_h - h) > 0.27f;
+    } else if (V == FLOCK_UWD) {
+        f1 = fabsf(hmean - h) > 0.20f;
+    }
+}
+
+template <int V>
+__device__ __forceinline__ float agent_reward(const Params& p, bool coll, float x, float y, float h,
+                                              float prev_h, float comx, float comy, float hmean) {
+    bool f1, f2;
+    reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);
+    return reward_from_flags<V>(coll, f1, f2);
 }
 
 // reward in 2^-32 fixed point (order-free integer accumulation of episode returns)

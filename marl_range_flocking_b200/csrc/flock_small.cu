@@ -6,6 +6,8 @@
 // and the all-pairs loop reads them back as broadcast float4 (4 neighbours per LDS.128 pair);
 // the per-row k-smallest list lives in registers. One launch = one env step
 // (integrate -> wrap -> all-pairs range -> k-NN -> collisions/dones -> reward -> obs).
+#include <cstdlib>
+
 #include "flock_device.cuh"
 #include "flock_launch.h"
 
@@ -21,10 +23,10 @@ struct LaneMap {
     unsigned gmask;
 };
 
-__device__ __forceinline__ LaneMap lane_map(int lane, int N, int G) {
+__device__ __forceinline__ LaneMap lane_map(int lane, int N, int G, int g_magic) {
     LaneMap m;
     m.lane_ok = lane < G * N;
-    m.g = m.lane_ok ? lane / N : 0;
+    m.g = m.lane_ok ? (lane * g_magic) >> 16 : 0;      // lane / N without the integer divide
     m.a = m.lane_ok ? lane - m.g * N : 0;
     const unsigned ones = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
     m.gmask = m.lane_ok ? (ones << (m.g * N)) : (1u << lane);
@@ -84,15 +86,30 @@ __device__ __forceinline__ void write_obs(const Params& p, size_t idx, const flo
         if (s < k) o[s] = dist[s];
 }
 
-// sum of the episode-return increments of one env group (integer, order free) via REDUX
-__device__ __forceinline__ long long group_sum_fx(unsigned gmask, long long fx) {
-    const unsigned lo = (unsigned)fx & 0xffffu;
-    const unsigned mid = (unsigned)(fx >> 16) & 0xffffu;
-    const int hi = (int)(fx >> 32);
-    const unsigned slo = __reduce_add_sync(gmask, lo);
-    const unsigned smid = __reduce_add_sync(gmask, mid);
-    const int shi = __reduce_add_sync(gmask, hi);
-    return ((long long)shi << 32) + ((long long)smid << 16) + (long long)slo;
+// Sum over one env group of reward_fx(reward), order free and exact: rewards take at most 8 values
+// (one per combination of threshold flags), so the sum is sum_c popc(lanes of class c) * fx(class c)
+// with compile-time class constants -- three ballots instead of a 64-bit segmented reduction.
+// Must be called by ALL 32 lanes (full-mask ballots; lanes without an agent pass false flags).
+template <int V>
+__device__ __forceinline__ long long group_return_fx(unsigned gmask, bool coll, bool f1, bool f2, unsigned& bc_out) {
+    const unsigned bc = __ballot_sync(0xffffffffu, coll) & gmask;
+    bc_out = bc;
+    if (V == FLOCK_V2) {
+        const int nc = __popc(bc), n = __popc(gmask);
+        return (long long)nc * reward_fx(reward_from_flags<V>(true, false, false)) +
+               (long long)(n - nc) * reward_fx(reward_from_flags<V>(false, false, false));
+    }
+    const unsigned b1 = __ballot_sync(0xffffffffu, f1) & gmask;
+    const unsigned b2 = (V == FLOCK_UW) ? (__ballot_sync(0xffffffffu, f2) & gmask) : 0u;
+    long long sum = 0;
+#pragma unroll
+    for (int c = 0; c < ((V == FLOCK_UW) ? 8 : 4); ++c) {
+        const bool cc = c & 1, c1 = c & 2, c2 = c & 4;
+        unsigned m = (cc ? bc : ~bc) & (c1 ? b1 : ~b1) & gmask;
+        if (V == FLOCK_UW) m &= (c2 ? b2 : ~b2);
+        sum += (long long)__popc(m) * reward_fx(reward_from_flags<V>(cc, c1, c2));
+    }
+    return sum;
 }
 
 // all-pairs range + k-NN of row `a` against the staged positions of its env group
@@ -148,10 +165,12 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     float* sy = s_stage[wib][1];
     float* sh = s_stage[wib][2];
     const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
-    const LaneMap m = lane_map(lane, N, G);
-    const int num_tasks = (p.E + G - 1) / G;
+    pdl_launch_dependents();
+    const LaneMap m = lane_map(lane, N, G, p.g_magic);
+    const int num_tasks = p.num_tasks;
     const int warps_total = gridDim.x * kSmallWarps;
     const int nsteps = MULTI ? p.num_steps : 1;
+    pdl_wait_prior_grid();
 
     for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
         const int env = task * G + m.g;
@@ -232,6 +251,8 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             stage_xy(sx, sy, m, N, sstride, live, x, y);
             if (V == FLOCK_UWD && m.lane_ok) sh[m.g * sstride + m.a] = h;
             __syncwarp();
+            bool f1 = false, f2 = false;
+            coll = false;
             if (live) {
                 const float* sxg = sx + m.g * sstride;
                 const float* syg = sy + m.g * sstride;
@@ -243,10 +264,9 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 if (V == FLOCK_UWD) hmean = __fdiv_rn(seq_sum(sh + m.g * sstride, N), (float)N);  // uwd:256
                 knn_small<K, PER>(sxg, syg, m.a, sstride, x, y, p.B, t);
                 coll = finish_row<K>(t, k, p.sensor_range, p.cd, dist);
-                rew = agent_reward<V>(p, coll, x, y, h, prev_h, comx, comy, hmean);
+                reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);
+                rew = reward_from_flags<V>(coll, f1, f2);
                 if (V == FLOCK_UW) prev_h = h;
-                env_coll = (__ballot_sync(m.gmask, coll) & m.gmask) != 0u;
-                ret_fx += group_sum_fx(m.gmask, reward_fx(rew));
                 if (MULTI && V == FLOCK_UW && st + 1 < nsteps) {
 #pragma unroll
                     for (int s = 3 * K - 1; s >= K; --s) hist[s] = hist[s - K];   // K-strided copy of the window
@@ -254,6 +274,10 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     for (int s = 0; s < K; ++s) hist[s] = dist[s];
                 }
             }
+            // env-level reductions: warp-wide ballots, each env reads its own lane group
+            unsigned bc;
+            ret_fx += group_return_fx<V>(m.gmask, live && coll, live && f1, live && f2, bc);
+            env_coll = bc != 0u;
         }
 
         if (live) {
@@ -305,8 +329,8 @@ __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const 
     float* sx = s_stage[wib][0];
     float* sy = s_stage[wib][1];
     const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
-    const LaneMap m = lane_map(lane, N, G);
-    const int num_tasks = (p.E + G - 1) / G;
+    const LaneMap m = lane_map(lane, N, G, p.g_magic);
+    const int num_tasks = p.num_tasks;
     const int warps_total = gridDim.x * kSmallWarps;
     const size_t EN = (size_t)p.E * N;
 
@@ -350,8 +374,13 @@ __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const 
             if (need) {   // whole group shares `need`
                 knn_small<K, false>(sx + m.g * sstride, sy + m.g * sstride, m.a, sstride, x, y, p.B, t);  // Euclidean, v2:100
                 coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
-                env_coll = (__ballot_sync(m.gmask, coll) & m.gmask) != 0u;
-                need = env_coll && (int)attempts < max_att;
+            }
+            {
+                const unsigned bc = __ballot_sync(0xffffffffu, need && coll) & m.gmask;   // full-mask ballot
+                if (need) {
+                    env_coll = bc != 0u;
+                    need = env_coll && (int)attempts < max_att;
+                }
             }
         }
         if (live) {
@@ -426,7 +455,7 @@ __global__ void flock_debug_philox_kernel(const uint32_t* ck, int n, uint32_t* o
 // host-side dispatch
 // -------------------------------------------------------------------------------------------------
 static int small_grid(const Params& p, int sm_count) {
-    const int tasks = (p.E + p.G - 1) / p.G;
+    const int tasks = p.num_tasks;
     const int blocks = (tasks + kSmallWarps - 1) / kSmallWarps;
     const int cap = sm_count * 16;     // 16 resident 128-thread CTAs per SM
     return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
@@ -435,9 +464,30 @@ static int small_grid(const Params& p, int sm_count) {
 template <int V, int K, bool PER>
 static cudaError_t launch_step_small_vkp(const Params& p, bool multi, int sm_count, cudaStream_t s) {
     const int grid = small_grid(p, sm_count);
-    if (multi) flock_step_small_kernel<V, K, PER, true><<<grid, kSmallThreads, 0, s>>>(p);
-    else flock_step_small_kernel<V, K, PER, false><<<grid, kSmallThreads, 0, s>>>(p);
-    return cudaGetLastError();
+    if (multi) {
+        flock_step_small_kernel<V, K, PER, true><<<grid, kSmallThreads, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+    static const bool use_pdl = [] {
+        const char* v = getenv("FLOCK_PDL");
+        return v != nullptr && v[0] == '1';
+    }();
+    if (!use_pdl) {
+        flock_step_small_kernel<V, K, PER, false><<<grid, kSmallThreads, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+    // opt-in (FLOCK_PDL=1): programmatic dependent launch, back-to-back steps overlap launch latency
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kSmallThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false>, p);
 }
 
 template <int V, bool PER>

@@ -229,9 +229,11 @@ class VecEnv:
         return int(self.lib.flock_launch_count(self._h))
 
     # ---- the environment API -----------------------------------------------------------------
-    def reset(self, mask: Optional[torch.Tensor] = None, init_state: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def reset(self, mask: Optional[torch.Tensor] = None, init_state: Optional[torch.Tensor] = None,
+              keep_outputs: bool = False) -> torch.Tensor:
         """Batched `reset()`. `mask`: (E,) bool, only those envs; `init_state`: (3, E, N) x/y/heading
-        to install instead of drawing (parity injection)."""
+        to install instead of drawing (parity injection); `keep_outputs`: leave reward / dones of the
+        step that ended the episode untouched (auto-reset semantics)."""
         m = None
         if mask is not None:
             m = mask.to(device=self.device).reshape(self.num_envs)
@@ -240,8 +242,8 @@ class VecEnv:
         ini = None if init_state is None else self._as_input(init_state, (3, self.num_envs, self.num_particles), "init_state")
         with self._dev_guard():
             check(self.lib.flock_reset(self._h, None if m is None else m.data_ptr(),
-                                       None if ini is None else ini.data_ptr(), self.max_reset_attempts, 0,
-                                       self._stream()))
+                                       None if ini is None else ini.data_ptr(), self.max_reset_attempts,
+                                       _lib.FLOCK_RESET_KEEP_OUTPUTS if keep_outputs else 0, self._stream()))
         return self.observation
 
     def step(self, actions, dt: float = 0.1, noise=None):
