@@ -112,13 +112,30 @@ __device__ __forceinline__ long long group_return_fx(unsigned gmask, bool coll, 
     return sum;
 }
 
-// all-pairs range + k-NN of row `a` against the staged positions of its env group
-template <int K, bool PER>
-__device__ __forceinline__ void knn_small(const float* sxg, const float* syg, int a, int sstride, float x, float y,
-                                          float B, TopK<K>& t) {
+// all-pairs range + k-NN of row `a` against the staged positions of its env group.
+// NJ4 > 0: the stride is 4*NJ4 floats and the loop is fully unrolled (straight-line code, padding
+// slots of the last group skipped by warp-uniform branches); NJ4 == 0: generic runtime loop.
+template <int K, bool PER, int NJ4>
+__device__ __forceinline__ void knn_small(const float* sxg, const float* syg, int a, int N, int sstride, float x,
+                                          float y, float B, TopK<K>& t) {
     t.init();
     const float4* px = reinterpret_cast<const float4*>(sxg);
     const float4* py = reinterpret_cast<const float4*>(syg);
+    if (NJ4 > 0) {
+#pragma unroll
+        for (int j4 = 0; j4 < NJ4; ++j4) {
+            const float4 X = px[j4];
+            const float4 Y = py[j4];
+            const int j = j4 << 2;
+            const bool last = j4 == NJ4 - 1;
+            float d;
+            d = pair_d2<PER>(x, y, X.x, Y.x, B); d = (j == a) ? kInf : d; t.insert(d, j);
+            if (!last || j + 1 < N) { d = pair_d2<PER>(x, y, X.y, Y.y, B); d = (j + 1 == a) ? kInf : d; t.insert(d, j + 1); }
+            if (!last || j + 2 < N) { d = pair_d2<PER>(x, y, X.z, Y.z, B); d = (j + 2 == a) ? kInf : d; t.insert(d, j + 2); }
+            if (!last || j + 3 < N) { d = pair_d2<PER>(x, y, X.w, Y.w, B); d = (j + 3 == a) ? kInf : d; t.insert(d, j + 3); }
+        }
+        return;
+    }
     const int n4 = sstride >> 2;
     for (int j4 = 0; j4 < n4; ++j4) {
         const float4 X = px[j4];
@@ -157,7 +174,7 @@ __device__ __forceinline__ float seq_sum(const float* s, int N) {
 // gym_flock_uw_discrete.py:110-122). NSTEPS > 1 (flock_step_n) keeps the state in registers and
 // draws the canonical random actions in-kernel.
 // -------------------------------------------------------------------------------------------------
-template <int V, int K, bool PER, bool MULTI>
+template <int V, int K, bool PER, bool MULTI, int NJ4>
 __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const __grid_constant__ Params p) {
     __shared__ __align__(16) float s_stage[kSmallWarps][3][kSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -165,7 +182,6 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     float* sy = s_stage[wib][1];
     float* sh = s_stage[wib][2];
     const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
-    pdl_launch_dependents();
     const LaneMap m = lane_map(lane, N, G, p.g_magic);
     const int num_tasks = p.num_tasks;
     const int warps_total = gridDim.x * kSmallWarps;
@@ -262,7 +278,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     comy = __fdiv_rn(seq_sum(syg, N), (float)N);
                 }
                 if (V == FLOCK_UWD) hmean = __fdiv_rn(seq_sum(sh + m.g * sstride, N), (float)N);  // uwd:256
-                knn_small<K, PER>(sxg, syg, m.a, sstride, x, y, p.B, t);
+                knn_small<K, PER, NJ4>(sxg, syg, m.a, N, sstride, x, y, p.B, t);
                 coll = finish_row<K>(t, k, p.sensor_range, p.cd, dist);
                 reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);
                 rew = reward_from_flags<V>(coll, f1, f2);
@@ -280,6 +296,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             env_coll = bc != 0u;
         }
 
+        pdl_launch_dependents();   // the next kernel may start launching while we store the results
         if (live) {
             p.xo[idx] = x;
             p.yo[idx] = y;
@@ -372,7 +389,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const 
             stage_xy(sx, sy, m, N, sstride, live, x, y);
             __syncwarp();
             if (need) {   // whole group shares `need`
-                knn_small<K, false>(sx + m.g * sstride, sy + m.g * sstride, m.a, sstride, x, y, p.B, t);  // Euclidean, v2:100
+                knn_small<K, false, 0>(sx + m.g * sstride, sy + m.g * sstride, m.a, N, sstride, x, y, p.B, t);  // Euclidean, v2:100
                 coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
             }
             {
@@ -383,6 +400,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const 
                 }
             }
         }
+        pdl_launch_dependents();   // the next kernel may start launching while we store the results
         if (live) {
             p.xo[idx] = x;
             p.yo[idx] = y;
@@ -461,22 +479,23 @@ static int small_grid(const Params& p, int sm_count) {
     return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
 }
 
-template <int V, int K, bool PER>
-static cudaError_t launch_step_small_vkp(const Params& p, bool multi, int sm_count, cudaStream_t s) {
+template <int V, int K, bool PER, int NJ4>
+static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_count, cudaStream_t s) {
     const int grid = small_grid(p, sm_count);
     if (multi) {
-        flock_step_small_kernel<V, K, PER, true><<<grid, kSmallThreads, 0, s>>>(p);
+        flock_step_small_kernel<V, K, PER, true, NJ4><<<grid, kSmallThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
+    // Programmatic dependent launch (default on, FLOCK_PDL=0 disables): the kernel triggers its
+    // dependents right before its epilogue, so the next step's launch overlaps our result stores.
     static const bool use_pdl = [] {
         const char* v = getenv("FLOCK_PDL");
-        return v != nullptr && v[0] == '1';
+        return v == nullptr || v[0] != '0';
     }();
     if (!use_pdl) {
-        flock_step_small_kernel<V, K, PER, false><<<grid, kSmallThreads, 0, s>>>(p);
+        flock_step_small_kernel<V, K, PER, false, NJ4><<<grid, kSmallThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
-    // opt-in (FLOCK_PDL=1): programmatic dependent launch, back-to-back steps overlap launch latency
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kSmallThreads);
@@ -487,7 +506,18 @@ static cudaError_t launch_step_small_vkp(const Params& p, bool multi, int sm_cou
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false>, p);
+    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4>, p);
+}
+
+// unrolled pair loops for the strides of the BASELINE configs (N = 9..12, 13..16, 29..32)
+template <int V, int K, bool PER>
+static cudaError_t launch_step_small_vkp(const Params& p, bool multi, int sm_count, cudaStream_t s) {
+    switch (p.sstride) {
+        case 12: return launch_step_small_vkpn<V, K, PER, 3>(p, multi, sm_count, s);
+        case 16: return launch_step_small_vkpn<V, K, PER, 4>(p, multi, sm_count, s);
+        case 32: return launch_step_small_vkpn<V, K, PER, 8>(p, multi, sm_count, s);
+        default: return launch_step_small_vkpn<V, K, PER, 0>(p, multi, sm_count, s);
+    }
 }
 
 template <int V, bool PER>
