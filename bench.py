@@ -106,7 +106,9 @@ def cpu_run(w, steps, warmup, budget_s, nthreads=None):
     """Time `steps` oracle steps on a bounded sample of the workload's envs; returns a dict."""
     from oracle import flock_oracle as fo
 
-    threads = nthreads or fo.max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle sets the
+    # OpenMP team size explicitly, so that default does not apply)
+    threads = nthreads or len(os.sched_getaffinity(0)) or fo.max_threads()
     E_full = w["E"]
     # calibrate the sample size so that warmup+steps fit the time budget
     probe_E = min(E_full, max(threads * 4, 64))
