@@ -378,8 +378,9 @@ def run_gpu(args, w):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the committed
-# ncu --set full captures under profiles/ (None until measured)
-TRAFFIC_PER_LAUNCH = {}
+# ncu --set full captures (profiles/r01_cfg2_step_small_raw.txt, r01_cfg5_step_tiled_raw.txt); the
+# result stores of one launch are still in L2 when the capture ends, so writes read ~0.
+TRAFFIC_PER_LAUNCH = {"cfg2": 883200, "cfg5": 6857472}
 
 
 def main():

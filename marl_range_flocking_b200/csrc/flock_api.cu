@@ -2,6 +2,7 @@
 // parameter marshalling and kernel dispatch. No torch types, no exceptions across the boundary.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -39,6 +40,9 @@ struct flock_env {
     float* stage_actions;  // device staging for host-call / step_n(tiled) actions
     float* stage_noise;
     unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
+    const void* zc_host[5];       // last host buffers seen by flock_step_host and their device aliases
+    void* zc_dev[5];
+    bool zc_ok;
     size_t action_floats;
 };
 
@@ -110,10 +114,24 @@ int check_bound(const flock_env* e) {
     return FLOCK_OK;
 }
 
-int step_device(flock_env* e, const float* actions, float dt, const float* noise, cudaStream_t s) {
+struct HostMirrors {
+    float* obs = nullptr;
+    float* reward = nullptr;
+    uint8_t* agent_done = nullptr;
+    uint8_t* env_done = nullptr;
+};
+
+int step_device(flock_env* e, const float* actions, float dt, const float* noise, cudaStream_t s,
+                const HostMirrors* mirrors = nullptr) {
     Params p = make_params(e, dt);
     p.actions = actions;
     p.noise = noise;
+    if (mirrors != nullptr) {
+        p.m_obs = mirrors->obs;
+        p.m_reward = mirrors->reward;
+        p.m_agent_done = mirrors->agent_done;
+        p.m_env_done = mirrors->env_done;
+    }
     cudaError_t err;
     if (e->path == 0) {
         err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
@@ -125,6 +143,42 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
     }
     if (err != cudaSuccess) return cuda_fail(err, "step kernel launch");
     e->step_index += 1;
+    return FLOCK_OK;
+}
+
+int copy_results_to_host(flock_env* e, float* h_obs, float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done,
+                         cudaStream_t s) {
+    const size_t EN = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+    cudaError_t err = cudaSuccess;
+    // When the caller laid obs | reward | agent_done | env_done out back to back on BOTH sides (the
+    // Python host does), the four results travel as one D2H copy instead of four.
+    const size_t obs_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float);
+    const size_t rew_bytes = EN * sizeof(float);
+    const char* d0 = reinterpret_cast<const char*>(e->b.obs);
+    char* h0 = reinterpret_cast<char*>(h_obs);
+    const bool packed = h_obs && h_reward && h_agent_done && h_env_done &&
+                        reinterpret_cast<const char*>(e->b.reward) == d0 + obs_bytes &&
+                        reinterpret_cast<const char*>(e->b.agent_done) == d0 + obs_bytes + rew_bytes &&
+                        reinterpret_cast<const char*>(e->b.env_done) == d0 + obs_bytes + rew_bytes + EN &&
+                        reinterpret_cast<char*>(h_reward) == h0 + obs_bytes &&
+                        reinterpret_cast<char*>(h_agent_done) == h0 + obs_bytes + rew_bytes &&
+                        reinterpret_cast<char*>(h_env_done) == h0 + obs_bytes + rew_bytes + EN;
+    if (packed) {
+        err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes + rew_bytes + EN + (size_t)e->cfg.num_envs,
+                              cudaMemcpyDeviceToHost, s);
+    } else {
+        if (h_obs != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes, cudaMemcpyDeviceToHost, s);
+        if (h_reward != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_reward, e->b.reward, rew_bytes, cudaMemcpyDeviceToHost, s);
+        if (h_agent_done != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_agent_done, e->b.agent_done, EN, cudaMemcpyDeviceToHost, s);
+        if (h_env_done != nullptr && err == cudaSuccess)
+            err = cudaMemcpyAsync(h_env_done, e->b.env_done, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s);
+    }
+    if (err != cudaSuccess) return cuda_fail(err, "D2H outputs");
+    err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) return cuda_fail(err, "stream synchronize");
     return FLOCK_OK;
 }
 
@@ -271,6 +325,55 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
     if (h_actions == nullptr) return fail(FLOCK_E_INVALID, "h_actions is NULL");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t EN = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+    // Zero-copy fast path: when every host buffer is pinned (device-visible under UVA) the kernel
+    // reads the actions from and writes the results to host memory itself -- no staging copies, the
+    // PCIe traffic overlaps the kernel, one synchronisation per step.
+    if (h_obs && h_reward && h_agent_done && h_env_done && (h_noise == nullptr || e->cfg.variant != FLOCK_UWD)) {
+        const void* hp[5] = {h_actions, h_obs, h_reward, h_agent_done, h_env_done};
+        bool same = true;
+        for (int i = 0; i < 5; ++i) same = same && (hp[i] == e->zc_host[i]);
+        if (!same) {
+            e->zc_ok = true;
+            for (int i = 0; i < 5; ++i) {
+                cudaPointerAttributes a;
+                cudaError_t pe = cudaPointerGetAttributes(&a, hp[i]);
+                if (pe != cudaSuccess || a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) {
+                    cudaGetLastError();
+                    e->zc_ok = false;
+                    break;
+                }
+                e->zc_dev[i] = a.devicePointer;
+            }
+            for (int i = 0; i < 5; ++i) e->zc_host[i] = hp[i];
+        }
+        // Policy (measured on B200, profiles/README.md): SM-posted writes to host memory beat a DMA
+        // copy only while the result set is small (latency bound); large result sets move faster by
+        // DMA. The tiled path re-reads actions once per CTA, so it always stages.
+        static const int zc_mode = [] {   // FLOCK_ZEROCOPY = 0 (never) | 1 (always) | unset (auto)
+            const char* v = getenv("FLOCK_ZEROCOPY");
+            return v == nullptr ? 2 : (v[0] == '0' ? 0 : 1);
+        }();
+        const size_t out_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float) + EN * 5 + (size_t)e->cfg.num_envs;
+        const bool zc_inputs = e->zc_ok && e->path == 0 && zc_mode != 0;
+        const bool zc_outputs = zc_inputs && (zc_mode == 1 || out_bytes <= (size_t)3 << 20);
+        if (zc_outputs) {
+            HostMirrors mir;
+            mir.obs = static_cast<float*>(e->zc_dev[1]);
+            mir.reward = static_cast<float*>(e->zc_dev[2]);
+            mir.agent_done = static_cast<uint8_t*>(e->zc_dev[3]);
+            mir.env_done = static_cast<uint8_t*>(e->zc_dev[4]);
+            rc = step_device(e, static_cast<const float*>(e->zc_dev[0]), dt, nullptr, s, &mir);
+            if (rc != FLOCK_OK) return rc;
+            cudaError_t se = cudaStreamSynchronize(s);
+            if (se != cudaSuccess) return cuda_fail(se, "stream synchronize");
+            return FLOCK_OK;
+        }
+        if (zc_inputs) {   // actions read in place, results by one packed DMA copy below
+            rc = step_device(e, static_cast<const float*>(e->zc_dev[0]), dt, nullptr, s);
+            if (rc != FLOCK_OK) return rc;
+            return copy_results_to_host(e, h_obs, h_reward, h_agent_done, h_env_done, s);
+        }
+    }
     cudaError_t err = cudaMemcpyAsync(e->stage_actions, h_actions, e->action_floats * sizeof(float),
                                       cudaMemcpyHostToDevice, s);
     if (err != cudaSuccess) return cuda_fail(err, "H2D actions");
@@ -282,36 +385,7 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
     }
     rc = step_device(e, e->stage_actions, dt, d_noise, s);
     if (rc != FLOCK_OK) return rc;
-    // When the caller laid obs | reward | agent_done | env_done out back to back on BOTH sides (the
-    // Python host does), the four results travel as one D2H copy instead of four.
-    const size_t obs_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float);
-    const size_t rew_bytes = EN * sizeof(float);
-    const char* d0 = reinterpret_cast<const char*>(e->b.obs);
-    char* h0 = reinterpret_cast<char*>(h_obs);
-    const bool packed = h_obs && h_reward && h_agent_done && h_env_done &&
-                        reinterpret_cast<const char*>(e->b.reward) == d0 + obs_bytes &&
-                        reinterpret_cast<const char*>(e->b.agent_done) == d0 + obs_bytes + rew_bytes &&
-                        reinterpret_cast<const char*>(e->b.env_done) == d0 + obs_bytes + rew_bytes + EN &&
-                        reinterpret_cast<char*>(h_reward) == h0 + obs_bytes &&
-                        reinterpret_cast<char*>(h_agent_done) == h0 + obs_bytes + rew_bytes &&
-                        reinterpret_cast<char*>(h_env_done) == h0 + obs_bytes + rew_bytes + EN;
-    if (packed) {
-        err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes + rew_bytes + EN + (size_t)e->cfg.num_envs,
-                              cudaMemcpyDeviceToHost, s);
-    } else {
-        if (h_obs != nullptr && err == cudaSuccess)
-            err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes, cudaMemcpyDeviceToHost, s);
-        if (h_reward != nullptr && err == cudaSuccess)
-            err = cudaMemcpyAsync(h_reward, e->b.reward, rew_bytes, cudaMemcpyDeviceToHost, s);
-        if (h_agent_done != nullptr && err == cudaSuccess)
-            err = cudaMemcpyAsync(h_agent_done, e->b.agent_done, EN, cudaMemcpyDeviceToHost, s);
-        if (h_env_done != nullptr && err == cudaSuccess)
-            err = cudaMemcpyAsync(h_env_done, e->b.env_done, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s);
-    }
-    if (err != cudaSuccess) return cuda_fail(err, "D2H outputs");
-    err = cudaStreamSynchronize(s);
-    if (err != cudaSuccess) return cuda_fail(err, "stream synchronize");
-    return FLOCK_OK;
+    return copy_results_to_host(e, h_obs, h_reward, h_agent_done, h_env_done, s);
 }
 
 int flock_state_slot(const flock_env_t* e) { return e ? e->slot : 0; }

@@ -50,6 +50,11 @@ struct Params {
     int32_t* ep_len;
     unsigned long long* stats;
     unsigned int* tile_scratch;   // tiled path: [E] CTA arrival counters, [E] collision counters (self-resetting)
+    // host-call path: device-visible HOST mirrors of the step results (zero-copy), nullable
+    float* m_obs;
+    float* m_reward;
+    uint8_t* m_agent_done;
+    uint8_t* m_env_done;
 };
 
 // Programmatic dependent launch (PDL): a step kernel lets the NEXT kernel of the stream start

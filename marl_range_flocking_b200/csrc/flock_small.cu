@@ -331,6 +331,24 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = ep_ret0 + ret_fx;
                 p.ep_len[env] = (int)ep0 + nsteps;
             }
+            if (!MULTI && p.m_obs != nullptr) {
+                // host-call path: the results also go straight to mapped host memory (posted PCIe
+                // writes overlap the rest of the kernel; no separate device->host copy)
+                if (fast_win) {
+                    float4* o4 = reinterpret_cast<float4*>(p.m_obs + idx * 12);
+                    o4[0] = make_float4(dist[0], dist[1], dist[2 % K], w0.x);
+                    o4[1] = make_float4(w0.y, w0.z, w0.w, w1.x);
+                    o4[2] = make_float4(w1.y, w1.z, w1.w, w2.x);
+                } else if (p.H == 1) {
+                    store_row<float, K>(p.m_obs + idx * k, dist, k);
+                } else {
+                    const size_t hk = (size_t)p.H * k;
+                    for (size_t u = 0; u < hk; ++u) p.m_obs[idx * hk + u] = p.obs[idx * hk + u];
+                }
+                p.m_reward[idx] = rew;
+                p.m_agent_done[idx] = coll ? 1 : 0;
+                if (m.a == 0) p.m_env_done[env] = env_coll ? 1 : 0;
+            }
         }
     }
 }

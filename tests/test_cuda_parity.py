@@ -388,3 +388,26 @@ def test_single_env_facade_matches_oracle_trajectory():
         assert_same("reward", rew[:, 0], orc.reward[0])
         assert done[1] == bool(orc.env_done[0])
         assert_same("nn", env.nearest_neighbors.int(), orc.nn[0])
+
+
+@pytest.mark.parametrize("variant,N,k", [("v2", 10, 4), ("uw", 32, 3), ("uw", 12, 4), ("uwd", 16, 4), ("v2", 64, 4)])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_zero_copy_and_staged_paths(variant, N, k, pinned):
+    """flock_step_host: pinned host buffers take the zero-copy path (kernel reads actions from and
+    writes results to mapped host memory), pageable ones the staged-copy path; both must equal the
+    device path bit for bit."""
+    E = 96
+    env, orc = make_pair(variant, E, N, k, 0.5, (0, 100), 9.0, seed=21)
+    env.reset()
+    orc.reset()
+    for t in range(4):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        ta = torch.from_numpy(a.copy())
+        obs, rew, (ad, ed), _ = env.step_host(ta.pin_memory() if pinned else ta, 0.1)
+        want_obs = orc.obs if env.obs_hist > 1 else orc.obs[:, :, 0, :]
+        assert_same("host obs", obs, want_obs)
+        assert_same("host reward", rew[..., 0], orc.reward)
+        assert_same("host agent_done", ad.to(torch.uint8), orc.agent_done)
+        assert_same("host env_done", ed.to(torch.uint8), orc.env_done)
+    compare_all(env, orc, tag="host path:")
