@@ -115,12 +115,26 @@ __device__ __forceinline__ long long group_return_fx(unsigned gmask, bool coll, 
 // all-pairs range + k-NN of row `a` against the staged positions of its env group.
 // NJ4 > 0: the stride is 4*NJ4 floats and the loop is fully unrolled (straight-line code, padding
 // slots of the last group skipped by warp-uniform branches); NJ4 == 0: generic runtime loop.
-template <int K, bool PER, int NJ4>
+// SUMS: also accumulate the sequential (agent order) float32 sums of x and y that the uw centre of
+// mass needs (gym_flock_uw.py:193) from the values the loop loads anyway.
+template <int K, bool PER, int NJ4, bool SUMS>
 __device__ __forceinline__ void knn_small(const float* sxg, const float* syg, int a, int N, int sstride, float x,
-                                          float y, float B, TopK<K>& t) {
+                                          float y, float B, TopK<K>& t, float& sumx, float& sumy) {
     t.init();
+    sumx = 0.0f;
+    sumy = 0.0f;
     const float4* px = reinterpret_cast<const float4*>(sxg);
     const float4* py = reinterpret_cast<const float4*>(syg);
+#define FLOCK_PAIR(XC, YC, JJ)                          \
+    {                                                   \
+        float d = pair_d2<PER>(x, y, XC, YC, B);        \
+        d = ((JJ) == a) ? kInf : d;                     \
+        t.insert(d, (JJ));                              \
+        if (SUMS) {                                     \
+            sumx = sumx + (XC);                         \
+            sumy = sumy + (YC);                         \
+        }                                               \
+    }
     if (NJ4 > 0) {
 #pragma unroll
         for (int j4 = 0; j4 < NJ4; ++j4) {
@@ -128,11 +142,10 @@ __device__ __forceinline__ void knn_small(const float* sxg, const float* syg, in
             const float4 Y = py[j4];
             const int j = j4 << 2;
             const bool last = j4 == NJ4 - 1;
-            float d;
-            d = pair_d2<PER>(x, y, X.x, Y.x, B); d = (j == a) ? kInf : d; t.insert(d, j);
-            if (!last || j + 1 < N) { d = pair_d2<PER>(x, y, X.y, Y.y, B); d = (j + 1 == a) ? kInf : d; t.insert(d, j + 1); }
-            if (!last || j + 2 < N) { d = pair_d2<PER>(x, y, X.z, Y.z, B); d = (j + 2 == a) ? kInf : d; t.insert(d, j + 2); }
-            if (!last || j + 3 < N) { d = pair_d2<PER>(x, y, X.w, Y.w, B); d = (j + 3 == a) ? kInf : d; t.insert(d, j + 3); }
+            FLOCK_PAIR(X.x, Y.x, j)
+            if (!last || j + 1 < N) FLOCK_PAIR(X.y, Y.y, j + 1)
+            if (!last || j + 2 < N) FLOCK_PAIR(X.z, Y.z, j + 2)
+            if (!last || j + 3 < N) FLOCK_PAIR(X.w, Y.w, j + 3)
         }
         return;
     }
@@ -141,12 +154,13 @@ __device__ __forceinline__ void knn_small(const float* sxg, const float* syg, in
         const float4 X = px[j4];
         const float4 Y = py[j4];
         const int j = j4 << 2;
-        float d;
-        d = pair_d2<PER>(x, y, X.x, Y.x, B); d = (j == a) ? kInf : d; t.insert(d, j);
-        d = pair_d2<PER>(x, y, X.y, Y.y, B); d = (j + 1 == a) ? kInf : d; t.insert(d, j + 1);
-        d = pair_d2<PER>(x, y, X.z, Y.z, B); d = (j + 2 == a) ? kInf : d; t.insert(d, j + 2);
-        d = pair_d2<PER>(x, y, X.w, Y.w, B); d = (j + 3 == a) ? kInf : d; t.insert(d, j + 3);
+        const bool last = j4 == n4 - 1;
+        FLOCK_PAIR(X.x, Y.x, j)
+        if (!last || j + 1 < N) FLOCK_PAIR(X.y, Y.y, j + 1)
+        if (!last || j + 2 < N) FLOCK_PAIR(X.z, Y.z, j + 2)
+        if (!last || j + 3 < N) FLOCK_PAIR(X.w, Y.w, j + 3)
     }
+#undef FLOCK_PAIR
 }
 
 // stage one value per lane plus +inf / 0 padding up to the group stride
@@ -162,10 +176,20 @@ __device__ __forceinline__ void stage_xy(float* sx, float* sy, const LaneMap& m,
     }
 }
 
-// sequential float32 sum over the env's agents (canonical order 0..N-1)
+// sequential float32 sum over the env's agents (canonical order 0..N-1), 128-bit shared loads;
+// s is 16-byte aligned and readable up to the next multiple of 4
 __device__ __forceinline__ float seq_sum(const float* s, int N) {
     float acc = 0.0f;
-    for (int j = 0; j < N; ++j) acc = acc + s[j];
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    const int n4 = (N + 3) >> 2;
+    for (int j4 = 0; j4 < n4; ++j4) {
+        const float4 v = s4[j4];
+        const int j = j4 << 2;
+        acc = acc + v.x;
+        if (j + 1 < N) acc = acc + v.y;
+        if (j + 2 < N) acc = acc + v.z;
+        if (j + 3 < N) acc = acc + v.w;
+    }
     return acc;
 }
 
@@ -188,10 +212,17 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     const int nsteps = MULTI ? p.num_steps : 1;
     pdl_wait_prior_grid();
 
+    const int GN = G * N;
+    const unsigned EN = (unsigned)p.E * (unsigned)N;
     for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
+        // the warp's agents are one contiguous run: index = task*G*N + lane, so the loads below can
+        // issue after two integer operations (the env / agent split is only needed later).
+        // (Prefetching the warp's next task with two tasks per warp was measured slower on B200 for
+        // all BASELINE configs: at these batch sizes more resident warps beat software pipelining.)
+        const unsigned flat = (unsigned)task * (unsigned)GN + (unsigned)lane;
+        const bool live = lane < GN && flat < EN;
+        const size_t idx = live ? flat : 0u;
         const int env = task * G + m.g;
-        const bool live = m.lane_ok && env < p.E;
-        const size_t idx = (size_t)(live ? env : 0) * N + m.a;
         float x = 0.f, y = 0.f, h = 0.f, prev_h = 0.f;
         float prev_h_in = 0.f;
         uint32_t ep0 = 0u, repoch = 0u;   // per-env Philox epoch (episode step, reset epoch)
@@ -272,13 +303,13 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             if (live) {
                 const float* sxg = sx + m.g * sstride;
                 const float* syg = sy + m.g * sstride;
-                float comx = 0.f, comy = 0.f, hmean = 0.f;
-                if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
-                    comx = __fdiv_rn(seq_sum(sxg, N), (float)N);
-                    comy = __fdiv_rn(seq_sum(syg, N), (float)N);
-                }
+                float comx = 0.f, comy = 0.f, hmean = 0.f, sumx, sumy;
                 if (V == FLOCK_UWD) hmean = __fdiv_rn(seq_sum(sh + m.g * sstride, N), (float)N);  // uwd:256
-                knn_small<K, PER, NJ4>(sxg, syg, m.a, N, sstride, x, y, p.B, t);
+                knn_small<K, PER, NJ4, V == FLOCK_UW>(sxg, syg, m.a, N, sstride, x, y, p.B, t, sumx, sumy);
+                if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
+                    comx = __fdiv_rn(sumx, (float)N);
+                    comy = __fdiv_rn(sumy, (float)N);
+                }
                 coll = finish_row<K>(t, k, p.sensor_range, p.cd, dist);
                 reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);
                 rew = reward_from_flags<V>(coll, f1, f2);
@@ -407,7 +438,9 @@ __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const 
             stage_xy(sx, sy, m, N, sstride, live, x, y);
             __syncwarp();
             if (need) {   // whole group shares `need`
-                knn_small<K, false, 0>(sx + m.g * sstride, sy + m.g * sstride, m.a, N, sstride, x, y, p.B, t);  // Euclidean, v2:100
+                float unused_sx, unused_sy;
+                knn_small<K, false, 0, false>(sx + m.g * sstride, sy + m.g * sstride, m.a, N, sstride, x, y, p.B, t,
+                                              unused_sx, unused_sy);  // Euclidean, v2:100
                 coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
             }
             {
