@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflock_b200.so")
+# FLOCK_LIBRARY_PATH lets a developer A/B an alternative build of the same ABI (still a CUDA library)
+LIB_PATH = os.environ.get("FLOCK_LIBRARY_PATH") or os.path.join(_HERE, "libflock_b200.so")
 
 FLOCK_ABI_VERSION = 1
 FLOCK_MAX_K = 8

@@ -13,7 +13,7 @@
 
 namespace flock {
 
-constexpr int kSmallThreads = 128;
+constexpr int kSmallThreads = 64;    // 64-thread CTAs measured best (8.27 vs 8.43 us on cfg3, 7.57 vs 7.89 on cfg4)
 constexpr int kSmallWarps = kSmallThreads / kWarp;
 constexpr int kSlots = 64;  // floats per staged array per warp: G * roundup(N,4) <= 64
 
@@ -176,20 +176,11 @@ __device__ __forceinline__ void stage_xy(float* sx, float* sy, const LaneMap& m,
     }
 }
 
-// sequential float32 sum over the env's agents (canonical order 0..N-1), 128-bit shared loads;
-// s is 16-byte aligned and readable up to the next multiple of 4
+// sequential float32 sum over the env's agents (canonical order 0..N-1); the scalar loop measured
+// faster than a 128-bit-load version with tail guards
 __device__ __forceinline__ float seq_sum(const float* s, int N) {
     float acc = 0.0f;
-    const float4* s4 = reinterpret_cast<const float4*>(s);
-    const int n4 = (N + 3) >> 2;
-    for (int j4 = 0; j4 < n4; ++j4) {
-        const float4 v = s4[j4];
-        const int j = j4 << 2;
-        acc = acc + v.x;
-        if (j + 1 < N) acc = acc + v.y;
-        if (j + 2 < N) acc = acc + v.z;
-        if (j + 3 < N) acc = acc + v.w;
-    }
+    for (int j = 0; j < N; ++j) acc = acc + s[j];
     return acc;
 }
 
@@ -198,7 +189,9 @@ __device__ __forceinline__ float seq_sum(const float* s, int N) {
 // gym_flock_uw_discrete.py:110-122). NSTEPS > 1 (flock_step_n) keeps the state in registers and
 // draws the canonical random actions in-kernel.
 // -------------------------------------------------------------------------------------------------
-template <int V, int K, bool PER, bool MULTI, int NJ4>
+// MIRROR: also write the results to device-visible host memory (flock_step_host zero-copy path);
+// a separate instantiation because even the untaken branch costs 3 % in the plain kernel.
+template <int V, int K, bool PER, bool MULTI, int NJ4, bool MIRROR>
 __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const __grid_constant__ Params p) {
     __shared__ __align__(16) float s_stage[kSmallWarps][3][kSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -362,7 +355,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = ep_ret0 + ret_fx;
                 p.ep_len[env] = (int)ep0 + nsteps;
             }
-            if (!MULTI && p.m_obs != nullptr) {
+            if (MIRROR) {
                 // host-call path: the results also go straight to mapped host memory (posted PCIe
                 // writes overlap the rest of the kernel; no separate device->host copy)
                 if (fast_win) {
@@ -526,7 +519,7 @@ __global__ void flock_debug_philox_kernel(const uint32_t* ck, int n, uint32_t* o
 static int small_grid(const Params& p, int sm_count) {
     const int tasks = p.num_tasks;
     const int blocks = (tasks + kSmallWarps - 1) / kSmallWarps;
-    const int cap = sm_count * 16;     // 16 resident 128-thread CTAs per SM
+    const int cap = sm_count * 32;     // 32 resident 64-thread CTAs per SM
     return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
 }
 
@@ -534,9 +527,10 @@ template <int V, int K, bool PER, int NJ4>
 static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_count, cudaStream_t s) {
     const int grid = small_grid(p, sm_count);
     if (multi) {
-        flock_step_small_kernel<V, K, PER, true, NJ4><<<grid, kSmallThreads, 0, s>>>(p);
+        flock_step_small_kernel<V, K, PER, true, NJ4, false><<<grid, kSmallThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
+    const bool mirror = p.m_obs != nullptr;
     // Programmatic dependent launch (default on, FLOCK_PDL=0 disables): the kernel triggers its
     // dependents right before its epilogue, so the next step's launch overlaps our result stores.
     static const bool use_pdl = [] {
@@ -544,7 +538,8 @@ static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_co
         return v == nullptr || v[0] != '0';
     }();
     if (!use_pdl) {
-        flock_step_small_kernel<V, K, PER, false, NJ4><<<grid, kSmallThreads, 0, s>>>(p);
+        if (mirror) flock_step_small_kernel<V, K, PER, false, NJ4, true><<<grid, kSmallThreads, 0, s>>>(p);
+        else flock_step_small_kernel<V, K, PER, false, NJ4, false><<<grid, kSmallThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -557,7 +552,8 @@ static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_co
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4>, p);
+    if (mirror) return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, true>, p);
+    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, false>, p);
 }
 
 // unrolled pair loops for the strides of the BASELINE configs (N = 9..12, 13..16, 29..32)

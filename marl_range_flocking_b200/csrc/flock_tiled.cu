@@ -312,12 +312,6 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
         p.reward[idx] = rew;
         p.agent_done[idx] = coll ? 1 : 0;
-        if (p.m_obs != nullptr) {   // host-call path: mirror the results into mapped host memory
-            const size_t hk = (size_t)p.H * k;
-            for (size_t u = 0; u < hk; ++u) p.m_obs[idx * hk + u] = p.obs[idx * hk + u];
-            p.m_reward[idx] = rew;
-            p.m_agent_done[idx] = coll ? 1 : 0;
-        }
     }
     // env-level reductions. The episode return is an order-free integer sum. env_done and the
     // episode-step counter are published by the LAST CTA of the env to finish (arrival counter), so
@@ -346,7 +340,6 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
             __threadfence();
             const unsigned c = atomicExch(collide, 0u);
             p.env_done[env] = c != 0u ? 1 : 0;
-            if (p.m_env_done != nullptr) p.m_env_done[env] = c != 0u ? 1 : 0;
             p.ep_len[env] += 1;
             *arrive = 0u;
         }
