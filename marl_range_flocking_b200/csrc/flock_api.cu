@@ -87,6 +87,8 @@ Params make_params(const flock_env* e, float dt) {
     p.dt = dt;
     p.range_lo = c.range_lo; p.reset_hi = c.reset_hi; p.heading_hi = c.heading_hi;
     p.reset_cd = c.reset_collision_distance;
+    p.fill_hi = c.rigid_boundary ? c.boundary : 0.001f;
+    p.fill_lo = c.rigid_boundary ? 0.0f : c.boundary;
     p.seed_lo = (uint32_t)c.seed; p.seed_hi = (uint32_t)(c.seed >> 32);
     p.step_offset = 0;
     p.num_steps = 1;

@@ -28,6 +28,7 @@ struct Params {
     int sstride;  // shared-memory stride of one env group, floats (small path)
     float B, halfB, sensor_range, cd, cd4, vmax, noise_std, dt;
     float range_lo, reset_hi, heading_hi, reset_cd;
+    float fill_hi, fill_lo;   // check_boundary replacement values (see wrap_coord)
     uint32_t seed_lo, seed_hi, step_offset;   // step_offset: flock_random_actions look-ahead
     int num_steps;      // step_n
     int max_attempts;   // reset
@@ -173,15 +174,13 @@ __device__ __forceinline__ float nan_to_num(float v) {
     return (v != v) ? 0.0f : t;
 }
 
-// check_boundary per coordinate (gym_flock_v2.py:271-304)
-__device__ __forceinline__ float wrap_coord(float c, float B, int rigid) {
-    if (rigid) {
-        c = (c < B) ? c : B;
-        c = (c > 0.0f) ? c : 0.0f;
-    } else {
-        c = (c < B) ? c : 0.001f;
-        c = (c > 0.0f) ? c : B;
-    }
+// check_boundary per coordinate (gym_flock_v2.py:271-304): both modes are
+//   c = (c < B) ? c : fill_hi;  c = (c > 0) ? c : fill_lo
+// with (fill_hi, fill_lo) = (0.001, B) for the default wrap (:292-304) and (B, 0) for the rigid
+// boundary (:273-289); the host passes the two fill values, so the kernel has no mode branch.
+__device__ __forceinline__ float wrap_coord(float c, float B, float fill_hi, float fill_lo) {
+    c = (c < B) ? c : fill_hi;
+    c = (c > 0.0f) ? c : fill_lo;
     return c;
 }
 
@@ -238,8 +237,8 @@ __device__ __forceinline__ void integrate_agent(const Params& p, float a0, float
     vy = vy * dt;
     x = x + vx;
     y = y + vy;
-    x = wrap_coord(x, p.B, p.rigid);
-    y = wrap_coord(y, p.B, p.rigid);
+    x = wrap_coord(x, p.B, p.fill_hi, p.fill_lo);
+    y = wrap_coord(y, p.B, p.fill_hi, p.fill_lo);
 }
 
 // Philox stream layout: key = seed; counter = (global env, agent, episode step, tag + 4*reset_epoch).

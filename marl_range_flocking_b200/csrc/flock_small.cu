@@ -38,6 +38,10 @@ template <typename T, int MAXN>
 __device__ __forceinline__ void store_row(T* dst, const T (&v)[MAXN], int n) {
     static_assert(sizeof(T) == 4, "4-byte elements");
     struct alignas(16) Vec4 { T a, b, c, d; };
+    if constexpr (MAXN == 4) {   // K = 4 is only instantiated for k == 4: always one 16-byte store
+        reinterpret_cast<Vec4*>(dst)[0] = Vec4{v[0], v[1], v[2], v[3]};
+        return;
+    }
     if constexpr (MAXN >= 8) {
         if (n == 8) {
             reinterpret_cast<Vec4*>(dst)[0] = Vec4{v[0], v[1], v[2], v[3]};
@@ -344,6 +348,8 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 o4[0] = make_float4(dist[0], dist[1], dist[2 % K], w0.x);
                 o4[1] = make_float4(w0.y, w0.z, w0.w, w1.x);
                 o4[2] = make_float4(w1.y, w1.z, w1.w, w2.x);
+            } else if (V != FLOCK_UW) {
+                store_row<float, K>(p.obs + idx * k, dist, k);      // H == 1
             } else {
                 write_obs<K>(p, idx, dist, false);
             }
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     o4[0] = make_float4(dist[0], dist[1], dist[2 % K], w0.x);
                     o4[1] = make_float4(w0.y, w0.z, w0.w, w1.x);
                     o4[2] = make_float4(w1.y, w1.z, w1.w, w2.x);
-                } else if (p.H == 1) {
+                } else if (V != FLOCK_UW) {
                     store_row<float, K>(p.m_obs + idx * k, dist, k);
                 } else {
                     const size_t hk = (size_t)p.H * k;
@@ -423,8 +429,8 @@ __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const 
                     const float th = (0.0f - p.heading_hi) * u24(r.z);  // gym_flock_v2.py:96
                     h = th + p.heading_hi;
                 }
-                x = wrap_coord(x, p.B, p.rigid);                      // check_boundary, v2:99
-                y = wrap_coord(y, p.B, p.rigid);
+                x = wrap_coord(x, p.B, p.fill_hi, p.fill_lo);                      // check_boundary, v2:99
+                y = wrap_coord(y, p.B, p.fill_hi, p.fill_lo);
                 attempts += 1;
             }
             __syncwarp();

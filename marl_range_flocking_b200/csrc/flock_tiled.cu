@@ -138,6 +138,7 @@ __device__ __forceinline__ void knn_tiled(const float* sx, const float* sy, uint
         const float d3 = pair_d2<PER>(x, y, X.w, Y.w, B);
         const float m = fminf(fminf(d0, d1), fminf(d2, d3));
         if (__any_sync(kFull, m <= thr)) {
+            // (one vote per candidate instead of four predicated appends was measured slower)
             const int j = j4 << 2;
             if (d0 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d0), (unsigned)j); ++cnt; }
             if (d1 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d1), (unsigned)(j + 1)); ++cnt; }
@@ -384,8 +385,8 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(cons
                 const float th = (0.0f - p.heading_hi) * u24(r.z);
                 h = th + p.heading_hi;
             }
-            sm.sx[a] = wrap_coord(x, p.B, p.rigid);
-            sm.sy[a] = wrap_coord(y, p.B, p.rigid);
+            sm.sx[a] = wrap_coord(x, p.B, p.fill_hi, p.fill_lo);
+            sm.sy[a] = wrap_coord(y, p.B, p.fill_hi, p.fill_lo);
             sm.sh[a] = h;
         }
         attempts += 1;
