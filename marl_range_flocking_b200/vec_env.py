@@ -16,8 +16,12 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
+import contextlib
+
 from . import _lib
 from ._lib import FlockBuffers, FlockCfg, VARIANT_IDS, check
+
+_NULL_GUARD = contextlib.nullcontext()
 
 # reference per-variant constants
 _HEADING_HI = {"v2": math.pi * 1.5, "uw": math.pi * 2, "uwd": math.pi / 1.2}   # v2:96, uw:92, uwd:133
@@ -115,6 +119,10 @@ class VecEnv:
             ptr(self._ep_len), ptr(self._stats))
         check(self.lib.flock_bind(self._h, ctypes.byref(bufs)))
         self._host = None   # pinned host mirrors for step_host
+        self._dev_index = self.device.index
+        self._numel_cache = {}
+        self._act_shape = (E, N) if variant == "uwd" else (E, N, 2)
+        self._obs_view = self._obs if self.obs_hist > 1 else self._obs[:, :, 0, :]
 
     # ------------------------------------------------------------------------------------------
     def _alloc_outputs(self, device, pin: bool = False):
@@ -141,20 +149,30 @@ class VecEnv:
         self.__del__()
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        # raw handle of torch's current stream on our device (follows stream contexts and graph capture)
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def _slot(self) -> int:
         return self.lib.flock_state_slot(self._h) if self.tiled else 0
 
     def _dev_guard(self):
+        # kernels must be launched with our device current; the common single-GPU-per-process case
+        # needs no switch at all
+        if torch.cuda.current_device() == self._dev_index:
+            return _NULL_GUARD
         return torch.cuda.device(self.device)
 
     def _as_input(self, t, shape, name) -> torch.Tensor:
+        # fast path: already a contiguous float32 tensor of the right size on our device
+        if (type(t) is torch.Tensor and t.dtype is torch.float32 and t.device == self.device and t.is_contiguous()
+                and t.numel() == self._numel_cache.get(shape, -1)):
+            return t
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
         t = t.to(device=self.device, dtype=torch.float32)
         if t.numel() != math.prod(shape):
             raise ValueError(f"{name} has {t.numel()} elements, expected shape {tuple(shape)}")
+        self._numel_cache[shape] = math.prod(shape)
         return t.reshape(shape).contiguous()
 
     # ---- views of the device state (zero copy; overwritten by the next step) ------------------
@@ -251,19 +269,19 @@ class VecEnv:
 
         Returns `(obs, reward (E,N,1), (agent_done (E,N) bool, env_done (E,) bool), {})`; all are
         views of env-owned device tensors."""
-        E, N = self.num_envs, self.num_particles
-        a = self._as_input(actions, (E, N) if self.variant == "uwd" else (E, N, 2), "actions")
-        nz = None if noise is None else self._as_input(noise, (E, N, 2), "noise")
+        a = self._as_input(actions, self._act_shape, "actions")
+        nz = None if noise is None else self._as_input(noise, (self.num_envs, self.num_particles, 2), "noise")
         with self._dev_guard():
-            check(self.lib.flock_step(self._h, a.data_ptr(), float(dt), None if nz is None else nz.data_ptr(),
-                                      self._stream()))
+            rc = self.lib.flock_step(self._h, a.data_ptr(), dt, None if nz is None else nz.data_ptr(), self._stream())
+            if rc:
+                check(rc)
             info: Dict = {}
             if self.auto_reset:
                 # finished envs restart in place; reward / dones of the finishing step are kept and
                 # the returned obs of those envs is the first observation of the new episode
                 check(self.lib.flock_reset(self._h, self._env_done.data_ptr(), None, self.max_reset_attempts,
                                            _lib.FLOCK_RESET_KEEP_OUTPUTS, self._stream()))
-        return self.observation, self._reward, (self._agent_done, self._env_done), info
+        return self._obs_view, self._reward, (self._agent_done, self._env_done), info
 
     def step_n(self, num_steps: int, dt: float = 0.1):
         """`num_steps` steps with the canonical in-kernel random actions (one persistent launch when N <= 32)."""
@@ -285,7 +303,9 @@ class VecEnv:
         E, N = self.num_envs, self.num_particles
         if self._host is None:
             slab, (o, r, ad, ed) = self._alloc_outputs(None, pin=True)
-            self._host = dict(slab=slab, obs=o, reward=r, agent_done=ad, env_done=ed)
+            self._host = dict(slab=slab, obs=o, reward=r, agent_done=ad, env_done=ed,
+                              ptrs=(o.data_ptr(), r.data_ptr(), ad.data_ptr(), ed.data_ptr()),
+                              ret=(o if self.obs_hist > 1 else o[:, :, 0, :], r, (ad, ed), {}))
         if actions_cpu.device.type != "cpu" or actions_cpu.dtype != torch.float32 or not actions_cpu.is_contiguous():
             raise ValueError("step_host wants a contiguous float32 CPU tensor")
         want = E * N * (1 if self.variant == "uwd" else 2)
@@ -293,12 +313,11 @@ class VecEnv:
             raise ValueError(f"actions has {actions_cpu.numel()} elements, expected {want}")
         hb = self._host
         with self._dev_guard():
-            check(self.lib.flock_step_host(self._h, actions_cpu.data_ptr(), float(dt),
-                                           None if noise_cpu is None else noise_cpu.data_ptr(),
-                                           hb["obs"].data_ptr(), hb["reward"].data_ptr(), hb["agent_done"].data_ptr(),
-                                           hb["env_done"].data_ptr(), self._stream()))
-        obs = hb["obs"] if self.obs_hist > 1 else hb["obs"][:, :, 0, :]
-        return obs, hb["reward"], (hb["agent_done"], hb["env_done"]), {}
+            rc = self.lib.flock_step_host(self._h, actions_cpu.data_ptr(), dt,
+                                          None if noise_cpu is None else noise_cpu.data_ptr(), *hb["ptrs"], self._stream())
+            if rc:
+                check(rc)
+        return hb["ret"]
 
     # ---- checkpoint / injection --------------------------------------------------------------
     def get_state(self) -> Dict[str, torch.Tensor]:
