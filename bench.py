@@ -348,6 +348,22 @@ def run_gpu(args, w):
         per_launch_s = ms_max * 1e-3 / steps
         alg_bytes = E * N * w["bytes"]
         achieved = alg_bytes / per_launch_s / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": TRAFFIC_PER_LAUNCH.get(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "achieved = algorithmic bytes / mean launch-to-launch time of the timed region"}
+        if envs[0].tiled:
+            # large swarms are FP32-pipe bound, not HBM bound: E*N*(N-1) pair evaluations x 9
+            # FP32 operations (no FMA: parity forbids contraction) against 128 lanes x SMs x max clock
+            props = torch.cuda.get_device_properties(device)
+            flops = E * N * (N - 1) * 9.0
+            peak_tf = props.multi_processor_count * 128 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+            ach_tf = flops / per_launch_s / 1e12
+            roof = {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                    "traffic": TRAFFIC_PER_LAUNCH.get(args.workload),
+                    "peak_source": "SMs x 128 FP32 lanes x max SM clock, one non-fused FP32 op per lane per clock",
+                    "algorithmic_flops_per_launch": flops,
+                    "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}}
         line = {
             "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak",
@@ -356,10 +372,7 @@ def run_gpu(args, w):
                        "l2_policy": f"inputs larger than L2: ring of {ring} independent env batches "
                                     f"({ring * bytes_per_batch / 2**20:.0f} MiB), step s touches batch s % {ring}",
                        "launch": "CUDA graph replay, one fused kernel per step, single stream"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_PER_LAUNCH.get(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "achieved = algorithmic bytes / mean launch-to-launch time of the timed region"},
+            "roofline": roof,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "VecEnv.step_host -> flock_step_host (pinned host buffers, sync per step)"},
