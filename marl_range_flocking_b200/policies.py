@@ -1,0 +1,146 @@
+"""Batched policy inference next to the env step ("next" scope, plain PyTorch).
+
+The reference evaluates one small network per agent in a Python loop
+(`learners/maddpg_shared_critic/train_flock.py:114-115`, `learners/vdn/net.py:27-37`). With E envs
+on the device that loop becomes one batched matrix multiply per layer over the agent dimension:
+weights of the N per-agent networks are stacked to `(N, in, out)` and applied to observations laid
+out `(N, E, in)` with `torch.baddbmm` (cuBLAS; library GEMMs are fine here -- this is not the
+env hot path). Parameters load from the reference's own `state_dict`s.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+def _stack(sds: Sequence[Dict[str, torch.Tensor]], key: str) -> torch.Tensor:
+    return torch.stack([sd[key] for sd in sds])
+
+
+class BatchedActors(torch.nn.Module):
+    """N per-agent DDPG actors (`ActorNetwork`, learners/maddpg_shared_critic/ddpg_network.py:85-141):
+    fc1 -> LayerNorm -> ReLU -> fc2 -> LayerNorm -> ReLU -> mu -> tanh, evaluated for all envs and
+    agents at once. `forward(obs)` takes `(E, N, ...)` observations (trailing dims are flattened, as
+    `obs.reshape(N, -1)` does upstream, train_flock.py:115) and returns `(E, N, n_actions)`."""
+
+    def __init__(self, num_agents: int, input_dims: int, fc1_dims: int = 400, fc2_dims: int = 300, n_actions: int = 2,
+                 device=None, dtype=torch.float32):
+        super().__init__()
+        kw = dict(device=device, dtype=dtype)
+        n = num_agents
+
+        def uni(shape, bound):
+            return torch.nn.Parameter(torch.empty(*shape, **kw).uniform_(-bound, bound))
+
+        f1, f2, f3 = fc1_dims ** -0.5, fc2_dims ** -0.5, 0.003          # ddpg_network.py:108-126
+        self.w1, self.b1 = uni((n, input_dims, fc1_dims), f1), uni((n, 1, fc1_dims), f1)
+        self.g1 = torch.nn.Parameter(torch.ones(n, 1, fc1_dims, **kw))
+        self.be1 = torch.nn.Parameter(torch.zeros(n, 1, fc1_dims, **kw))
+        self.w2, self.b2 = uni((n, fc1_dims, fc2_dims), f2), uni((n, 1, fc2_dims), f2)
+        self.g2 = torch.nn.Parameter(torch.ones(n, 1, fc2_dims, **kw))
+        self.be2 = torch.nn.Parameter(torch.zeros(n, 1, fc2_dims, **kw))
+        self.w3, self.b3 = uni((n, fc2_dims, n_actions), f3), uni((n, 1, n_actions), f3)
+        self.num_agents, self.input_dims = n, input_dims
+
+    @classmethod
+    def from_state_dicts(cls, sds: Sequence[Dict[str, torch.Tensor]], device=None, dtype=torch.float32):
+        """Build from N reference `ActorNetwork.state_dict()`s (keys fc1/bn1/fc2/bn2/mu .weight/.bias)."""
+        w1 = _stack(sds, "fc1.weight")
+        self = cls(len(sds), w1.shape[2], w1.shape[1], sds[0]["fc2.weight"].shape[0], sds[0]["mu.weight"].shape[0],
+                   device=device, dtype=dtype)
+        with torch.no_grad():
+            for wt, b, name in ((self.w1, self.b1, "fc1"), (self.w2, self.b2, "fc2"), (self.w3, self.b3, "mu")):
+                wt.copy_(_stack(sds, name + ".weight").transpose(1, 2))
+                b.copy_(_stack(sds, name + ".bias").unsqueeze(1))
+            for g, be, name in ((self.g1, self.be1, "bn1"), (self.g2, self.be2, "bn2")):
+                g.copy_(_stack(sds, name + ".weight").unsqueeze(1))
+                be.copy_(_stack(sds, name + ".bias").unsqueeze(1))
+        return self
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        E, N = obs.shape[0], obs.shape[1]
+        x = obs.reshape(E, N, -1).transpose(0, 1).to(self.w1.dtype)              # (N, E, in)
+        x = torch.baddbmm(self.b1, x, self.w1)
+        x = F.relu(F.layer_norm(x, x.shape[-1:]) * self.g1 + self.be1)
+        x = torch.baddbmm(self.b2, x, self.w2)
+        x = F.relu(F.layer_norm(x, x.shape[-1:]) * self.g2 + self.be2)
+        mu = torch.tanh(torch.baddbmm(self.b3, x, self.w3))
+        return mu.transpose(0, 1).float().contiguous()                           # (E, N, n_actions)
+
+
+class BatchedQNet(torch.nn.Module):
+    """The VDN per-agent Q networks (`QNet`, learners/vdn/net.py:11-37): Linear(n_obs,64)-ReLU-
+    Linear(64,32)-ReLU [-GRUCell(32,32)] -Linear(32,n_actions) per agent, batched over agents.
+    `forward(obs (E,N,n_obs), hidden (E,N,32)) -> (q (E,N,A), hidden)`; `sample_action` is the
+    epsilon-greedy of net.py:52-58 with the exploration decision per env, on the device."""
+
+    def __init__(self, num_agents: int, n_obs: int, n_actions: int, recurrent: bool = False, hx_size: int = 32,
+                 device=None, dtype=torch.float32):
+        super().__init__()
+        kw = dict(device=device, dtype=dtype)
+        n = num_agents
+
+        def lin(i, o):
+            bound = i ** -0.5
+            return (torch.nn.Parameter(torch.empty(n, i, o, **kw).uniform_(-bound, bound)),
+                    torch.nn.Parameter(torch.empty(n, 1, o, **kw).uniform_(-bound, bound)))
+
+        self.w1, self.b1 = lin(n_obs, 64)
+        self.w2, self.b2 = lin(64, hx_size)
+        self.wq, self.bq = lin(hx_size, n_actions)
+        self.recurrent, self.hx_size, self.num_agents = recurrent, hx_size, n
+        if recurrent:
+            self.w_ih, self.b_ih = lin(hx_size, 3 * hx_size)
+            self.w_hh, self.b_hh = lin(hx_size, 3 * hx_size)
+
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], num_agents: int, device=None, dtype=torch.float32):
+        """Load a reference `QNet.state_dict()` (keys agent_feature_i.{0,2}, agent_gru_i, agent_q_i)."""
+        rec = any(k.startswith("agent_gru_0") for k in sd)
+        n_obs = sd["agent_feature_0.0.weight"].shape[1]
+        self = cls(num_agents, n_obs, sd["agent_q_0.weight"].shape[0], rec, sd["agent_feature_0.2.weight"].shape[0],
+                   device=device, dtype=dtype)
+        per = lambda fmt: torch.stack([sd[fmt.format(i)] for i in range(num_agents)])
+        with torch.no_grad():
+            self.w1.copy_(per("agent_feature_{}.0.weight").transpose(1, 2)); self.b1.copy_(per("agent_feature_{}.0.bias").unsqueeze(1))
+            self.w2.copy_(per("agent_feature_{}.2.weight").transpose(1, 2)); self.b2.copy_(per("agent_feature_{}.2.bias").unsqueeze(1))
+            self.wq.copy_(per("agent_q_{}.weight").transpose(1, 2)); self.bq.copy_(per("agent_q_{}.bias").unsqueeze(1))
+            if rec:
+                self.w_ih.copy_(per("agent_gru_{}.weight_ih").transpose(1, 2)); self.b_ih.copy_(per("agent_gru_{}.bias_ih").unsqueeze(1))
+                self.w_hh.copy_(per("agent_gru_{}.weight_hh").transpose(1, 2)); self.b_hh.copy_(per("agent_gru_{}.bias_hh").unsqueeze(1))
+        return self
+
+    def init_hidden(self, batch_size: int = 1) -> torch.Tensor:
+        return torch.zeros(batch_size, self.num_agents, self.hx_size, device=self.w1.device)
+
+    def forward(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        x = obs.transpose(0, 1).to(self.w1.dtype)                                 # (N, E, n_obs)
+        x = F.relu(torch.baddbmm(self.b1, x, self.w1))
+        x = F.relu(torch.baddbmm(self.b2, x, self.w2))
+        if self.recurrent:
+            h = hidden.transpose(0, 1).to(x.dtype)
+            gi = torch.baddbmm(self.b_ih, x, self.w_ih)
+            gh = torch.baddbmm(self.b_hh, h, self.w_hh)
+            i_r, i_z, i_n = gi.chunk(3, dim=-1)
+            h_r, h_z, h_n = gh.chunk(3, dim=-1)
+            r = torch.sigmoid(i_r + h_r)
+            z = torch.sigmoid(i_z + h_z)
+            n = torch.tanh(i_n + r * h_n)
+            x = (1 - z) * n + z * h                                                # torch.nn.GRUCell
+            next_hidden = x.transpose(0, 1).float()
+        else:
+            next_hidden = torch.empty(obs.shape[0], self.num_agents, self.hx_size, device=obs.device)
+        q = torch.baddbmm(self.bq, x, self.wq).transpose(0, 1).float()             # (E, N, A)
+        return q, next_hidden
+
+    @torch.no_grad()
+    def sample_action(self, obs: torch.Tensor, hidden: Optional[torch.Tensor], epsilon: float,
+                      generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        q, hidden = self.forward(obs, hidden)
+        E, N, A = q.shape
+        explore = torch.rand(E, device=q.device, generator=generator) <= epsilon   # one decision per env, net.py:54
+        rand_a = torch.randint(0, A, (E, N), device=q.device, generator=generator)
+        action = torch.where(explore[:, None], rand_a, q.argmax(dim=2)).float()    # float-coded ids, net.py:56-57
+        return action, hidden

@@ -411,3 +411,24 @@ def test_step_host_zero_copy_and_staged_paths(variant, N, k, pinned):
         assert_same("host agent_done", ad.to(torch.uint8), orc.agent_done)
         assert_same("host env_done", ed.to(torch.uint8), orc.env_done)
     compare_all(env, orc, tag="host path:")
+
+
+def test_actor_rollout_into_device_replay():
+    """8f items 1-3 together: batched per-agent actors drive a uw VecEnv, transitions land in the
+    device-resident replay, nothing is read back until the statistics."""
+    from marl_range_flocking_b200 import VecEnv
+    from marl_range_flocking_b200.policies import BatchedActors
+    from marl_range_flocking_b200.replay import DeviceReplay
+    from marl_range_flocking_b200.rollout import collect
+    E, N, k, T = 64, 8, 3, 40
+    env = VecEnv("uw", E, N, k, 0.5, range_start=(0, 80), sensor_range=7, seed=4)
+    actors = BatchedActors(N, 4 * k, 64, 48, 2, device="cuda")
+    rb = DeviceReplay(E, N, 4 * k, 2, capacity_steps=T, device="cuda", chunk_size=10)
+    stats = collect(env, actors, T, max_episode_steps=15, sink=rb.add)
+    assert len(rb) == T * E and stats["episodes"] >= E * (T // 15)
+    s, r, ns, d, a_s, a_ns, a_a = rb.get_minibatch(32)
+    assert s.shape == (32, 10, N, 4 * k) and a_a.shape == (N, 32, 10, 2) and bool((a_a.abs() <= 1).all())
+    # the newest row of next_obs is the newest row of the following obs unless the episode ended in between
+    t = 5
+    cont = ~rb.episode_end[t]
+    assert torch.equal(rb.next_obs[t][cont], rb.obs[t + 1][cont])
