@@ -168,6 +168,11 @@ FLOCK_API uint64_t flock_launch_count(const flock_env_t *env);
 /* 0: warp-per-env-group path (N <= 32), 1: tiled path (N > 32). */
 FLOCK_API int flock_path(const flock_env_t *env);
 
+/* Kernel choice on the tiled path: 0 = automatic (default), 1 = one thread per row (many envs),
+ * 2 = one warp per row with a warp-shuffle bitonic top-k merge (few envs x large swarm). Results are
+ * identical bit for bit; only speed differs. */
+FLOCK_API int flock_set_tiled_mode(flock_env_t *env, int mode);
+
 FLOCK_API const char *flock_last_error(void);
 FLOCK_API int flock_abi_version(void);
 

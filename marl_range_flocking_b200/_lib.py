@@ -79,6 +79,7 @@ def load_library() -> ctypes.CDLL:
         "flock_set_step_index": (i32, [vp, u32]),
         "flock_launch_count": (u64, [vp]),
         "flock_path": (i32, [vp]),
+        "flock_set_tiled_mode": (i32, [vp, i32]),
         "flock_last_error": (ctypes.c_char_p, []),
         "flock_abi_version": (i32, []),
         "flock_debug_sincos": (i32, [vp, i32, vp, vp, vp]),

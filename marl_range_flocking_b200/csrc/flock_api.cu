@@ -35,6 +35,7 @@ struct flock_env {
     int sm_count;
     int path;            // 0 small, 1 tiled
     int slot;            // current state copy on the tiled path
+    int tiled_mode;      // 0 auto, 1 thread-per-row, 2 warp-per-row
     uint32_t step_index;
     uint64_t launches;
     float* stage_actions;  // device staging for host-call / step_n(tiled) actions
@@ -139,7 +140,7 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
         e->launches += 1;
     } else {
-        err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, e->sm_count, s);
+        err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, e->sm_count, e->tiled_mode, s);
         e->launches += 1;
         if (err == cudaSuccess) e->slot ^= 1;
     }
@@ -399,6 +400,12 @@ int flock_set_step_index(flock_env_t* e, uint32_t step_index) {
 }
 uint64_t flock_launch_count(const flock_env_t* e) { return e ? e->launches : 0ULL; }
 int flock_path(const flock_env_t* e) { return e ? e->path : 0; }
+int flock_set_tiled_mode(flock_env_t* e, int mode) {
+    if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
+    if (mode < 0 || mode > 2) return fail(FLOCK_E_INVALID, "tiled mode %d not in {0,1,2}", mode);
+    e->tiled_mode = mode;
+    return FLOCK_OK;
+}
 
 int flock_debug_sincos(const float* h, int n, float* sn, float* cs, void* stream) {
     cudaError_t err = flock::launch_debug_sincos(h, n, sn, cs, static_cast<cudaStream_t>(stream));

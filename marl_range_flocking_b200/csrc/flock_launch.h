@@ -17,6 +17,6 @@ cudaError_t launch_debug_philox(const uint32_t* ck, int n, uint32_t* out, cudaSt
 // flock_tiled.cu (N > 32)
 cudaError_t tiled_configure(int num_agents);   // opt in to the dynamic shared memory the env needs
 size_t tiled_smem_bytes(int num_agents, int rows, bool need_sh);
-cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int sm_count, cudaStream_t s);
+cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int sm_count, int tiled_mode, cudaStream_t s);
 cudaError_t launch_reset_tiled(const Params& p, cudaStream_t s);
 }  // namespace flock

@@ -8,6 +8,8 @@
 // concurrent CTAs of the same env still read the old state), then runs its rows against all j as
 // broadcast 128-bit shared-memory reads with a register-resident k-smallest list per row.
 // One launch = one env step, as on the small path.
+#include <cstdlib>
+
 #include "flock_device.cuh"
 #include "flock_launch.h"
 
@@ -347,6 +349,198 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Few envs x large swarm (fewer row tiles than SMs): one WARP per row instead of one thread per row.
+// Lane l scans neighbours j = l, l+32, ... into a private sorted k-list, then the 32 partial lists
+// are merged by a warp-shuffle bitonic top-k: five xor-butterfly rounds, each taking
+// min(mine[i], partner[K-1-i]) (a bitonic sequence holding the K smallest of both lists) and
+// re-sorting it with a log2(K)-stage bitonic network, on 64-bit keys (d2 bits << 32 | j) whose
+// unsigned order IS the canonical (d2, j) order, so ties resolve to the lower index across lanes.
+// grid = (row tiles, E), blockDim = 256 (8 warps), each warp handles `rows_per_warp` rows.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int K>
+__device__ __forceinline__ void warp_bitonic_topk(unsigned long long (&key)[K]) {
+    static_assert((K & (K - 1)) == 0, "K must be a power of two");
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        unsigned long long other[K];
+#pragma unroll
+        for (int s = 0; s < K; ++s) other[s] = shfl_xor_u64(key[s], m);
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            const unsigned long long o = other[K - 1 - s];
+            key[s] = o < key[s] ? o : key[s];
+        }
+#pragma unroll
+        for (int stride = K / 2; stride >= 1; stride >>= 1) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                if ((s & stride) == 0) {
+                    const unsigned long long a = key[s], b = key[s + stride];
+                    key[s] = a < b ? a : b;
+                    key[s + stride] = a < b ? b : a;
+                }
+            }
+        }
+    }
+}
+
+template <int V, int K, bool PER>
+__global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(const __grid_constant__ Params p,
+                                                                           int rows_per_warp) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int N = p.N, k = p.k;
+    const int env = blockIdx.y, tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int rows_per_cta = warps * rows_per_warp;
+    const int row0 = tile * rows_per_cta;
+    const TileSmem sm = carve(smem, N, true);
+    const size_t base = (size_t)env * N;
+    uint32_t ep = 0u, repoch = 0u;
+    if (V == FLOCK_UWD) {
+        ep = (uint32_t)p.ep_len[env];
+        repoch = p.reset_epoch[env];
+    }
+    stage_xy(p, sm, &bar, env);
+
+    // integrate every agent in place; the thread that integrates one of this CTA's rows also writes
+    // its state (other copy) and displacement
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        float ax = sm.sx[a], ay = sm.sy[a], ah = p.h[base + a];
+        float a0, a1 = 0.0f;
+        if (V == FLOCK_UWD) {
+            a0 = p.actions[base + a];
+        } else {
+            const float2 act = reinterpret_cast<const float2*>(p.actions)[base + a];
+            a0 = act.x;
+            a1 = act.y;
+        }
+        float nzu = 0.f, nzw = 0.f;
+        if (V == FLOCK_UWD) {
+            if (p.noise != nullptr) {
+                const float2 nz = reinterpret_cast<const float2*>(p.noise)[base + a];
+                nzu = nz.x;
+                nzw = nz.y;
+            } else if (p.noise_std > 0.0f) {
+                act_noise(p, p.env_offset + env, a, ep, repoch, nzu, nzw);
+            }
+        }
+        float avx, avy;
+        integrate_agent<V>(p, a0, a1, nzu, nzw, ax, ay, ah, avx, avy);
+        sm.sx[a] = ax;
+        sm.sy[a] = ay;
+        sm.sh[a] = ah;
+        if (a >= row0 && a < row0 + rows_per_cta) {
+            p.xo[base + a] = ax;
+            p.yo[base + a] = ay;
+            p.ho[base + a] = ah;
+            if (p.vx != nullptr) {
+                p.vx[base + a] = avx;
+                p.vy[base + a] = avy;
+            }
+        }
+    }
+    __syncthreads();
+
+    float comx = 0.f, comy = 0.f, hmean = 0.f;
+    if (V == FLOCK_UW) {
+        float sx_ = 0.f, sy_ = 0.f;
+        for (int j = 0; j < N; ++j) {
+            sx_ = sx_ + sm.sx[j];
+            sy_ = sy_ + sm.sy[j];
+        }
+        comx = __fdiv_rn(sx_, (float)N);
+        comy = __fdiv_rn(sy_, (float)N);
+    }
+    if (V == FLOCK_UWD) {
+        float sh_ = 0.f;
+        for (int j = 0; j < N; ++j) sh_ = sh_ + sm.sh[j];
+        hmean = __fdiv_rn(sh_, (float)N);
+    }
+
+    long long fx_acc = 0;
+    bool coll_any = false;
+    for (int r = 0; r < rows_per_warp; ++r) {
+        const int i = row0 + wid * rows_per_warp + r;     // warp-uniform
+        if (i >= N) break;
+        const size_t idx = base + i;
+        const float xi = sm.sx[i], yi = sm.sy[i];
+        // threshold from last step's neighbour list: lane s < k checks hint s
+        float thr = kFltMax;
+        if (p.nn != nullptr) {
+            const int hj = lane < k ? p.nn[idx * k + lane] : -1;
+            bool ok = lane >= k || (hj >= 0 && hj < N && hj != i);
+#pragma unroll
+            for (int u = 1; u < FLOCK_MAX_K; ++u) {     // distinctness among the first k lanes
+                const int other = __shfl_sync(0xffffffffu, hj, (lane + u) & (FLOCK_MAX_K - 1));
+                if (lane < k && ((lane + u) & (FLOCK_MAX_K - 1)) < k && other == hj) ok = false;
+            }
+            const int jj = (lane < k && ok) ? hj : 0;
+            float hd = lane < k ? pair_d2<PER>(xi, yi, sm.sx[jj], sm.sy[jj], p.B) : 0.0f;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) hd = fmaxf(hd, __shfl_xor_sync(0xffffffffu, hd, m));
+            thr = __all_sync(0xffffffffu, ok) ? hd : kFltMax;
+        }
+        TopK<K> t;
+        t.init();
+        for (int j = lane; j < N; j += 32) {
+            const float d = pair_d2<PER>(xi, yi, sm.sx[j], sm.sy[j], p.B);
+            if (j != i && d <= thr && d < t.worst()) t.insert(d, j);
+        }
+        unsigned long long key[K];
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+            key[s] = ((unsigned long long)__float_as_uint(t.d[s]) << 32) | (unsigned)t.idx[s];
+        warp_bitonic_topk<K>(key);
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                t.d[s] = __uint_as_float((unsigned)(key[s] >> 32));
+                t.idx[s] = (int)(unsigned)key[s];
+            }
+            float dist[K];
+            const bool coll = finish_row<K>(t, k, p.sensor_range, p.cd, dist);
+            const float h = sm.sh[i];
+            float prev_h = 0.f;
+            if (V == FLOCK_UW) prev_h = p.prev_h[idx];
+            const float rew = agent_reward<V>(p, coll, xi, yi, h, prev_h, comx, comy, hmean);
+            fx_acc += reward_fx(rew);
+            coll_any = coll_any || coll;
+            if (V == FLOCK_UW && !(prev_h == h)) p.prev_h[idx] = h;
+            write_obs_t<K>(p, idx, dist, false);
+            if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
+            p.reward[idx] = rew;
+            p.agent_done[idx] = coll ? 1 : 0;
+        }
+    }
+    unsigned int* arrive = p.tile_scratch + env;
+    unsigned int* collide = p.tile_scratch + p.E + env;
+    if (lane == 0) {
+        if (coll_any) atomicAdd(collide, 1u);
+        if (p.ep_return_fx != nullptr && fx_acc != 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.ep_return_fx + env), (unsigned long long)fx_acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(arrive, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            const unsigned c = atomicExch(collide, 0u);
+            p.env_done[env] = c != 0u ? 1 : 0;
+            p.ep_len[env] += 1;
+            *arrive = 0u;
+        }
+    }
+}
+
 // reset, grid = E, one CTA per env, bounded rejection loop (gym_flock_v2.py:85-108)
 template <int K>
 __global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(const __grid_constant__ Params p) {
@@ -458,29 +652,54 @@ static int choose_rows(int N, int E, int sm_count) {
     return best;
 }
 
+// few envs x large swarm: fewer 128-row tiles than SMs -> warp-per-row kernel (bitonic top-k merge)
 template <int V, int K, bool PER>
-static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, cudaStream_t s) {
+static cudaError_t launch_rowwarp(const Params& p, int sm_count, cudaStream_t s) {
+    const int warps = kMaxTileThreads / 32;
+    long long rpw = ((long long)p.N * p.E + (long long)warps * sm_count * 2 - 1) / ((long long)warps * sm_count * 2);
+    if (rpw < 1) rpw = 1;
+    if (rpw > 64) rpw = 64;
+    const int rows_per_cta = warps * (int)rpw;
+    const dim3 grid((p.N + rows_per_cta - 1) / rows_per_cta, p.E);
+    flock_step_rowwarp_kernel<V, K, PER><<<grid, kMaxTileThreads, tiled_smem_bytes(p.N, kMaxTileThreads, true), s>>>(
+        p, (int)rpw);
+    return cudaGetLastError();
+}
+
+// tiled_mode: 0 auto, 1 thread-per-row, 2 warp-per-row (flock_set_tiled_mode). Measured on B200
+// (tools/single_env_latency.py, N = 2048, k = 8): E = 1: 51 -> 16 us with warp-per-row, E = 4: 52 -> 43,
+// E = 16: 58 -> 180 -- the warp-per-row kernel wins while the whole job has <= ~55 rows per SM.
+static bool use_rowwarp(const Params& p, int sm_count, int tiled_mode) {
+    if (tiled_mode == 1) return false;
+    if (tiled_mode == 2) return true;
+    return (long long)p.N * p.E <= 55LL * sm_count;
+}
+
+template <int V, int K, bool PER>
+static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, int tiled_mode, cudaStream_t s) {
+    if (use_rowwarp(p, sm_count, tiled_mode)) return launch_rowwarp<V, (K < 4 ? 4 : K), PER>(p, sm_count, s);
     const int rows = choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);
     flock_step_tiled_kernel<V, K, PER><<<grid, rows, tiled_smem_bytes(p.N, rows, V == FLOCK_UWD), s>>>(p);
     return cudaGetLastError();
 }
 template <int V, bool PER>
-static cudaError_t launch_tiled_vp(const Params& p, int sm_count, cudaStream_t s) {
-    if (p.k <= 3) return launch_tiled_vkp<V, 3, PER>(p, sm_count, s);
-    if (p.k == 4) return launch_tiled_vkp<V, 4, PER>(p, sm_count, s);
-    return launch_tiled_vkp<V, 8, PER>(p, sm_count, s);
+static cudaError_t launch_tiled_vp(const Params& p, int sm_count, int tiled_mode, cudaStream_t s) {
+    if (p.k <= 3) return launch_tiled_vkp<V, 3, PER>(p, sm_count, tiled_mode, s);
+    if (p.k == 4) return launch_tiled_vkp<V, 4, PER>(p, sm_count, tiled_mode, s);
+    return launch_tiled_vkp<V, 8, PER>(p, sm_count, tiled_mode, s);
 }
 
-cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int sm_count, cudaStream_t s) {
+cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int sm_count, int tiled_mode,
+                              cudaStream_t s) {
     switch (variant) {
         case FLOCK_V2:
-            return periodic ? launch_tiled_vp<FLOCK_V2, true>(p, sm_count, s)
-                            : launch_tiled_vp<FLOCK_V2, false>(p, sm_count, s);
+            return periodic ? launch_tiled_vp<FLOCK_V2, true>(p, sm_count, tiled_mode, s)
+                            : launch_tiled_vp<FLOCK_V2, false>(p, sm_count, tiled_mode, s);
         case FLOCK_UW:
-            return launch_tiled_vp<FLOCK_UW, false>(p, sm_count, s);
+            return launch_tiled_vp<FLOCK_UW, false>(p, sm_count, tiled_mode, s);
         default:
-            return launch_tiled_vp<FLOCK_UWD, false>(p, sm_count, s);
+            return launch_tiled_vp<FLOCK_UWD, false>(p, sm_count, tiled_mode, s);
     }
 }
 
@@ -509,6 +728,12 @@ cudaError_t tiled_configure(int num_agents) {
     FLOCK_OPT(FLOCK_UW, 3, false) FLOCK_OPT(FLOCK_UW, 4, false) FLOCK_OPT(FLOCK_UW, 8, false)
     FLOCK_OPT(FLOCK_UWD, 3, false) FLOCK_OPT(FLOCK_UWD, 4, false) FLOCK_OPT(FLOCK_UWD, 8, false)
 #undef FLOCK_OPT
+#define FLOCK_OPT_RW(V, K, PER) \
+    if (e == cudaSuccess) e = opt_in(flock_step_rowwarp_kernel<V, K, PER>, b);
+    FLOCK_OPT_RW(FLOCK_V2, 4, true) FLOCK_OPT_RW(FLOCK_V2, 8, true) FLOCK_OPT_RW(FLOCK_V2, 4, false)
+    FLOCK_OPT_RW(FLOCK_V2, 8, false) FLOCK_OPT_RW(FLOCK_UW, 4, false) FLOCK_OPT_RW(FLOCK_UW, 8, false)
+    FLOCK_OPT_RW(FLOCK_UWD, 4, false) FLOCK_OPT_RW(FLOCK_UWD, 8, false)
+#undef FLOCK_OPT_RW
     if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<3>, b);
     if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<4>, b);
     if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<8>, b);

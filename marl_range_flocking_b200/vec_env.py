@@ -47,7 +47,7 @@ class VecEnv:
                  device=None, seed: int = 0, env_offset: int = 0, auto_reset: bool = False,
                  max_reset_attempts: int = 64, reset_collision_distance: Optional[float] = None,
                  act_noise_std: Optional[float] = None, periodic: Optional[bool] = None,
-                 track_velocities: bool = True, track_neighbors: bool = True):
+                 track_velocities: bool = True, track_neighbors: bool = True, tiled_mode: int = 0):
         if variant not in VARIANT_IDS:
             raise ValueError(f"variant must be one of {sorted(VARIANT_IDS)}, got {variant!r}")
         if normalize_distance:
@@ -92,6 +92,7 @@ class VecEnv:
             check(self.lib.flock_create(ctypes.byref(self.cfg), self.device.index, ctypes.byref(handle)))
         self._h = handle
         self.tiled = self.lib.flock_path(self._h) == 1
+        check(self.lib.flock_set_tiled_mode(self._h, int(tiled_mode)))
         E, N, H = self.num_envs, self.num_particles, self.obs_hist
         f32 = dict(dtype=torch.float32, device=self.device)
         z = lambda *shape, **kw: torch.zeros(*shape, **{**f32, **kw})

@@ -84,8 +84,8 @@ TILED = [
 ]
 
 
-def _run_parity(variant, E, N, k, cd, rs, sr, T, rigid=False):
-    env, orc = make_pair(variant, E, N, k, cd, rs, sr, rigid=rigid)
+def _run_parity(variant, E, N, k, cd, rs, sr, T, rigid=False, **kw):
+    env, orc = make_pair(variant, E, N, k, cd, rs, sr, rigid=rigid, **kw)
     env.reset()
     orc.reset()
     compare_all(env, orc, tag="reset:")
@@ -112,14 +112,16 @@ def test_small_path_bit_exact(case):
     _run_parity(*case, T=40)
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["thread-per-row", "warp-per-row-bitonic"])
 @pytest.mark.parametrize("case", TILED, ids=[f"{c[0]}-E{c[1]}-N{c[2]}-k{c[3]}" for c in TILED])
-def test_tiled_path_bit_exact(case):
-    _run_parity(*case, T=12)
+def test_tiled_path_bit_exact(case, mode):
+    _run_parity(*case, T=12, tiled_mode=mode)
 
 
 def test_rigid_boundary_bit_exact():
     _run_parity("v2", 40, 10, 4, 1.0, (0, 6), 9.0, T=60, rigid=True)
-    _run_parity("v2", 2, 64, 4, 0.1, (0, 6), 9.0, T=30, rigid=True)
+    _run_parity("v2", 2, 64, 4, 0.1, (0, 6), 9.0, T=30, rigid=True, tiled_mode=1)
+    _run_parity("v2", 2, 64, 4, 0.1, (0, 6), 9.0, T=30, rigid=True, tiled_mode=2)
 
 
 def test_dense_world_wraps_and_collides():
@@ -290,9 +292,10 @@ def test_full_size_configs_bit_exact(case):
     assert bool(((nn >= 0) & (nn < N)).all())
 
 
-def test_large_swarm_config5_bit_exact():
+@pytest.mark.parametrize("mode", [1, 2], ids=["thread-per-row", "warp-per-row-bitonic"])
+def test_large_swarm_config5_bit_exact(mode):
     # BASELINE config 5 shape (E reduced to keep the CPU oracle fast): 2048 agents, k = 8
-    env, orc = make_pair("v2", 4, 2048, 8, 0.05, (0, 2000), 100.0, seed=0x5EED)
+    env, orc = make_pair("v2", 4, 2048, 8, 0.05, (0, 2000), 100.0, seed=0x5EED, tiled_mode=mode)
     env.reset()
     orc.reset()
     compare_all(env, orc, tag="reset:")

@@ -1,0 +1,29 @@
+"""Latency of one step for few-env large swarms: thread-per-row vs warp-per-row (bitonic merge)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from marl_range_flocking_b200 import VecEnv
+
+for E, N in ((1, 2048), (4, 2048), (16, 2048), (1, 512), (64, 2048)):
+    for mode, name in ((1, "thread-per-row"), (2, "warp-per-row")):
+        env = VecEnv("v2", E, N, 8, 0.05, range_start=(0, 2000), sensor_range=100.0, seed=3, tiled_mode=mode)
+        env.reset()
+        acts = [env.random_actions(i) for i in range(2)]
+        for i in range(5):
+            env.step(acts[i & 1])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(20):
+                env.step(acts[i & 1])
+        g.replay()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(5):
+            g.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        print(f"E={E:3d} N={N:5d} {name:15s} {ev0.elapsed_time(ev1) * 1e3 / 100:8.1f} us/step")
