@@ -435,3 +435,71 @@ def test_actor_rollout_into_device_replay():
     t = 5
     cont = ~rb.episode_end[t]
     assert torch.equal(rb.next_obs[t][cont], rb.obs[t + 1][cont])
+
+
+def test_bench_line_satisfies_the_contract():
+    """`python bench.py` prints ONE JSON line with every key of the measurement contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "1", "--steps", "64", "--warmup", "8",
+                          "--ring", "2", "--no-sweep"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "clocks", "e2e", "gpu_launches"):
+        assert key in j, key
+    assert j["steps"] == 64 and j["warmup"] == 8 and j["n_gpus"] == 1 and j["scaling"] == "weak"
+    assert j["vs_baseline"] is None and j["dtype"] == "f32" and j["data"] == "synthetic" and j["higher_is_better"] is True
+    assert "workload" in j["config"] and "model" not in j["config"]
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = j["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    e = j["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 * 10 * 2 * 4
+    assert e["d2h_bytes_per_step"] == 4096 * 10 * (4 * 4 + 4 + 1) + 4096 and e["value"] < j["value"]
+    assert j["gpu_launches"] == 64 and j["value"] > 1e8
+    assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_randomised_configuration_sweep_bit_exact():
+    """60 random (variant, E, N, k, world, dt, boundary mode) configurations, a few steps each:
+    covers every shared-memory stride of the small path (unrolled and generic), ragged tiles of both
+    tiled kernels, k from 1 to 8 and k = N-1."""
+    rng = np.random.default_rng(2024)
+    variants = ["v2", "uw", "uwd"]
+    for trial in range(60):
+        variant = variants[trial % 3]
+        if trial % 5 == 4:
+            N = int(rng.integers(33, 200))
+        else:
+            N = int(rng.integers(2, 33))
+        k = int(rng.integers(1, min(8, N - 1) + 1))
+        E = int(rng.integers(1, 40)) if N <= 32 else int(rng.integers(1, 5))
+        B = float(rng.choice([6.0, 20.0, 75.0, 300.0]))
+        cd = float(rng.choice([0.3, 1.0, 2.5]))
+        sr = float(rng.choice([2.0, 7.0, 50.0]))
+        rigid = bool(rng.integers(0, 4) == 0)
+        mode = int(rng.integers(1, 3))
+        env, orc = make_pair(variant, E, N, k, cd, (0, B), sr, seed=int(rng.integers(0, 2**31)), rigid=rigid,
+                             reset_collision_distance=cd, tiled_mode=mode, max_reset_attempts=3)
+        env.reset()
+        orc.reset(max_attempts=3)
+        tag = f"trial {trial} {variant} E{E} N{N} k{k} B{B} rigid{rigid} mode{mode}: "
+        compare_all(env, orc, tag=tag + "reset ")
+        for t in range(4):
+            a = orc.random_actions()
+            dt = float(rng.choice([0.05, 0.1, 0.2, 1.0]))
+            orc.step(a, dt)
+            env.step(torch.from_numpy(a).cuda(), dt)
+            compare_all(env, orc, tag=tag + f"step {t} ")
+        env.step_n(3, 0.1)
+        for _ in range(3):
+            orc.step(orc.random_actions(), 0.1)
+        compare_all(env, orc, tag=tag + "step_n ")
