@@ -68,7 +68,8 @@ typedef struct flock_cfg_t {
     float reset_collision_distance; /* uwd: 4 (gym_flock_uw_discrete.py:145); else collision_distance */
     float max_linear_velocity;
     float act_noise_std;        /* uwd: 0.1 (gym_flock_uw_discrete.py:333-334); else 0 */
-    float reserved0;
+    float range_noise_std;      /* optional sensing noise on the observed ranges, N(0, std); the reference has
+                                   none, default 0 (parity). Applied by a follow-up kernel only when > 0 */
     uint64_t seed;              /* Philox4x32-10 key */
 } flock_cfg_t;
 

@@ -38,7 +38,7 @@ class FlockCfg(ctypes.Structure):
         ("heading_hi", ctypes.c_float), ("sensor_range", ctypes.c_float),
         ("collision_distance", ctypes.c_float), ("reset_collision_distance", ctypes.c_float),
         ("max_linear_velocity", ctypes.c_float), ("act_noise_std", ctypes.c_float),
-        ("reserved0", ctypes.c_float), ("seed", ctypes.c_uint64),
+        ("range_noise_std", ctypes.c_float), ("seed", ctypes.c_uint64),
     ]
 
 

@@ -63,6 +63,7 @@ int validate(const flock_cfg_t& c) {
     if (c.obs_hist != want_h) return fail(FLOCK_E_INVALID, "obs_hist must be %d for variant %d", want_h, c.variant);
     if (c.periodic && c.variant != FLOCK_V2) return fail(FLOCK_E_INVALID, "periodic metric is only defined for v2");
     if (!(c.boundary > 0.0f)) return fail(FLOCK_E_INVALID, "boundary must be > 0");
+    if (!(c.range_noise_std >= 0.0f)) return fail(FLOCK_E_INVALID, "range_noise_std must be >= 0");
     if ((long long)c.num_envs * c.num_agents > (1LL << 31) - 1) return fail(FLOCK_E_INVALID, "E*N too large");
     return FLOCK_OK;
 }
@@ -90,6 +91,7 @@ Params make_params(const flock_env* e, float dt) {
     p.reset_cd = c.reset_collision_distance;
     p.fill_hi = c.rigid_boundary ? c.boundary : 0.001f;
     p.fill_lo = c.rigid_boundary ? 0.0f : c.boundary;
+    p.range_noise_std = c.range_noise_std;
     p.seed_lo = (uint32_t)c.seed; p.seed_hi = (uint32_t)(c.seed >> 32);
     p.step_offset = 0;
     p.num_steps = 1;
@@ -146,6 +148,12 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
     }
     if (err != cudaSuccess) return cuda_fail(err, "step kernel launch");
     e->step_index += 1;
+    if (e->cfg.range_noise_std > 0.0f) {     // optional sensing noise, separate launch (see flock_small.cu)
+        Params q = make_params(e, dt);        // after the slot flip: reads the current counters
+        err = flock::launch_range_noise(q, e->sm_count, s);
+        e->launches += 1;
+        if (err != cudaSuccess) return cuda_fail(err, "range noise kernel launch");
+    }
     return FLOCK_OK;
 }
 
@@ -275,6 +283,13 @@ int flock_reset(flock_env_t* e, const uint8_t* env_mask, const float* init_state
     cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s) : flock::launch_reset_tiled(p, s);
     e->launches += 1;
     if (err != cudaSuccess) return cuda_fail(err, "reset kernel launch");
+    if (e->cfg.range_noise_std > 0.0f) {
+        Params q = make_params(e, 0.0f);
+        q.env_mask = env_mask;                // only the envs that were reset get a fresh noisy first observation
+        err = flock::launch_range_noise(q, e->sm_count, s);
+        e->launches += 1;
+        if (err != cudaSuccess) return cuda_fail(err, "range noise kernel launch");
+    }
     return FLOCK_OK;
 }
 
@@ -303,7 +318,7 @@ int flock_step_n(flock_env_t* e, int num_steps, float dt, void* stream) {
     if (rc != FLOCK_OK) return rc;
     if (num_steps < 1) return fail(FLOCK_E_INVALID, "num_steps must be >= 1");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (e->path == 0) {
+    if (e->path == 0 && e->cfg.range_noise_std == 0.0f) {   // sensing noise needs the per-step follow-up kernel
         Params p = make_params(e, dt);
         p.num_steps = num_steps;
         cudaError_t err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, true, e->sm_count, s);
@@ -358,7 +373,8 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
         }();
         const size_t out_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float) + EN * 5 + (size_t)e->cfg.num_envs;
         const bool zc_inputs = e->zc_ok && e->path == 0 && zc_mode != 0;
-        const bool zc_outputs = zc_inputs && (zc_mode == 1 || out_bytes <= (size_t)3 << 20);
+        const bool zc_outputs = zc_inputs && e->cfg.range_noise_std == 0.0f &&   // noise is applied after the step
+                                (zc_mode == 1 || out_bytes <= (size_t)3 << 20);
         if (zc_outputs) {
             HostMirrors mir;
             mir.obs = static_cast<float*>(e->zc_dev[1]);

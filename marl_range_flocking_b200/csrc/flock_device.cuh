@@ -16,7 +16,7 @@ constexpr int kWarp = 32;
 #define kInf (__int_as_float(0x7f800000))
 constexpr float kFltMax = 3.4028234663852886e38f;
 
-enum : uint32_t { kTagReset = 0u, kTagNoise = 1u, kTagAction = 2u };
+enum : uint32_t { kTagReset = 0u, kTagNoise = 1u, kTagAction = 2u, kTagRange = 3u };
 
 // Kernel parameters (passed by value as a __grid_constant__).
 struct Params {
@@ -29,6 +29,7 @@ struct Params {
     float B, halfB, sensor_range, cd, cd4, vmax, noise_std, dt;
     float range_lo, reset_hi, heading_hi, reset_cd;
     float fill_hi, fill_lo;   // check_boundary replacement values (see wrap_coord)
+    float range_noise_std;
     uint32_t seed_lo, seed_hi, step_offset;   // step_offset: flock_random_actions look-ahead
     int num_steps;      // step_n
     int max_attempts;   // reset

@@ -10,6 +10,7 @@ struct Params;
 cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool multi, int sm_count, cudaStream_t s);
 cudaError_t launch_reset_small(const Params& p, int sm_count, cudaStream_t s);
 cudaError_t launch_random_actions(int variant, const Params& p, float* out, int sm_count, cudaStream_t s);
+cudaError_t launch_range_noise(const Params& p, int sm_count, cudaStream_t s);
 cudaError_t launch_debug_sincos(const float* h, int n, float* sn, float* cs, cudaStream_t s);
 cudaError_t launch_debug_normal2(const uint32_t* w, int n, float* z, cudaStream_t s);
 cudaError_t launch_debug_philox(const uint32_t* ck, int n, uint32_t* out, cudaStream_t s);

@@ -503,6 +503,35 @@ __global__ void flock_random_actions_kernel(const __grid_constant__ Params p, fl
     }
 }
 
+// Optional sensing noise (north-star extension; the reference has none): the newest row of range
+// observations becomes clamp(d + std * z, 0, sensor_range), z ~ N(0,1) from the Philox stream
+// (global env, agent + 65536 * call, ep_len[env], tag 3 + 4 * reset_epoch). Collisions, dones and
+// rewards keep using the true ranges. Launched right after step / reset only when std > 0, so the
+// default (parity) path carries no trace of it.
+__global__ void flock_range_noise_kernel(const __grid_constant__ Params p) {
+    const size_t n = (size_t)p.E * p.N;
+    const int k = p.k;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int env = (int)(i / p.N), a = (int)(i - (size_t)env * p.N);
+        if (p.env_mask != nullptr && p.env_mask[env] == 0) continue;
+        const uint32_t epoch = (uint32_t)p.ep_len[env], word = stream_word(kTagRange, p.reset_epoch[env]);
+        float* o = p.obs + i * (size_t)(p.H * k);
+        for (int c = 0; c * 4 < k; ++c) {
+            const uint4 r = philox4x32_10((uint32_t)(p.env_offset + env), (uint32_t)a + 65536u * (uint32_t)c, epoch, word,
+                                          p.seed_lo, p.seed_hi);
+            float z[4];
+            normal2(r.x, r.y, z[0], z[1]);
+            normal2(r.z, r.w, z[2], z[3]);
+            for (int s = 0; s < 4 && c * 4 + s < k; ++s) {
+                const float nz = p.range_noise_std * z[s];
+                float d = o[c * 4 + s] + nz;
+                d = fminf(fmaxf(d, 0.0f), p.sensor_range);
+                o[c * 4 + s] = d;
+            }
+        }
+    }
+}
+
 __global__ void flock_debug_sincos_kernel(const float* h, int n, float* sn, float* cs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sincos_canon(h[i], sn[i], cs[i]);
@@ -608,6 +637,15 @@ cudaError_t launch_random_actions(int variant, const Params& p, float* out, int 
     if (variant == FLOCK_V2) flock_random_actions_kernel<FLOCK_V2><<<grid, 256, 0, s>>>(p, out);
     else if (variant == FLOCK_UW) flock_random_actions_kernel<FLOCK_UW><<<grid, 256, 0, s>>>(p, out);
     else flock_random_actions_kernel<FLOCK_UWD><<<grid, 256, 0, s>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_range_noise(const Params& p, int sm_count, cudaStream_t s) {
+    const size_t n = (size_t)p.E * p.N;
+    int grid = (int)((n + 255) / 256);
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    if (grid < 1) grid = 1;
+    flock_range_noise_kernel<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -38,7 +38,10 @@ class VecEnv:
     Constructor arguments up to `desired_distance` mirror `MultiAgentEnv.__init__`
     (gym_flock_v2.py:21-32; `normalize_distance` / `desired_distance` are accepted and ignored
     exactly as the reference's live code path ignores them). Keyword-only arguments
-    are the batched extensions.
+    are the batched extensions: `seed` / `env_offset` (Philox key and global env index of env 0),
+    `auto_reset` (finished envs restart in place after each step), `tiled_mode` (kernel choice for
+    N > 32, see flock_set_tiled_mode), `range_noise_std` (optional N(0, std) sensing noise on the
+    observed ranges; 0 = the reference's noise-free sensing).
     """
 
     def __init__(self, variant: str, num_envs: int, agents: int, k: int = 4, collision_distance: float = 3,
@@ -47,7 +50,8 @@ class VecEnv:
                  device=None, seed: int = 0, env_offset: int = 0, auto_reset: bool = False,
                  max_reset_attempts: int = 64, reset_collision_distance: Optional[float] = None,
                  act_noise_std: Optional[float] = None, periodic: Optional[bool] = None,
-                 track_velocities: bool = True, track_neighbors: bool = True, tiled_mode: int = 0):
+                 track_velocities: bool = True, track_neighbors: bool = True, tiled_mode: int = 0,
+                 range_noise_std: float = 0.0):
         if variant not in VARIANT_IDS:
             raise ValueError(f"variant must be one of {sorted(VARIANT_IDS)}, got {variant!r}")
         if normalize_distance:
@@ -86,7 +90,7 @@ class VecEnv:
                             int(self.rigid_boundary), int(bool(periodic)), self.obs_hist, int(env_offset),
                             float(r1), float(r0), float(reset_hi), _f32(_HEADING_HI[variant]), float(sensor_range),
                             float(collision_distance), float(reset_collision_distance), float(max_linear_velocity),
-                            float(act_noise_std), 0.0, int(seed) & 0xFFFFFFFFFFFFFFFF)
+                            float(act_noise_std), float(range_noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF)
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             check(self.lib.flock_create(ctypes.byref(self.cfg), self.device.index, ctypes.byref(handle)))

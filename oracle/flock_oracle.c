@@ -51,7 +51,7 @@ typedef struct {
     float reset_collision_distance; /* uwd: 4 (gym_flock_uw_discrete.py:145), else = collision_distance */
     float max_linear_velocity;
     float act_noise_std;      /* uwd: 0.1 (gym_flock_uw_discrete.py:333-334) */
-    float pad_;
+    float range_noise_std;    /* optional sensing noise (extension, reference has none): default 0 */
     uint64_t seed;
 } orc_cfg_t;
 
@@ -143,7 +143,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * (global env id, agent id, epoch, tag word). tag 0: reset draw (epoch = per-env attempt counter
  * reset_epoch, tag word 0); tag 1: actuation noise, tag 2: random actions (epoch = ep_len[env] =
  * steps since the env's last reset, tag word = tag + 4 * reset_epoch[env]). */
-enum { TAG_RESET = 0, TAG_NOISE = 1, TAG_ACTION = 2 };
+enum { TAG_RESET = 0, TAG_NOISE = 1, TAG_ACTION = 2, TAG_RANGE = 3 };
 
 static float u24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); } /* [0,1), torch.rand grid */
 
@@ -521,6 +521,36 @@ int orc_reset(const orc_cfg_t *c, orc_buf_t *b, const uint8_t *mask, const float
         b->ep_return_fx[e] = 0;
     }
     return gave_up;
+}
+
+/* Optional sensing noise (extension of the north star, not in the reference): newest obs row
+ * becomes clamp(d + std*z, 0, sensor_range); Philox (global env, agent + 65536*call, ep_len, tag 3
+ * + 4*reset_epoch). Applied after step / reset, only to masked envs. */
+void orc_range_noise(const orc_cfg_t *c, orc_buf_t *b, const uint8_t *mask)
+{
+    const int E = c->num_envs, N = c->num_agents, k = c->k, H = c->obs_hist;
+    if (!(c->range_noise_std > 0.0f)) return;
+    for (int e = 0; e < E; ++e) {
+        if (mask && !mask[e]) continue;
+        for (int a = 0; a < N; ++a) {
+            float *o = b->obs + ((size_t)e * N + a) * H * k;
+            for (int cc = 0; cc * 4 < k; ++cc) {
+                uint32_t r[4];
+                philox4x32_10((uint32_t)(c->env_offset + e), (uint32_t)a + 65536u * (uint32_t)cc, (uint32_t)b->ep_len[e],
+                              TAG_RANGE + (b->reset_epoch[e] << 2), (uint32_t)c->seed, (uint32_t)(c->seed >> 32), r);
+                float z[4];
+                flock_normal2(r[0], r[1], &z[0], &z[1]);
+                flock_normal2(r[2], r[3], &z[2], &z[3]);
+                for (int s = 0; s < 4 && cc * 4 + s < k; ++s) {
+                    float nz = c->range_noise_std * z[s];
+                    float d = o[cc * 4 + s] + nz;
+                    d = d < 0.0f ? 0.0f : d;
+                    d = d > c->sensor_range ? c->sensor_range : d;
+                    o[cc * 4 + s] = d;
+                }
+            }
+        }
+    }
 }
 
 int orc_max_threads(void)

@@ -44,7 +44,7 @@ class _Cfg(ctypes.Structure):
         ("heading_hi", ctypes.c_float), ("sensor_range", ctypes.c_float),
         ("collision_distance", ctypes.c_float), ("reset_collision_distance", ctypes.c_float),
         ("max_linear_velocity", ctypes.c_float), ("act_noise_std", ctypes.c_float),
-        ("pad_", ctypes.c_float), ("seed", ctypes.c_uint64),
+        ("range_noise_std", ctypes.c_float), ("seed", ctypes.c_uint64),
     ]
 
 
@@ -99,7 +99,8 @@ class OracleEnv:
     def __init__(self, variant: str, num_envs: int, agents: int, k: int, collision_distance: float,
                  range_start=(0, 100), sensor_range: float = 7, max_linear_velocity: float = 2.5,
                  rigid_boundary: bool = False, seed: int = 0, env_offset: int = 0,
-                 reset_collision_distance=None, act_noise_std=None, periodic=None, nthreads: int = 1):
+                 reset_collision_distance=None, act_noise_std=None, periodic=None, nthreads: int = 1,
+                 range_noise_std: float = 0.0):
         assert agents >= k + 1 and 1 <= k <= 16
         d = variant_defaults(variant, range_start, collision_distance)
         if reset_collision_distance is not None:
@@ -114,7 +115,7 @@ class OracleEnv:
                         d["obs_hist"], env_offset, float(range_start[1]), float(range_start[0]),
                         float(d["reset_hi"]), float(d["heading_hi"]), float(sensor_range),
                         float(collision_distance), float(d["reset_collision_distance"]),
-                        float(max_linear_velocity), float(d["act_noise_std"]), 0.0, seed)
+                        float(max_linear_velocity), float(d["act_noise_std"]), float(range_noise_std), seed)
         E, N, H = num_envs, agents, self.H
         f32 = np.float32
         self.x = np.zeros((E, N), f32); self.y = np.zeros((E, N), f32); self.h = np.zeros((E, N), f32)
@@ -144,10 +145,12 @@ class OracleEnv:
         ini = None if init is None else np.ascontiguousarray(init, np.float32)
         if ini is not None:
             assert ini.shape == (3, self.E, self.N)
-        return self._lib.orc_reset(ctypes.byref(self.cfg), ctypes.byref(self._buf),
-                                   None if m is None else _ptr(m), None if ini is None else _ptr(ini),
-                                   ctypes.c_int(max_attempts), ctypes.c_int(int(keep_outputs)),
-                                   ctypes.c_int(self.nthreads))
+        rc = self._lib.orc_reset(ctypes.byref(self.cfg), ctypes.byref(self._buf),
+                                 None if m is None else _ptr(m), None if ini is None else _ptr(ini),
+                                 ctypes.c_int(max_attempts), ctypes.c_int(int(keep_outputs)),
+                                 ctypes.c_int(self.nthreads))
+        self._lib.orc_range_noise(ctypes.byref(self.cfg), ctypes.byref(self._buf), None if m is None else _ptr(m))
+        return rc
 
     def step(self, actions, dt: float = 0.1, noise=None):
         aw = 1 if self.variant == "uwd" else 2
@@ -157,6 +160,7 @@ class OracleEnv:
         self._lib.orc_step(ctypes.byref(self.cfg), ctypes.byref(self._buf), _ptr(a),
                            None if nz is None else _ptr(nz), ctypes.c_float(dt), ctypes.c_int(self.nthreads))
         self.step_index += 1
+        self._lib.orc_range_noise(ctypes.byref(self.cfg), ctypes.byref(self._buf), None)
 
     def random_actions(self, step_offset: int = 0) -> np.ndarray:
         aw = 1 if self.variant == "uwd" else 2

@@ -12,7 +12,7 @@ def make_pair(variant, E, N, k, cd, rs=(0, 100), sr=7.0, seed=1234, env_offset=0
     from marl_range_flocking_b200 import VecEnv
     env = VecEnv(variant, E, N, k, cd, rigid_boundary=rigid, range_start=rs, sensor_range=sr, seed=seed,
                  env_offset=env_offset, **kw)
-    okw = {k_: v_ for k_, v_ in kw.items() if k_ in ("reset_collision_distance", "act_noise_std", "periodic")}
+    okw = {k_: v_ for k_, v_ in kw.items() if k_ in ("reset_collision_distance", "act_noise_std", "periodic", "range_noise_std")}
     # tiled_mode / auto_reset / ... only exist on the CUDA side
     orc = OracleEnv(variant, E, N, k, cd, range_start=rs, sensor_range=sr, seed=seed, env_offset=env_offset,
                     rigid_boundary=rigid, nthreads=8, **okw)

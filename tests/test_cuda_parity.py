@@ -503,3 +503,38 @@ def test_randomised_configuration_sweep_bit_exact():
         for _ in range(3):
             orc.step(orc.random_actions(), 0.1)
         compare_all(env, orc, tag=tag + "step_n ")
+
+
+@pytest.mark.parametrize("variant,E,N,k", [("v2", 40, 10, 4), ("uw", 20, 32, 3), ("uwd", 30, 16, 4), ("v2", 2, 96, 8),
+                                           ("v2", 33, 7, 6)])
+def test_optional_range_sensing_noise_bit_exact(variant, E, N, k):
+    """north-star extension: Philox N(0, std) noise on the observed ranges (the reference has none;
+    std = 0 is the default and is what every other test runs)."""
+    env, orc = make_pair(variant, E, N, k, 0.5, (0, 60), 9.0, seed=31, range_noise_std=0.25)
+    env.reset()
+    orc.reset()
+    compare_all(env, orc, tag="noisy reset:")
+    clean, _ = make_pair(variant, E, N, k, 0.5, (0, 60), 9.0, seed=31)
+    clean.reset()
+    for t in range(6):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        env.step(torch.from_numpy(a).cuda(), 0.1)
+        clean.step(torch.from_numpy(a).cuda(), 0.1)
+        compare_all(env, orc, tag=f"noisy step {t}:")
+    # noise touches the observation only: state, dones and rewards equal the noise-free run
+    assert torch.equal(env.x, clean.x) and torch.equal(env.reward, clean.reward) and torch.equal(env.dones[0], clean.dones[0])
+    d_noisy, d_clean = env.distances_to_nearest_neighbors, clean.distances_to_nearest_neighbors
+    assert not torch.equal(d_noisy, d_clean) and bool((d_noisy >= 0).all()) and bool((d_noisy <= 9.0).all())
+    inside = (d_clean > 1.5) & (d_clean < 7.5)          # away from the clamps the residual is N(0, 0.25)
+    if int(inside.sum()) > 200:
+        res = (d_noisy - d_clean)[inside]
+        assert abs(float(res.mean())) < 0.06 and abs(float(res.std()) - 0.25) < 0.06
+    env.step_n(4, 0.1)
+    for _ in range(4):
+        orc.step(orc.random_actions(), 0.1)
+    compare_all(env, orc, tag="noisy step_n:")
+    a = orc.random_actions()
+    orc.step(a, 0.1)
+    obs, *_ = env.step_host(torch.from_numpy(a).pin_memory(), 0.1)      # staged path (noise after the step)
+    assert_same("noisy host obs", obs, orc.obs if env.obs_hist > 1 else orc.obs[:, :, 0, :])

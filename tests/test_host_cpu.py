@@ -75,7 +75,7 @@ def test_config_validation_errors_come_back_through_the_abi(lib):
         base = dict(variant=0, num_envs=4, num_agents=10, k=4, rigid_boundary=0, periodic=1, obs_hist=1, env_offset=0,
                     boundary=50.0, range_lo=0.0, reset_hi=50.0, heading_hi=4.7, sensor_range=14.0,
                     collision_distance=2.5, reset_collision_distance=2.5, max_linear_velocity=2.5, act_noise_std=0.0,
-                    reserved0=0.0, seed=1)
+                    range_noise_std=0.0, seed=1)
         base.update(kw)
         return FlockCfg(**base)
 
