@@ -137,6 +137,14 @@ FLOCK_API int flock_reset(flock_env_t *env, const uint8_t *env_mask, const float
  *           gym_flock_uw_discrete.py:333-334). */
 FLOCK_API int flock_step(flock_env_t *env, const float *actions, float dt, const float *noise, void *stream);
 
+/* Auto-reset mode (the batched form of "caller resets on done[1]", main.py:31-51): when enabled,
+ * every flock_step also restarts the envs whose step ended with a collision -- inside the same
+ * kernel launch when N <= 32, by a follow-up masked reset otherwise. reward / agent_done / env_done
+ * keep the values of the finishing step; obs (and nn_idx) of a restarted env are those of its new
+ * first state. Equivalent to flock_step followed by flock_reset(env_done, NULL, max_attempts,
+ * FLOCK_RESET_KEEP_OUTPUTS). */
+FLOCK_API int flock_set_auto_reset(flock_env_t *env, int enabled, int max_attempts);
+
 /* T consecutive steps with the canonical in-kernel random actions (action_space sampling:
  * v2 U[-1.5,1.5)^2 gym_flock_v2.py:58, uw U[-1,1)^2 gym_flock_uw.py:57, uwd id in [0,k)
  * gym_flock_uw_discrete.py:98). N <= 32: one persistent launch with the state in registers;

@@ -36,6 +36,8 @@ struct flock_env {
     int path;            // 0 small, 1 tiled
     int slot;            // current state copy on the tiled path
     int tiled_mode;      // 0 auto, 1 thread-per-row, 2 warp-per-row
+    int auto_reset;      // flock_set_auto_reset: restart finished envs as part of flock_step
+    int auto_reset_attempts;
     uint32_t step_index;
     uint64_t launches;
     float* stage_actions;  // device staging for host-call / step_n(tiled) actions
@@ -119,6 +121,28 @@ int check_bound(const flock_env* e) {
     return FLOCK_OK;
 }
 
+int reset_device(flock_env* e, const uint8_t* env_mask, const float* init_state, int max_attempts, int flags,
+                 cudaStream_t s) {
+    Params p = make_params(e, 0.0f);
+    p.env_mask = env_mask;
+    p.init_state = init_state;
+    p.max_attempts = max_attempts > 0 ? max_attempts : 64;
+    p.reset_flags = flags;
+    // reset installs the state into the CURRENT copy
+    p.xo = const_cast<float*>(p.x); p.yo = const_cast<float*>(p.y); p.ho = const_cast<float*>(p.h);
+    cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s) : flock::launch_reset_tiled(p, s);
+    e->launches += 1;
+    if (err != cudaSuccess) return cuda_fail(err, "reset kernel launch");
+    if (e->cfg.range_noise_std > 0.0f) {
+        Params q = make_params(e, 0.0f);
+        q.env_mask = env_mask;                // only the envs that were reset get a fresh noisy first observation
+        err = flock::launch_range_noise(q, e->sm_count, s);
+        e->launches += 1;
+        if (err != cudaSuccess) return cuda_fail(err, "range noise kernel launch");
+    }
+    return FLOCK_OK;
+}
+
 struct HostMirrors {
     float* obs = nullptr;
     float* reward = nullptr;
@@ -138,7 +162,12 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         p.m_env_done = mirrors->env_done;
     }
     cudaError_t err;
+    const bool fused_reset = e->auto_reset && e->path == 0 && mirrors == nullptr && e->cfg.range_noise_std == 0.0f;
     if (e->path == 0) {
+        if (fused_reset) {
+            p.fused_auto_reset = 1;
+            p.max_attempts = e->auto_reset_attempts;
+        }
         err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
         e->launches += 1;
     } else {
@@ -153,6 +182,10 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         err = flock::launch_range_noise(q, e->sm_count, s);
         e->launches += 1;
         if (err != cudaSuccess) return cuda_fail(err, "range noise kernel launch");
+    }
+    if (e->auto_reset && !fused_reset) {      // tiled path / host mirrors / sensing noise: second launch
+        int rc = reset_device(e, e->b.env_done, nullptr, e->auto_reset_attempts, FLOCK_RESET_KEEP_OUTPUTS, s);
+        if (rc != FLOCK_OK) return rc;
     }
     return FLOCK_OK;
 }
@@ -272,24 +305,13 @@ int flock_reset(flock_env_t* e, const uint8_t* env_mask, const float* init_state
                 void* stream) {
     int rc = check_bound(e);
     if (rc != FLOCK_OK) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    Params p = make_params(e, 0.0f);
-    p.env_mask = env_mask;
-    p.init_state = init_state;
-    p.max_attempts = max_attempts > 0 ? max_attempts : 64;
-    p.reset_flags = flags;
-    // reset installs the state into the CURRENT copy
-    p.xo = const_cast<float*>(p.x); p.yo = const_cast<float*>(p.y); p.ho = const_cast<float*>(p.h);
-    cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s) : flock::launch_reset_tiled(p, s);
-    e->launches += 1;
-    if (err != cudaSuccess) return cuda_fail(err, "reset kernel launch");
-    if (e->cfg.range_noise_std > 0.0f) {
-        Params q = make_params(e, 0.0f);
-        q.env_mask = env_mask;                // only the envs that were reset get a fresh noisy first observation
-        err = flock::launch_range_noise(q, e->sm_count, s);
-        e->launches += 1;
-        if (err != cudaSuccess) return cuda_fail(err, "range noise kernel launch");
-    }
+    return reset_device(e, env_mask, init_state, max_attempts, flags, static_cast<cudaStream_t>(stream));
+}
+
+int flock_set_auto_reset(flock_env_t* e, int enabled, int max_attempts) {
+    if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
+    e->auto_reset = enabled != 0;
+    e->auto_reset_attempts = max_attempts > 0 ? max_attempts : 64;
     return FLOCK_OK;
 }
 
@@ -327,13 +349,14 @@ int flock_step_n(flock_env_t* e, int num_steps, float dt, void* stream) {
         e->step_index += (uint32_t)num_steps;
         return FLOCK_OK;
     }
-    for (int t = 0; t < num_steps; ++t) {
+    const int saved_auto_reset = e->auto_reset;   // step_n never restarts envs (same as the persistent kernel)
+    e->auto_reset = 0;
+    for (int t = 0; t < num_steps && rc == FLOCK_OK; ++t) {
         rc = flock_random_actions(e, 0u, e->stage_actions, stream);
-        if (rc != FLOCK_OK) return rc;
-        rc = step_device(e, e->stage_actions, dt, nullptr, s);
-        if (rc != FLOCK_OK) return rc;
+        if (rc == FLOCK_OK) rc = step_device(e, e->stage_actions, dt, nullptr, s);
     }
-    return FLOCK_OK;
+    e->auto_reset = saved_auto_reset;
+    return rc;
 }
 
 int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
@@ -373,7 +396,7 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
         }();
         const size_t out_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float) + EN * 5 + (size_t)e->cfg.num_envs;
         const bool zc_inputs = e->zc_ok && e->path == 0 && zc_mode != 0;
-        const bool zc_outputs = zc_inputs && e->cfg.range_noise_std == 0.0f &&   // noise is applied after the step
+        const bool zc_outputs = zc_inputs && e->cfg.range_noise_std == 0.0f && !e->auto_reset &&   // post-step launches
                                 (zc_mode == 1 || out_bytes <= (size_t)3 << 20);
         if (zc_outputs) {
             HostMirrors mir;

@@ -34,6 +34,7 @@ struct Params {
     int num_steps;      // step_n
     int max_attempts;   // reset
     int reset_flags;    // reset: FLOCK_RESET_*
+    int fused_auto_reset;   // step (small path): restart finished envs in the same launch
     const float* actions;
     const float* noise;
     const float* init_state;

@@ -193,9 +193,15 @@ __device__ __forceinline__ float seq_sum(const float* s, int N) {
 // gym_flock_uw_discrete.py:110-122). NSTEPS > 1 (flock_step_n) keeps the state in registers and
 // draws the canonical random actions in-kernel.
 // -------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void reset_groups(const Params& p, const LaneMap& m, float* sx, float* sy, int env,
+                                             size_t idx, bool want, bool keep_outputs);
+
 // MIRROR: also write the results to device-visible host memory (flock_step_host zero-copy path);
-// a separate instantiation because even the untaken branch costs 3 % in the plain kernel.
-template <int V, int K, bool PER, bool MULTI, int NJ4, bool MIRROR>
+// AUTORESET: env groups whose step ended with a collision are re-drawn in the same launch (reward
+// and done flags of the finishing step stay, obs becomes the first observation of the new episode).
+// Both are separate instantiations because even an untaken branch costs ~3 % in the plain kernel.
+template <int V, int K, bool PER, bool MULTI, int NJ4, bool MIRROR, bool AUTORESET>
 __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const __grid_constant__ Params p) {
     __shared__ __align__(16) float s_stage[kSmallWarps][3][kSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -380,113 +386,124 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 if (m.a == 0) p.m_env_done[env] = env_coll ? 1 : 0;
             }
         }
+        if (AUTORESET) {
+            const bool want = live && env_coll;
+            if (__any_sync(0xffffffffu, want)) reset_groups<K>(p, m, sx, sy, env, idx, want, true);
+        }
     }
 }
 
 // -------------------------------------------------------------------------------------------------
 // reset: MultiAgentEnv.reset (gym_flock_v2.py:85-108, gym_flock_uw.py:83-111,
 // gym_flock_uw_discrete.py:124-156) with a BOUNDED rejection loop, masked and batched.
+// reset_groups() (re)draws the env groups of the calling warp whose lanes pass `want` (uniform per
+// group); ALL 32 lanes must call it. It is the body of the reset kernel and, with keep_outputs, the
+// fused auto-reset tail of the step kernel.
 // -------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void reset_groups(const Params& p, const LaneMap& m, float* sx, float* sy, int env,
+                                             size_t idx, bool want, bool keep_outputs) {
+    const int N = p.N, k = p.k, sstride = p.sstride;
+    const size_t EN = (size_t)p.E * N;
+    float x = 0.f, y = 0.f, h = 0.f;
+    const uint32_t epoch = want ? p.reset_epoch[env] : 0u;
+    uint32_t attempts = 0;
+    bool need = want;       // group still needs a (re)draw
+    bool coll = false, env_coll = false;
+    float dist[K];
+    TopK<K> t;
+    const int max_att = p.init_state != nullptr ? 1 : p.max_attempts;
+    while (__any_sync(0xffffffffu, need)) {
+        if (need) {
+            if (p.init_state != nullptr) {
+                x = p.init_state[idx];
+                y = p.init_state[EN + idx];
+                h = p.init_state[2 * EN + idx];
+            } else {
+                const uint4 r = philox4x32_10((uint32_t)(p.env_offset + env), (uint32_t)m.a, epoch + attempts, kTagReset,
+                                              p.seed_lo, p.seed_hi);
+                const float span = p.range_lo - p.reset_hi;      // (r0 - r1) * U + r1, gym_flock_v2.py:87-89
+                const float tx = span * u24(r.x);
+                x = tx + p.reset_hi;
+                const float ty = span * u24(r.y);
+                y = ty + p.reset_hi;
+                const float th = (0.0f - p.heading_hi) * u24(r.z);  // gym_flock_v2.py:96
+                h = th + p.heading_hi;
+            }
+            x = wrap_coord(x, p.B, p.fill_hi, p.fill_lo);                      // check_boundary, v2:99
+            y = wrap_coord(y, p.B, p.fill_hi, p.fill_lo);
+            attempts += 1;
+        }
+        __syncwarp();
+        stage_xy(sx, sy, m, N, sstride, want, x, y);
+        __syncwarp();
+        if (need) {   // whole group shares `need`
+            float unused_sx, unused_sy;
+            knn_small<K, false, 0, false>(sx + m.g * sstride, sy + m.g * sstride, m.a, N, sstride, x, y, p.B, t,
+                                          unused_sx, unused_sy);  // Euclidean, v2:100
+            coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
+        }
+        {
+            const unsigned bc = __ballot_sync(0xffffffffu, need && coll) & m.gmask;   // full-mask ballot
+            if (need) {
+                env_coll = bc != 0u;
+                need = env_coll && (int)attempts < max_att;
+            }
+        }
+    }
+    if (want) {
+        p.xo[idx] = x;
+        p.yo[idx] = y;
+        p.ho[idx] = h;
+        p.prev_h[idx] = 0.0f;                                     // v2:95
+        if (p.vx != nullptr) {
+            p.vx[idx] = 0.0f;                                     // v2:94
+            p.vy[idx] = 0.0f;
+        }
+        write_obs<K>(p, idx, dist, true);
+        if (p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
+        if (!keep_outputs) {
+            p.reward[idx] = 0.0f;
+            p.agent_done[idx] = coll ? 1 : 0;
+        }
+        if (m.a == 0) {
+            if (!keep_outputs) p.env_done[env] = env_coll ? 1 : 0;
+            if (p.init_state == nullptr) p.reset_epoch[env] = epoch + attempts;
+            const int len = p.ep_len[env];
+            if (p.stats != nullptr) {
+                if (len > 0) {
+                    atomicAdd(&p.stats[FLOCK_STAT_EPISODES], 1ULL);
+                    atomicAdd(&p.stats[FLOCK_STAT_EP_STEPS], (unsigned long long)len);
+                    if (p.ep_return_fx != nullptr)
+                        atomicAdd(&p.stats[FLOCK_STAT_EP_RETURN_FX], (unsigned long long)p.ep_return_fx[env]);
+                }
+                if (p.init_state == nullptr) {
+                    atomicAdd(&p.stats[FLOCK_STAT_RESET_ATTEMPTS], (unsigned long long)attempts);
+                    if (env_coll) atomicAdd(&p.stats[FLOCK_STAT_RESET_GAVE_UP], 1ULL);
+                }
+            }
+            p.ep_len[env] = 0;
+            if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = 0;
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kSmallThreads) flock_reset_small_kernel(const __grid_constant__ Params p) {
     __shared__ __align__(16) float s_stage[kSmallWarps][2][kSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* sx = s_stage[wib][0];
     float* sy = s_stage[wib][1];
-    const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
+    const int N = p.N, G = p.G;
     const LaneMap m = lane_map(lane, N, G, p.g_magic);
     const int num_tasks = p.num_tasks;
     const int warps_total = gridDim.x * kSmallWarps;
-    const size_t EN = (size_t)p.E * N;
-
     for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
         const int env = task * G + m.g;
         bool live = m.lane_ok && env < p.E;
         if (live && p.env_mask != nullptr) live = p.env_mask[env] != 0;
         const size_t idx = (size_t)(live ? env : 0) * N + m.a;
-        float x = 0.f, y = 0.f, h = 0.f;
-        uint32_t epoch = live ? p.reset_epoch[env] : 0u;
-        uint32_t attempts = 0;
-        bool need = live;       // group still needs a (re)draw
-        bool coll = false, env_coll = false;
-        float dist[K];
-        TopK<K> t;
-        const int max_att = p.init_state != nullptr ? 1 : p.max_attempts;
-        while (__any_sync(0xffffffffu, need)) {
-            if (need) {
-                if (p.init_state != nullptr) {
-                    x = p.init_state[idx];
-                    y = p.init_state[EN + idx];
-                    h = p.init_state[2 * EN + idx];
-                } else {
-                        const uint4 r = philox4x32_10((uint32_t)(p.env_offset + env), (uint32_t)m.a, epoch + attempts,
-                                                  kTagReset, p.seed_lo, p.seed_hi);
-                    const float span = p.range_lo - p.reset_hi;      // (r0 - r1) * U + r1, gym_flock_v2.py:87-89
-                    const float tx = span * u24(r.x);
-                    x = tx + p.reset_hi;
-                    const float ty = span * u24(r.y);
-                    y = ty + p.reset_hi;
-                    const float th = (0.0f - p.heading_hi) * u24(r.z);  // gym_flock_v2.py:96
-                    h = th + p.heading_hi;
-                }
-                x = wrap_coord(x, p.B, p.fill_hi, p.fill_lo);                      // check_boundary, v2:99
-                y = wrap_coord(y, p.B, p.fill_hi, p.fill_lo);
-                attempts += 1;
-            }
-            __syncwarp();
-            stage_xy(sx, sy, m, N, sstride, live, x, y);
-            __syncwarp();
-            if (need) {   // whole group shares `need`
-                float unused_sx, unused_sy;
-                knn_small<K, false, 0, false>(sx + m.g * sstride, sy + m.g * sstride, m.a, N, sstride, x, y, p.B, t,
-                                              unused_sx, unused_sy);  // Euclidean, v2:100
-                coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
-            }
-            {
-                const unsigned bc = __ballot_sync(0xffffffffu, need && coll) & m.gmask;   // full-mask ballot
-                if (need) {
-                    env_coll = bc != 0u;
-                    need = env_coll && (int)attempts < max_att;
-                }
-            }
-        }
-        pdl_launch_dependents();   // the next kernel may start launching while we store the results
-        if (live) {
-            p.xo[idx] = x;
-            p.yo[idx] = y;
-            p.ho[idx] = h;
-            p.prev_h[idx] = 0.0f;                                     // v2:95
-            if (p.vx != nullptr) {
-                p.vx[idx] = 0.0f;                                     // v2:94
-                p.vy[idx] = 0.0f;
-            }
-            write_obs<K>(p, idx, dist, true);
-            if (p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
-            const bool keep = (p.reset_flags & FLOCK_RESET_KEEP_OUTPUTS) != 0;
-            if (!keep) {
-                p.reward[idx] = 0.0f;
-                p.agent_done[idx] = coll ? 1 : 0;
-            }
-            if (m.a == 0) {
-                if (!keep) p.env_done[env] = env_coll ? 1 : 0;
-                if (p.init_state == nullptr) p.reset_epoch[env] = epoch + attempts;
-                const int len = p.ep_len[env];
-                if (p.stats != nullptr) {
-                    if (len > 0) {
-                        atomicAdd(&p.stats[FLOCK_STAT_EPISODES], 1ULL);
-                        atomicAdd(&p.stats[FLOCK_STAT_EP_STEPS], (unsigned long long)len);
-                        if (p.ep_return_fx != nullptr)
-                            atomicAdd(&p.stats[FLOCK_STAT_EP_RETURN_FX], (unsigned long long)p.ep_return_fx[env]);
-                    }
-                    if (p.init_state == nullptr) {
-                        atomicAdd(&p.stats[FLOCK_STAT_RESET_ATTEMPTS], (unsigned long long)attempts);
-                        if (env_coll) atomicAdd(&p.stats[FLOCK_STAT_RESET_GAVE_UP], 1ULL);
-                    }
-                }
-                p.ep_len[env] = 0;
-                if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = 0;
-            }
-        }
+        reset_groups<K>(p, m, sx, sy, env, idx, live, (p.reset_flags & FLOCK_RESET_KEEP_OUTPUTS) != 0);
     }
 }
 
@@ -562,10 +579,14 @@ template <int V, int K, bool PER, int NJ4>
 static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_count, cudaStream_t s) {
     const int grid = small_grid(p, sm_count);
     if (multi) {
-        flock_step_small_kernel<V, K, PER, true, NJ4, false><<<grid, kSmallThreads, 0, s>>>(p);
+        flock_step_small_kernel<V, K, PER, true, NJ4, false, false><<<grid, kSmallThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
     const bool mirror = p.m_obs != nullptr;
+    if (p.fused_auto_reset && !mirror) {   // step + restart of the finished envs in one launch
+        flock_step_small_kernel<V, K, PER, false, NJ4, false, true><<<grid, kSmallThreads, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     // Programmatic dependent launch (default on, FLOCK_PDL=0 disables): the kernel triggers its
     // dependents right before its epilogue, so the next step's launch overlaps our result stores.
     static const bool use_pdl = [] {
@@ -573,8 +594,8 @@ static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_co
         return v == nullptr || v[0] != '0';
     }();
     if (!use_pdl) {
-        if (mirror) flock_step_small_kernel<V, K, PER, false, NJ4, true><<<grid, kSmallThreads, 0, s>>>(p);
-        else flock_step_small_kernel<V, K, PER, false, NJ4, false><<<grid, kSmallThreads, 0, s>>>(p);
+        if (mirror) flock_step_small_kernel<V, K, PER, false, NJ4, true, false><<<grid, kSmallThreads, 0, s>>>(p);
+        else flock_step_small_kernel<V, K, PER, false, NJ4, false, false><<<grid, kSmallThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -587,8 +608,8 @@ static cudaError_t launch_step_small_vkpn(const Params& p, bool multi, int sm_co
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (mirror) return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, true>, p);
-    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, false>, p);
+    if (mirror) return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, true, false>, p);
+    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, false, false>, p);
 }
 
 // unrolled pair loops for the strides of the BASELINE configs (N = 9..12, 13..16, 29..32)

@@ -97,6 +97,7 @@ class VecEnv:
         self._h = handle
         self.tiled = self.lib.flock_path(self._h) == 1
         check(self.lib.flock_set_tiled_mode(self._h, int(tiled_mode)))
+        check(self.lib.flock_set_auto_reset(self._h, int(self.auto_reset), self.max_reset_attempts))
         E, N, H = self.num_envs, self.num_particles, self.obs_hist
         f32 = dict(dtype=torch.float32, device=self.device)
         z = lambda *shape, **kw: torch.zeros(*shape, **{**f32, **kw})
@@ -280,12 +281,7 @@ class VecEnv:
             rc = self.lib.flock_step(self._h, a.data_ptr(), dt, None if nz is None else nz.data_ptr(), self._stream())
             if rc:
                 check(rc)
-            info: Dict = {}
-            if self.auto_reset:
-                # finished envs restart in place; reward / dones of the finishing step are kept and
-                # the returned obs of those envs is the first observation of the new episode
-                check(self.lib.flock_reset(self._h, self._env_done.data_ptr(), None, self.max_reset_attempts,
-                                           _lib.FLOCK_RESET_KEEP_OUTPUTS, self._stream()))
+            info: Dict = {}   # auto-reset, when enabled, happens inside flock_step (flock_set_auto_reset)
         return self._obs_view, self._reward, (self._agent_done, self._env_done), info
 
     def step_n(self, num_steps: int, dt: float = 0.1):
