@@ -76,13 +76,12 @@ Params make_params(const flock_env* e, float dt) {
     Params p;
     memset(&p, 0, sizeof(p));
     p.E = c.num_envs; p.N = c.num_agents; p.k = c.k; p.H = c.obs_hist;
-    p.rigid = c.rigid_boundary; p.env_offset = c.env_offset;
+    p.env_offset = c.env_offset;
     p.G = c.num_agents <= 32 ? 32 / c.num_agents : 0;
     p.sstride = (c.num_agents + 3) & ~3;
     p.g_magic = (65536 + c.num_agents - 1) / c.num_agents;
     p.num_tasks = p.G > 0 ? (c.num_envs + p.G - 1) / p.G : 0;
     p.B = c.boundary;
-    p.halfB = (float)((double)c.boundary / 2.0);
     p.sensor_range = c.sensor_range;
     p.cd = c.collision_distance;
     p.cd4 = (float)((double)c.collision_distance * 4.0);   // gym_flock_uw.py:197

@@ -21,12 +21,12 @@ enum : uint32_t { kTagReset = 0u, kTagNoise = 1u, kTagAction = 2u, kTagRange = 3
 // Kernel parameters (passed by value as a __grid_constant__).
 struct Params {
     int E, N, k, H;
-    int rigid, env_offset;
+    int env_offset;
     int G;        // envs per warp (small path)
     int g_magic;  // ceil(65536 / N): lane / N == (lane * g_magic) >> 16 for lane < 32
     int num_tasks;  // ceil(E / G)
     int sstride;  // shared-memory stride of one env group, floats (small path)
-    float B, halfB, sensor_range, cd, cd4, vmax, noise_std, dt;
+    float B, sensor_range, cd, cd4, vmax, noise_std, dt;
     float range_lo, reset_hi, heading_hi, reset_cd;
     float fill_hi, fill_lo;   // check_boundary replacement values (see wrap_coord)
     float range_noise_std;
