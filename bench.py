@@ -30,9 +30,11 @@ WORKLOADS = {
     "cfg2": dict(variant="v2", E=4096, N=10, k=4, cd=2.5, rs=(0, 50), sr=14.0, kw={}, bytes=53,
                  desc="gym_flock_v2 batched 4096 envs x 10 agents, k=4, random actions (BASELINE configs[1])"),
     "cfg3": dict(variant="uw", E=4096, N=32, k=3, cd=0.5, rs=(0, 200), sr=7.0, kw={}, bytes=125,
+                 env_kw=dict(track_neighbors=False),   # the reference discards the indices in uw (gym_flock_uw.py:141-144)
                  desc="gym_flock_uw 4096 envs x 32 agents, k=3, random actions, materialised (N,4,k) window"),
     "cfg4": dict(variant="uwd", E=8192, N=16, k=4, cd=0.5, rs=(0, 100), sr=7.0,
                  kw=dict(reset_collision_distance=1.0), bytes=49,
+                 env_kw=dict(track_neighbors=False),   # ... and in uw_discrete (gym_flock_uw_discrete.py:189-192)
                  desc="gym_flock_uw_discrete 8192 envs x 16 agents, k=4, random action ids, Philox actuation noise"),
     "cfg5": dict(variant="v2", E=64, N=2048, k=8, cd=0.05, rs=(0, 2000), sr=100.0, kw={}, bytes=69,
                  desc="gym_flock_v2 large swarm 64 envs x 2048 agents, k=8 (tiled all-pairs path)"),
@@ -166,7 +168,7 @@ def build_ring(w, E, ring, device, env_offset, seed=0x5EED):
     envs, acts = [], []
     for r in range(ring):
         env = VecEnv(w["variant"], E, w["N"], w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"],
-                     seed=seed + r, env_offset=env_offset, device=device, **w["kw"])
+                     seed=seed + r, env_offset=env_offset, device=device, **w["kw"], **w.get("env_kw", {}))
         env.reset()
         envs.append(env)
         acts.append([env.random_actions(i) for i in range(2)])
@@ -323,7 +325,7 @@ def run_gpu(args, w):
         peak_, _ = _peaks()
         big_E = E * ring
         big = VecEnv(w["variant"], big_E, N, w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"], seed=1,
-                     device=device, **w["kw"])
+                     device=device, **w["kw"], **w.get("env_kw", {}))
         big.reset()
         big_act = [big.random_actions(i) for i in range(2)]
         for i in range(3):

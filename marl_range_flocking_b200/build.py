@@ -15,8 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libflock_b200.so")
-SOURCES = ["flock_small.cu", "flock_tiled.cu", "flock_api.cu"]
-HEADERS = ["flock_device.cuh", "flock_launch.h", os.path.join("..", "..", "include", "flock_b200.h")]
+SOURCES = ["flock_small_v2p.cu", "flock_small_v2e.cu", "flock_small_uw.cu", "flock_small_uwn.cu", "flock_small_uwd.cu",
+           "flock_small_uwdn.cu", "flock_small.cu", "flock_tiled.cu", "flock_api.cu"]
+HEADERS = ["flock_device.cuh", "flock_small_impl.cuh", "flock_launch.h", os.path.join("..", "..", "include", "flock_b200.h")]
 
 # -fmad=false: no implicit FMA contraction (canonical arithmetic); explicit fmaf()/fma()
 # calls still emit FFMA/DFMA. Precise division / sqrt, denormals kept (the nvcc defaults, stated).
@@ -52,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
-    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with cf.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         for res in ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs):
             if verbose or res.returncode != 0:
                 sys.stderr.write(res.stdout + res.stderr)

@@ -323,10 +323,29 @@ struct TopK {
     __device__ __forceinline__ float worst() const { return d[K - 1]; }
 };
 
+// Values-only variant: the k smallest d2 WITH multiplicity (a min/max network, 2 FMNMX per slot), no
+// index tracking. The reference discards the neighbour indices in uw / uwd
+// (gym_flock_uw.py:141-144, gym_flock_uw_discrete.py:189-192), and the ranges -- hence obs,
+// collisions, dones, rewards -- are identical to the indexed list.
+template <int K>
+struct TopKValues {
+    float d[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < K; ++s) d[s] = kInf;
+    }
+    __device__ __forceinline__ void insert(float c, int) {
+#pragma unroll
+        for (int s = K - 1; s > 0; --s) d[s] = fminf(d[s], fmaxf(d[s - 1], c));
+        d[0] = fminf(d[0], c);
+    }
+    __device__ __forceinline__ float worst() const { return d[K - 1]; }
+};
+
 // sqrt + clamp(0, sensor_range) of the k winners (gym_flock_v2.py:151) and the collision flag
 // (gym_flock_v2.py:212-215, 314).
-template <int K>
-__device__ __forceinline__ bool finish_row(const TopK<K>& t, int k, float sensor_range, float cd, float* dist) {
+template <int K, typename List>
+__device__ __forceinline__ bool finish_row(const List& t, int k, float sensor_range, float cd, float* dist) {
     bool coll = false;
 #pragma unroll
     for (int s = 0; s < K; ++s) {

@@ -1,0 +1,7 @@
+// flock_small_uwn.cu -- explicit instantiation of the small-path step kernels for one variant
+// (V = FLOCK_UW, periodic metric = false, neighbour indices tracked = false); see flock_small_impl.cuh.
+#include "flock_small_impl.cuh"
+
+namespace flock {
+template cudaError_t launch_step_small_vpi<FLOCK_UW, false, false>(const Params&, bool, int, cudaStream_t);
+}  // namespace flock

@@ -52,7 +52,8 @@ def compare_all(env, orc, check_reward=True, tag=""):
     assert_same(tag + "vx", env._vx, orc.vx)
     assert_same(tag + "vy", env._vy, orc.vy)
     assert_same(tag + "obs", env._obs, orc.obs)
-    assert_same(tag + "nn", env.nearest_neighbors, orc.nn)
+    if env._nn is not None:
+        assert_same(tag + "nn", env.nearest_neighbors, orc.nn)
     assert_same(tag + "agent_done", env.dones[0].to(torch.uint8), orc.agent_done)
     assert_same(tag + "env_done", env.dones[1].to(torch.uint8), orc.env_done)
     if check_reward:

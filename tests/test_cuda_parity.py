@@ -554,3 +554,32 @@ def test_optional_range_sensing_noise_bit_exact(variant, E, N, k):
     orc.step(a, 0.1)
     obs, *_ = env.step_host(torch.from_numpy(a).pin_memory(), 0.1)      # staged path (noise after the step)
     assert_same("noisy host obs", obs, orc.obs if env.obs_hist > 1 else orc.obs[:, :, 0, :])
+
+
+@pytest.mark.parametrize("variant,E,N,k", [("uw", 64, 32, 3), ("uw", 40, 12, 4), ("uwd", 64, 16, 4), ("uwd", 30, 9, 8),
+                                           ("uw", 17, 5, 2), ("v2", 50, 10, 4)])
+def test_values_only_selection_when_indices_are_not_tracked(variant, E, N, k):
+    """track_neighbors=False: uw / uwd use the values-only selection network (the reference discards
+    the indices there); every other buffer must still match the oracle bit for bit."""
+    env, orc = make_pair(variant, E, N, k, 0.5, (0, 40), 9.0, seed=13, track_neighbors=False, auto_reset=(N == 12))
+    env.reset()
+    orc.reset()
+    compare_all(env, orc, tag="reset:")
+    for t in range(25):
+        a = orc.random_actions()
+        orc.step(a, 0.1)
+        if N == 12:
+            orc.reset(mask=orc.env_done.copy(), keep_outputs=True)
+        env.step(torch.from_numpy(a).cuda(), 0.1)
+        compare_all(env, orc, tag=f"step {t}:")
+    if N != 12:
+        env.step_n(7, 0.1)
+        for _ in range(7):
+            orc.step(orc.random_actions(), 0.1)
+        compare_all(env, orc, tag="step_n:")
+    a = orc.random_actions()
+    orc.step(a, 0.1)
+    if N == 12:
+        orc.reset(mask=orc.env_done.copy(), keep_outputs=True)
+    obs, *_ = env.step_host(torch.from_numpy(a).pin_memory(), 0.1)
+    assert_same("host obs", obs, orc.obs if env.obs_hist > 1 else orc.obs[:, :, 0, :])
