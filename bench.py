@@ -408,8 +408,14 @@ def main():
     ap.add_argument("--ring", type=int, default=0, help="number of env batches in the L2-defeating ring (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the large-batch roofline leg")
+    ap.add_argument("--no-index", action="store_true",
+                    help="do not track neighbour indices (values-only selection); default for uw / uwd, where the "
+                         "reference discards them, opt-in for v2, where the reference keeps `nearest_neighbors`")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.no_index:
+        w["env_kw"] = dict(w.get("env_kw", {}), track_neighbors=False)
+        w["desc"] += " [neighbour indices not tracked]"
     if args.impl == "reference":
         run_reference(args, w)
     else:

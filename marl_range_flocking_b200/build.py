@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libflock_b200.so")
-SOURCES = ["flock_small_v2p.cu", "flock_small_v2e.cu", "flock_small_uw.cu", "flock_small_uwn.cu", "flock_small_uwd.cu",
+SOURCES = ["flock_small_v2p.cu", "flock_small_v2e.cu", "flock_small_v2pn.cu", "flock_small_v2en.cu", "flock_small_uw.cu", "flock_small_uwn.cu", "flock_small_uwd.cu",
            "flock_small_uwdn.cu", "flock_small.cu", "flock_tiled.cu", "flock_api.cu"]
 HEADERS = ["flock_device.cuh", "flock_small_impl.cuh", "flock_launch.h", os.path.join("..", "..", "include", "flock_b200.h")]
 

@@ -89,11 +89,14 @@ __global__ void flock_debug_philox_kernel(const uint32_t* ck, int n, uint32_t* o
 
 // -------------------------------------------------------------------------------------------------
 // host-side dispatch. The step kernels live in flock_small_<variant>.cu (explicit instantiations).
-// v2 always tracks the neighbour indices (the reference keeps `nearest_neighbors`, gym_flock_v2.py:150);
-// uw / uwd track them only when the caller bound an nn_idx buffer (the reference discards them).
+// Neighbour indices are tracked only when the caller bound an nn_idx buffer: the reference keeps
+// `nearest_neighbors` in v2 (gym_flock_v2.py:150, VecEnv default track_neighbors=True) and discards
+// the indices in uw / uwd; without the buffer the values-only selection network is used.
 // -------------------------------------------------------------------------------------------------
 extern template cudaError_t launch_step_small_vpi<FLOCK_V2, true, true>(const Params&, bool, int, cudaStream_t);
 extern template cudaError_t launch_step_small_vpi<FLOCK_V2, false, true>(const Params&, bool, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_V2, true, false>(const Params&, bool, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_V2, false, false>(const Params&, bool, int, cudaStream_t);
 extern template cudaError_t launch_step_small_vpi<FLOCK_UW, false, true>(const Params&, bool, int, cudaStream_t);
 extern template cudaError_t launch_step_small_vpi<FLOCK_UW, false, false>(const Params&, bool, int, cudaStream_t);
 extern template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, true>(const Params&, bool, int, cudaStream_t);
@@ -103,8 +106,11 @@ cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool 
     const bool idx = p.nn != nullptr;
     switch (variant) {
         case FLOCK_V2:
-            return periodic ? launch_step_small_vpi<FLOCK_V2, true, true>(p, multi, sm_count, s)
-                            : launch_step_small_vpi<FLOCK_V2, false, true>(p, multi, sm_count, s);
+            if (idx)
+                return periodic ? launch_step_small_vpi<FLOCK_V2, true, true>(p, multi, sm_count, s)
+                                : launch_step_small_vpi<FLOCK_V2, false, true>(p, multi, sm_count, s);
+            return periodic ? launch_step_small_vpi<FLOCK_V2, true, false>(p, multi, sm_count, s)
+                            : launch_step_small_vpi<FLOCK_V2, false, false>(p, multi, sm_count, s);
         case FLOCK_UW:
             return idx ? launch_step_small_vpi<FLOCK_UW, false, true>(p, multi, sm_count, s)
                        : launch_step_small_vpi<FLOCK_UW, false, false>(p, multi, sm_count, s);
