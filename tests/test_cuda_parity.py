@@ -557,7 +557,7 @@ def test_optional_range_sensing_noise_bit_exact(variant, E, N, k):
 
 
 @pytest.mark.parametrize("variant,E,N,k", [("uw", 64, 32, 3), ("uw", 40, 12, 4), ("uwd", 64, 16, 4), ("uwd", 30, 9, 8),
-                                           ("uw", 17, 5, 2), ("v2", 50, 10, 4)])
+                                           ("uw", 17, 5, 2), ("v2", 50, 10, 4), ("v2", 3, 70, 4), ("uwd", 2, 130, 8)])
 def test_values_only_selection_when_indices_are_not_tracked(variant, E, N, k):
     """track_neighbors=False: uw / uwd use the values-only selection network (the reference discards
     the indices there); every other buffer must still match the oracle bit for bit."""
