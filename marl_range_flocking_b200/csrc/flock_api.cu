@@ -93,6 +93,7 @@ Params make_params(const flock_env* e, float dt) {
     p.fill_hi = c.rigid_boundary ? c.boundary : 0.001f;
     p.fill_lo = c.rigid_boundary ? 0.0f : c.boundary;
     p.range_noise_std = c.range_noise_std;
+    p.inv_n = (c.num_agents & (c.num_agents - 1)) == 0 ? 1.0f / (float)c.num_agents : 0.0f;
     p.seed_lo = (uint32_t)c.seed; p.seed_hi = (uint32_t)(c.seed >> 32);
     p.step_offset = 0;
     p.num_steps = 1;

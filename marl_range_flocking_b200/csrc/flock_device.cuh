@@ -30,6 +30,7 @@ struct Params {
     float range_lo, reset_hi, heading_hi, reset_cd;
     float fill_hi, fill_lo;   // check_boundary replacement values (see wrap_coord)
     float range_noise_std;
+    float inv_n;      // 1/N when N is a power of two (x * inv_n == x / N bit for bit), else 0
     uint32_t seed_lo, seed_hi, step_offset;   // step_offset: flock_random_actions look-ahead
     int num_steps;      // step_n
     int max_attempts;   // reset
@@ -405,6 +406,13 @@ __device__ __forceinline__ float agent_reward(const Params& p, bool coll, float 
     bool f1, f2;
     reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);
     return reward_from_flags<V>(coll, f1, f2);
+}
+
+// mean over the env's agents: sum / N (torch.mean, gym_flock_uw.py:193; sum/N, uwd:256). For a
+// power-of-two N the division is an exact scaling, so the multiply by 1/N gives the identical
+// correctly rounded result without the IEEE division sequence.
+__device__ __forceinline__ float mean_of_sum(const Params& p, float sum) {
+    return p.inv_n != 0.0f ? sum * p.inv_n : __fdiv_rn(sum, (float)p.N);
 }
 
 // reward in 2^-32 fixed point (order-free integer accumulation of episode returns)

@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 const float* sxg = sx + m.g * sstride;
                 const float* syg = sy + m.g * sstride;
                 float comx = 0.f, comy = 0.f, hmean = 0.f, sumx, sumy;
-                if (V == FLOCK_UWD) hmean = __fdiv_rn(seq_sum(sh + m.g * sstride, N), (float)N);  // uwd:256
+                if (V == FLOCK_UWD) hmean = mean_of_sum(p, seq_sum(sh + m.g * sstride, N));  // uwd:256
                 knn_small<K, PER, NJ4, V == FLOCK_UW, List>(sxg, syg, m.a, N, sstride, x, y, p.B, t, sumx, sumy);
                 if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
-                    comx = __fdiv_rn(sumx, (float)N);
-                    comy = __fdiv_rn(sumy, (float)N);
+                    comx = mean_of_sum(p, sumx);
+                    comy = mean_of_sum(p, sumy);
                 }
                 coll = finish_row<K, List>(t, k, p.sensor_range, p.cd, dist);
                 reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);

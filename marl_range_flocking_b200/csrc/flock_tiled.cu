@@ -280,13 +280,13 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
             sx_ = sx_ + sm.sx[j];
             sy_ = sy_ + sm.sy[j];
         }
-        comx = __fdiv_rn(sx_, (float)N);
-        comy = __fdiv_rn(sy_, (float)N);
+        comx = mean_of_sum(p, sx_);
+        comy = mean_of_sum(p, sy_);
     }
     if (V == FLOCK_UWD) {
         float sh_ = 0.f;
         for (int j = 0; j < N; ++j) sh_ = sh_ + sm.sh[j];
-        hmean = __fdiv_rn(sh_, (float)N);
+        hmean = mean_of_sum(p, sh_);
     }
 
     long long fx = 0;
@@ -456,13 +456,13 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(con
             sx_ = sx_ + sm.sx[j];
             sy_ = sy_ + sm.sy[j];
         }
-        comx = __fdiv_rn(sx_, (float)N);
-        comy = __fdiv_rn(sy_, (float)N);
+        comx = mean_of_sum(p, sx_);
+        comy = mean_of_sum(p, sy_);
     }
     if (V == FLOCK_UWD) {
         float sh_ = 0.f;
         for (int j = 0; j < N; ++j) sh_ = sh_ + sm.sh[j];
-        hmean = __fdiv_rn(sh_, (float)N);
+        hmean = mean_of_sum(p, sh_);
     }
 
     long long fx_acc = 0;
