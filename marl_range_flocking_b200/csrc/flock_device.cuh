@@ -105,31 +105,29 @@ __device__ __forceinline__ void sincos_canon(float h, float& sn, float& cs) {
     cs = co;
 }
 
-// ln(m * 2^-24), m integer in [1, 2^24], fp64 with explicit fma (Box-Muller radius).
-__device__ __forceinline__ double log_u24(uint32_t m) {
-    const double u = (double)m * (1.0 / 16777216.0);
-    unsigned long long bits = (unsigned long long)__double_as_longlong(u);
-    int e = (int)((bits >> 52) & 0x7ffULL) - 1022;
-    bits = (bits & 0x000fffffffffffffULL) | 0x3fe0000000000000ULL;
-    double f = __longlong_as_double((long long)bits);
-    if (f < 0.70710678118654752440) {
-        f = f * 2.0;
+// ln(m * 2^-24), m integer in [1, 2^24], binary32 with explicit fmaf (Box-Muller radius; ~1e-7
+// absolute error, irrelevant for a noise source but bit-identical to the oracle's restatement):
+// u = f * 2^e with f in [sqrt(1/2), sqrt(2)), s = (f-1)/(f+1), ln f = 2s(1 + s^2/3 + ... + s^8/9).
+__device__ __forceinline__ float log_u24(uint32_t m) {
+    const float u = (float)m * (1.0f / 16777216.0f);
+    uint32_t bits = __float_as_uint(u);
+    int e = (int)((bits >> 23) & 0xffu) - 126;
+    bits = (bits & 0x007fffffu) | 0x3f000000u;
+    float f = __uint_as_float(bits);                 // [0.5, 1)
+    if (f < 0.70710678118654752440f) {
+        f = f * 2.0f;
         e -= 1;
     }
-    const double s = (f - 1.0) / (f + 1.0);
-    const double s2 = s * s;
-    double p = 1.0 / 19.0;
-    p = fma(p, s2, 1.0 / 17.0);
-    p = fma(p, s2, 1.0 / 15.0);
-    p = fma(p, s2, 1.0 / 13.0);
-    p = fma(p, s2, 1.0 / 11.0);
-    p = fma(p, s2, 1.0 / 9.0);
-    p = fma(p, s2, 1.0 / 7.0);
-    p = fma(p, s2, 1.0 / 5.0);
-    p = fma(p, s2, 1.0 / 3.0);
-    p = fma(p, s2, 1.0);
-    const double lnf = 2.0 * s * p;
-    return fma((double)e, 0.69314718055994530942, lnf);
+    const float s = __fdiv_rn(f - 1.0f, f + 1.0f);
+    const float s2 = s * s;
+    float p = 1.0f / 9.0f;
+    p = fmaf(p, s2, 1.0f / 7.0f);
+    p = fmaf(p, s2, 1.0f / 5.0f);
+    p = fmaf(p, s2, 1.0f / 3.0f);
+    p = fmaf(p, s2, 1.0f);
+    const float two_s = 2.0f * s;
+    const float lnf = two_s * p;
+    return fmaf((float)e, 0.69314718055994530942f, lnf);
 }
 
 // Philox4x32-10, counter-based (Salmon et al. SC'11).
@@ -152,13 +150,13 @@ __device__ __forceinline__ float u24(uint32_t r) { return (float)(r >> 8) * (1.0
 
 // two standard normals from two 32-bit words (Box-Muller on the canonical log / sincos)
 __device__ __forceinline__ void normal2(uint32_t r0, uint32_t r1, float& z0, float& z1) {
-    const double ln = log_u24((r0 >> 8) + 1u);
-    const double rad = sqrt(-2.0 * ln);
+    const float ln = log_u24((r0 >> 8) + 1u);          // u1 in (0, 1]  =>  ln <= 0
+    const float rad = __fsqrt_rn(-2.0f * ln);
     const float theta = 6.28318530717958647692f * u24(r1);
     float sn, cs;
     sincos_canon(theta, sn, cs);
-    z0 = (float)(rad * (double)cs);
-    z1 = (float)(rad * (double)sn);
+    z0 = rad * cs;
+    z1 = rad * sn;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -92,29 +92,27 @@ static void flock_sincosf(float h, float *sn, float *cs)
     *sn = so; *cs = co;
 }
 
-/* natural log of m * 2^-24 for an integer m in [1, 2^24], in fp64 with explicit fma. */
-static double flock_log_u24(uint32_t m)
+/* natural log of m * 2^-24 for an integer m in [1, 2^24], binary32 with explicit fmaf (canonical
+ * definition shared with the CUDA kernels; accuracy ~1e-7 absolute, plenty for a noise source). */
+static float flock_log_u24(uint32_t m)
 {
-    double u = (double)m * (1.0 / 16777216.0);
-    uint64_t bits; memcpy(&bits, &u, 8);
-    int e = (int)((bits >> 52) & 0x7ff) - 1022;               /* u = f * 2^e, f in [0.5,1) */
-    bits = (bits & 0x000fffffffffffffULL) | 0x3fe0000000000000ULL;
-    double f; memcpy(&f, &bits, 8);
-    if (f < 0.70710678118654752440) { f = f * 2.0; e -= 1; }  /* f in [sqrt.5, sqrt2) */
-    double s = (f - 1.0) / (f + 1.0);
-    double s2 = s * s;
-    double p = 1.0 / 19.0;
-    p = fma(p, s2, 1.0 / 17.0);
-    p = fma(p, s2, 1.0 / 15.0);
-    p = fma(p, s2, 1.0 / 13.0);
-    p = fma(p, s2, 1.0 / 11.0);
-    p = fma(p, s2, 1.0 / 9.0);
-    p = fma(p, s2, 1.0 / 7.0);
-    p = fma(p, s2, 1.0 / 5.0);
-    p = fma(p, s2, 1.0 / 3.0);
-    p = fma(p, s2, 1.0);
-    double lnf = 2.0 * s * p;
-    return fma((double)e, 0.69314718055994530942, lnf);
+    float u = (float)m * (1.0f / 16777216.0f);
+    uint32_t bits; memcpy(&bits, &u, 4);
+    int e = (int)((bits >> 23) & 0xffu) - 126;                /* u = f * 2^e, f in [0.5,1) */
+    bits = (bits & 0x007fffffu) | 0x3f000000u;
+    float f; memcpy(&f, &bits, 4);
+    if (f < 0.70710678118654752440f) { f = f * 2.0f; e -= 1; } /* f in [sqrt.5, sqrt2) */
+    float num = f - 1.0f, den = f + 1.0f;
+    float s = num / den;
+    float s2 = s * s;
+    float p = 1.0f / 9.0f;
+    p = fmaf(p, s2, 1.0f / 7.0f);
+    p = fmaf(p, s2, 1.0f / 5.0f);
+    p = fmaf(p, s2, 1.0f / 3.0f);
+    p = fmaf(p, s2, 1.0f);
+    float two_s = 2.0f * s;
+    float lnf = two_s * p;
+    return fmaf((float)e, 0.69314718055994530942f, lnf);
 }
 
 /* Philox4x32-10 (Salmon et al., SC'11; constants of Random123 philox.h). */
@@ -150,13 +148,14 @@ static float u24(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); } 
 /* two independent standard normals (Box-Muller) from two 32-bit words */
 static void flock_normal2(uint32_t r0, uint32_t r1, float *z0, float *z1)
 {
-    double ln = flock_log_u24((r0 >> 8) + 1u);              /* u1 in (0,1] */
-    double rad = sqrt(-2.0 * ln);
+    float ln = flock_log_u24((r0 >> 8) + 1u);               /* u1 in (0,1] => ln <= 0 */
+    float m2 = -2.0f * ln;
+    float rad = sqrtf(m2);
     float theta = 6.28318530717958647692f * u24(r1);
     float sn, cs;
     flock_sincosf(theta, &sn, &cs);
-    *z0 = (float)(rad * (double)cs);
-    *z1 = (float)(rad * (double)sn);
+    *z0 = rad * cs;
+    *z1 = rad * sn;
 }
 
 void orc_sincosf(const float *h, int n, float *sn, float *cs)
