@@ -157,9 +157,15 @@ FLOCK_API int flock_step_n(flock_env_t *env, int num_steps, float dt, void *stre
  * are per-env device counters, so streams do not depend on the GPU count or on host state. */
 FLOCK_API int flock_random_actions(flock_env_t *env, uint32_t step_offset, float *actions, void *stream);
 
-/* Host-buffer form of step(): copies `h_actions` (pinned or pageable host memory) to the device,
- * runs the fused step, copies obs / reward / agent_done / env_done back and synchronises the
- * stream. Any output pointer may be NULL. This is the end-to-end path timed as `e2e`. */
+/* Host-buffer form of step(): host actions in, host obs / reward / agent_done / env_done out, stream
+ * synchronised before returning. This is the end-to-end path timed as `e2e`.
+ *   - pinned (device-visible) buffers, N <= 32: zero-copy -- the kernel reads the actions from host
+ *     memory and, when the result set is <= 3 MiB, also writes the results there itself;
+ *   - otherwise (pageable memory, N > 32, large result sets, auto-reset / sensing noise on): the
+ *     actions are staged with one copy and the results come back with one packed copy when the
+ *     caller laid obs | reward | agent_done | env_done out back to back on both sides.
+ * Any output pointer may be NULL (staged path). FLOCK_ZEROCOPY=0/1 in the environment overrides the
+ * policy. */
 FLOCK_API int flock_step_host(flock_env_t *env, const float *h_actions, float dt, const float *h_noise,
                     float *h_obs, float *h_reward, uint8_t *h_agent_done, uint8_t *h_env_done,
                     void *stream);
