@@ -345,6 +345,31 @@ def run_gpu(args, w):
                                 "note": "one launch over envs = E x ring; working set > L2, same fused kernel"}
         del big, big_act
 
+    # optional: closed-loop rollout with the batched per-agent actors of the shared-critic DDPG learner
+    # (BASELINE configs[2] "MADDPG actor rollout"; SURVEY 8f-2: the policy, not the env, bounds it)
+    if rank == 0 and args.policy == "actor" and w["variant"] != "uwd":
+        from marl_range_flocking_b200.policies import BatchedActors
+        env = envs[0]
+        obs = env.observation
+        in_dims = obs[0, 0].numel()
+        for dtype, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            actors = BatchedActors(N, in_dims, 400, 300, 2, device=device, dtype=dtype)
+            with torch.no_grad():
+                for _ in range(5):
+                    obs, *_ = env.step(actors(obs), DT)
+                torch.cuda.synchronize(device)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 100
+                ev0.record()
+                for _ in range(reps):
+                    obs, *_ = env.step(actors(obs), DT)
+                ev1.record()
+                torch.cuda.synchronize(device)
+            t = ev0.elapsed_time(ev1) * 1e-3 / reps
+            extra.setdefault("actor_rollout", {})[name] = {
+                "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
+                "policy": f"{N} per-agent MLPs {in_dims}-400-300-2 (LayerNorm, ReLU, tanh) as baddbmm over the agent dim"}
+
     if rank == 0:
         peak, peak_src = _peaks()
         per_launch_s = ms_max * 1e-3 / steps
@@ -408,6 +433,8 @@ def main():
     ap.add_argument("--ring", type=int, default=0, help="number of env batches in the L2-defeating ring (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the large-batch roofline leg")
+    ap.add_argument("--policy", default="none", choices=["none", "actor"],
+                    help="extra leg: closed-loop rollout with batched per-agent actors (policies.BatchedActors)")
     ap.add_argument("--no-index", action="store_true",
                     help="do not track neighbour indices (values-only selection); default for uw / uwd, where the "
                          "reference discards them, opt-in for v2, where the reference keeps `nearest_neighbors`")
