@@ -127,7 +127,7 @@ def test_numpy_restatement_agrees_bit_for_bit(variant, N, k, B, sr, cd):
             assert np.array_equal(_bits(r["prev_h"]), _bits(env.prev_h[e])) or variant == "v2"
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2**31 - 1), N=st.integers(3, 20), k=st.integers(1, 8))
 def test_permuting_agents_permutes_outputs(seed, N, k):
     k = min(k, N - 1)
