@@ -583,3 +583,83 @@ def test_values_only_selection_when_indices_are_not_tracked(variant, E, N, k):
         orc.reset(mask=orc.env_done.copy(), keep_outputs=True)
     obs, *_ = env.step_host(torch.from_numpy(a).pin_memory(), 0.1)
     assert_same("host obs", obs, orc.obs if env.obs_hist > 1 else orc.obs[:, :, 0, :])
+
+
+def _golden_files():
+    from tests.golden_util import traj_files
+    return traj_files()
+
+
+@pytest.mark.parametrize("path", _golden_files(), ids=[p.split("/")[-1][:-4] for p in _golden_files()])
+def test_cuda_free_running_against_reference_golden(path):
+    """The CUDA path DIRECTLY against the recorded outputs of the unmodified reference
+    (tests/golden/, produced by tests/golden/make_golden.py): same initial state, same actions (and
+    injected actuation noise), T free-running steps (1000 for BASELINE config 1). North-star
+    tolerance: k-NN index lists identical at every step, positions / headings / ranges within 1e-5
+    relative at the end, dones identical."""
+    from marl_range_flocking_b200 import VecEnv
+    from tests.golden_util import close, env_kwargs, load_traj, torus_close
+    g = load_traj(path)
+    v, cfg = g["variant"], g["cfg"]
+    kw = env_kwargs(v, cfg)
+    env = VecEnv(v, 1, kw["agents"], kw["k"], kw["collision_distance"], range_start=kw["range_start"],
+                 sensor_range=kw["sensor_range"], rigid_boundary=kw["rigid_boundary"])
+    B = float(kw["range_start"][1])
+    T = g["actions"].shape[0]
+    init = np.stack([g["pos0"][:, 0][None], g["pos0"][:, 1][None], g["h0"][None]])
+    obs0 = env.reset(init_state=torch.from_numpy(init).cuda())[0].cpu().numpy()
+    assert close(obs0, g["obs0"], 1e-5, 1e-6).all()
+    nn_bad = 0
+    acts = torch.from_numpy(g["actions"]).cuda()
+    noise = torch.from_numpy(g["noise"]).cuda() if "noise" in g else None
+    for t in range(T):
+        env.step(acts[t][None], float(g["dt"]), noise=None if noise is None else noise[t][None])
+        if "nn" in g:
+            nn_bad += int((env.nearest_neighbors[0].cpu().numpy() != g["nn"][t]).any(axis=1).sum())
+        if t % 50 == 49 or t == T - 1:
+            pos = env.positions[0].cpu().numpy()
+            assert torus_close(pos, g["pos"][t], B, 1e-5, 1e-5).all(), t
+            assert np.array_equal(env.dones[0][0].cpu().numpy(), g["agent_done"][t]), t
+    assert nn_bad == 0
+    assert close(env.headings[0].cpu().numpy(), g["h"][-1], 1e-5, 1e-6).all()
+    assert close(env.observation[0].cpu().numpy(), g["obs"][-1], 1e-5, 1e-5).all()
+    rew_ok = close(env.reward[0, :, 0].cpu().numpy(), g["reward"][-1][:, 0], 1e-6, 1e-7)
+    assert (~rew_ok).sum() <= 1      # a thresholded mean whose summation order torch leaves undefined
+
+
+def test_cuda_edge_cases_against_reference_golden():
+    """Single steps from hand-built states (walls, rigid boundary, NaN / Inf actions, zero action,
+    k = N-1, dt != 0.1, history window, coincident agents) against the reference's recorded outputs."""
+    from marl_range_flocking_b200 import VecEnv
+    from tests.golden_util import close, env_kwargs, load_edges
+    for case in load_edges():
+        v, cfg = case["variant"], case["cfg"]
+        kw = env_kwargs(v, cfg)
+        env = VecEnv(v, 1, kw["agents"], kw["k"], kw["collision_distance"], range_start=kw["range_start"],
+                     sensor_range=kw["sensor_range"], rigid_boundary=kw["rigid_boundary"])
+        pos, h = case["pos_in"], case["h_in"]
+        N = len(h)
+        state = dict(x=torch.from_numpy(pos[:, 0][None].copy()), y=torch.from_numpy(pos[:, 1][None].copy()),
+                     headings=torch.from_numpy(h[None].copy()),
+                     prev_headings=torch.from_numpy(case.get("prev_h_in", np.zeros_like(h))[None].copy()))
+        if "obs_mem_in" in case:
+            state["obs"] = torch.from_numpy(case["obs_mem_in"][None].copy())
+        env.set_state(state)
+        noise = None
+        if v == "uwd":
+            noise = torch.from_numpy(case.get("noise_in", np.zeros((N, 2), np.float32))[None].copy()).cuda()
+        env.step(torch.from_numpy(case["action"][None].copy()).cuda(), float(case["dt"]), noise=noise)
+        label = case["label"]
+        assert close(env.positions[0].cpu().numpy(), case["out_pos"], 1e-6, 1e-6).all(), label
+        hh = env.headings[0].cpu().numpy()
+        fin = ~np.isnan(case["out_h"])
+        assert np.array_equal(np.isnan(hh), ~fin) and close(hh[fin], case["out_h"][fin], 1e-6, 1e-6).all(), label
+        assert close(env.velocities[0].cpu().numpy(), case["out_vel"], 1e-5, 1e-7).all(), label
+        assert close(env.observation[0].cpu().numpy(), case["out_obs"], 1e-5, 1e-6).all(), label
+        if "out_nn" in case:
+            ref_nn = case["out_nn"]
+            ok_rows = ~(ref_nn == np.arange(N)[:, None]).any(axis=1)      # upstream lists self for coincident pairs
+            assert np.array_equal(env.nearest_neighbors[0].cpu().numpy()[ok_rows], ref_nn[ok_rows]), label
+        assert np.array_equal(env.dones[0][0].cpu().numpy(), case["out_agent_done"]), label
+        assert bool(env.dones[1][0]) == bool(case["out_env_done"]), label
+        assert close(env.reward[0, :, 0].cpu().numpy(), case["out_reward"][:, 0], 1e-6, 1e-7).all(), label
