@@ -203,8 +203,7 @@ __device__ __forceinline__ void integrate_agent(const Params& p, float a0, float
         vy = u * sn;
     } else if (V == FLOCK_UW) {
         float n2 = a0 * a0;
-        const float ay2 = a1 * a1;
-        n2 = n2 + ay2;
+        n2 = fmaf(a1, a1, n2);                            // torch.norm (gym_flock_uw.py:294)
         const float n = __fsqrt_rn(n2);
         vx = __fdiv_rn(a0, n);
         vy = __fdiv_rn(a1, n);
@@ -226,8 +225,7 @@ __device__ __forceinline__ void integrate_agent(const Params& p, float a0, float
         vx = u * cs;
         vy = u * sn;
         float n2 = vx * vx;
-        const float vy2 = vy * vy;
-        n2 = n2 + vy2;
+        n2 = fmaf(vy, vy, n2);                            // torch.norm (gym_flock_uw_discrete.py:358)
         const float n = __fsqrt_rn(n2);
         vx = __fdiv_rn(vx, n);
         vy = __fdiv_rn(vy, n);
@@ -290,6 +288,10 @@ __device__ __forceinline__ float pair_d2(float xi, float yi, float xj, float yj,
         dy = fminf(dy, B - dy);
     }
     const float a = dx * dx;
+    // Euclidean sites are torch.norm upstream, which accumulates the squares like an fma
+    // (fma(dy, dy, dx*dx): with this form the uw oracle reproduces the reference bit for bit);
+    // the periodic metric is an explicit multiply / add chain (gym_flock_v2.py:144): unfused.
+    if (!PER) return fmaf(dy, dy, a);
     const float b = dy * dy;
     return a + b;
 }
@@ -388,8 +390,7 @@ __device__ __forceinline__ void reward_flags(const Params& p, float x, float y, 
     if (V == FLOCK_UW) {
         const float ddx = x - comx, ddy = y - comy;
         float q = ddx * ddx;
-        const float q2 = ddy * ddy;
-        q = q + q2;
+        q = fmaf(ddy, ddy, q);                            // torch.norm (gym_flock_uw.py:194)
         const float dc = __fsqrt_rn(q);
         f1 = dc < p.cd4;
         f2 = fabsf(prev_h - h) > 0.27f;

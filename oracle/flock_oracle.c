@@ -224,8 +224,7 @@ static void integrate_agent(const orc_cfg_t *c, const float *act, float nzu, flo
     } else if (c->variant == 1) {
         float ax = act[0], ay = act[1];
         float n2 = ax * ax;
-        float ay2 = ay * ay;
-        n2 = n2 + ay2;
+        n2 = fmaf(ay, ay, n2);                     /* torch.norm accumulates like fma */
         float n = sqrtf(n2);
         vx = ax / n;
         vy = ay / n;
@@ -250,8 +249,7 @@ static void integrate_agent(const orc_cfg_t *c, const float *act, float nzu, flo
         vx = u * cs;
         vy = u * sn;
         float n2 = vx * vx;
-        float vy2 = vy * vy;
-        n2 = n2 + vy2;
+        n2 = fmaf(vy, vy, n2);
         float n = sqrtf(n2);
         vx = vx / n;
         vy = vy / n;
@@ -279,6 +277,10 @@ static float pair_d2(float xi, float yi, float xj, float yj, float B, float half
         if (dy > halfB) dy = B - dy;
     }
     float a = dx * dx;
+    /* Euclidean sites are torch.norm upstream, which accumulates like fma(dy, dy, dx*dx) (SURVEY 8c:
+     * with this form the uw golden trajectories are reproduced bit for bit); the periodic metric is an
+     * explicit multiply / add chain (gym_flock_v2.py:144) and stays unfused. */
+    if (!periodic) return fmaf(dy, dy, a);
     float b = dy * dy;
     return a + b;
 }
@@ -351,7 +353,7 @@ static int sense_env(const orc_cfg_t *c, int in_reset, const float *x, const flo
         } else if (c->variant == 1) {
             float pen = coll ? -5.0f : 0.01f;                      /* uw:186-189 */
             float ddx = x[i] - comx, ddy = y[i] - comy;            /* uw:191-197 */
-            float q = ddx * ddx; float q2 = ddy * ddy; q = q + q2;
+            float q = ddx * ddx; q = fmaf(ddy, ddy, q);
             float dc = sqrtf(q);
             float thr = (float)((double)c->collision_distance * 4.0);
             float rcom = dc < thr ? 0.01f : 0.0f;

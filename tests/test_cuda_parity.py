@@ -665,3 +665,26 @@ def test_cuda_edge_cases_against_reference_golden():
         assert np.array_equal(env.dones[0][0].cpu().numpy(), case["out_agent_done"]), label
         assert bool(env.dones[1][0]) == bool(case["out_env_done"]), label
         assert close(env.reward[0, :, 0].cpu().numpy(), case["out_reward"][:, 0], 1e-6, 1e-7).all(), label
+
+
+@pytest.mark.parametrize("path", [p for p in _golden_files() if "_uw_" in p],
+                         ids=[p.split("/")[-1][:-4] for p in _golden_files() if "_uw_" in p])
+def test_cuda_uw_is_bit_identical_to_the_reference(path):
+    """uw on the GPU, free-running, against the unmodified reference's recorded outputs: 0 ulp on
+    positions, displacements, the observation window, rewards and dones at every step."""
+    from marl_range_flocking_b200 import VecEnv
+    from tests.golden_util import env_kwargs, load_traj
+    g = load_traj(path)
+    kw = env_kwargs("uw", g["cfg"])
+    env = VecEnv("uw", 1, kw["agents"], kw["k"], kw["collision_distance"], range_start=kw["range_start"],
+                 sensor_range=kw["sensor_range"])
+    init = np.stack([g["pos0"][:, 0][None], g["pos0"][:, 1][None], g["h0"][None]])
+    env.reset(init_state=torch.from_numpy(init).cuda())
+    acts = torch.from_numpy(g["actions"]).cuda()
+    for t in range(g["actions"].shape[0]):
+        env.step(acts[t][None], float(g["dt"]))
+        assert_same(f"pos {t}", env.positions[0], g["pos"][t])
+        assert_same(f"vel {t}", env.velocities[0], g["vel"][t])
+        assert_same(f"obs {t}", env.observation[0], g["obs"][t])
+        assert_same(f"reward {t}", env.reward[0], g["reward"][t])
+        assert_same(f"done {t}", env.dones[0][0], g["agent_done"][t])

@@ -140,3 +140,26 @@ def test_edge_cases_against_reference(case):
     assert bool(env.env_done[0]) == bool(case["out_env_done"])
     assert close(env.reward[0], case["out_reward"][:, 0], 1e-6, 1e-7).all()
     assert close(env.prev_h[0][fin], case["out_prev_h"][fin], 1e-6, 1e-6).all()
+
+
+UW_TRAJ = [p for p in TRAJ if "_uw_" in p]
+
+
+@pytest.mark.parametrize("path", UW_TRAJ, ids=[p.split("/")[-1][:-4] for p in UW_TRAJ])
+def test_uw_free_running_is_bit_identical_to_the_reference(path):
+    """uw has no transcendental in its step (unit-vector motion, Euclidean torch.norm ranges), and
+    with the fma-like accumulation of torch.norm the restatement reproduces the reference BIT FOR
+    BIT: positions, displacements, the 4-row observation window, rewards and dones of every step."""
+    g = load_traj(path)
+    env = _mk("uw", g["cfg"])
+    env.reset(init=np.stack([g["pos0"][:, 0][None], g["pos0"][:, 1][None], g["h0"][None]]))
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    for t in range(g["actions"].shape[0]):
+        env.step(g["actions"][t][None], float(g["dt"]))
+        pos = np.stack([env.x[0], env.y[0]], axis=1)
+        vel = np.stack([env.vx[0], env.vy[0]], axis=1)
+        assert np.array_equal(bits(pos), bits(g["pos"][t])), t
+        assert np.array_equal(bits(vel), bits(g["vel"][t])), t
+        assert np.array_equal(bits(env.obs[0]), bits(g["obs"][t])), t
+        assert np.array_equal(bits(env.reward[0]), bits(g["reward"][t][:, 0])), t
+        assert np.array_equal(env.agent_done[0].astype(bool), g["agent_done"][t]), t

@@ -16,6 +16,12 @@ from oracle.flock_oracle import OracleEnv
 f32 = np.float32
 
 
+def fmaf_np(a, b, c):
+    """float32 fma through float64: the product is exact in binary64, so only the final conversion
+    rounds (up to a ~2^-29 double-rounding corner that the fixed seeds below do not hit)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+
 def np_step(variant, x, y, h, prev_h, act, dt, B, sr, cd, vmax, k, periodic, noise=None):
     """One env, numpy float32, straight from SURVEY appendix A.1 / A.3 / A.4."""
     x, y, h, prev_h = (a.astype(f32).copy() for a in (x, y, h, prev_h))
@@ -31,7 +37,7 @@ def np_step(variant, x, y, h, prev_h, act, dt, B, sr, cd, vmax, k, periodic, noi
             sn, cs = fo.sincosf(h)
             vx, vy = (u * cs).astype(f32), (u * sn).astype(f32)
         elif variant == "uw":
-            n = np.sqrt((act[:, 0] * act[:, 0] + act[:, 1] * act[:, 1]).astype(f32)).astype(f32)
+            n = np.sqrt(fmaf_np(act[:, 1], act[:, 1], (act[:, 0] * act[:, 0]).astype(f32))).astype(f32)
             vx, vy = (act[:, 0] / n).astype(f32), (act[:, 1] / n).astype(f32)
         else:
             ids = np.clip(np.nan_to_num(act, nan=0.0), 0, 9).astype(np.int64)
@@ -43,7 +49,7 @@ def np_step(variant, x, y, h, prev_h, act, dt, B, sr, cd, vmax, k, periodic, noi
             u = np.clip(u, f32(5e-6), f32(vmax))
             sn, cs = fo.sincosf(h)
             vx, vy = (u * cs).astype(f32), (u * sn).astype(f32)
-            n = np.sqrt((vx * vx + vy * vy).astype(f32)).astype(f32)
+            n = np.sqrt(fmaf_np(vy, vy, (vx * vx).astype(f32))).astype(f32)
             vx, vy = (vx / n).astype(f32), (vy / n).astype(f32)
         vx, vy = np.nan_to_num(vx).astype(f32), np.nan_to_num(vy).astype(f32)
         vx, vy = (vx * dt).astype(f32), (vy * dt).astype(f32)
@@ -58,7 +64,8 @@ def np_step(variant, x, y, h, prev_h, act, dt, B, sr, cd, vmax, k, periodic, noi
         half = f32(B / 2)
         dx = np.where(dx > half, (Bf - dx).astype(f32), dx)
         dy = np.where(dy > half, (Bf - dy).astype(f32), dy)
-    d2 = ((dx * dx).astype(f32) + (dy * dy).astype(f32)).astype(f32)
+    d2 = (((dx * dx).astype(f32) + (dy * dy).astype(f32)).astype(f32) if periodic
+          else fmaf_np(dy, dy, (dx * dx).astype(f32)))
     nn = np.zeros((N, k), np.int32)
     dk = np.zeros((N, k), f32)
     for i in range(N):
@@ -75,7 +82,7 @@ def np_step(variant, x, y, h, prev_h, act, dt, B, sr, cd, vmax, k, periodic, noi
             sx = f32(sx + x[j]); sy = f32(sy + y[j])
         cx, cy = f32(sx / f32(N)), f32(sy / f32(N))
         ddx, ddy = (x - cx).astype(f32), (y - cy).astype(f32)
-        dc = np.sqrt(((ddx * ddx).astype(f32) + (ddy * ddy).astype(f32)).astype(f32)).astype(f32)
+        dc = np.sqrt(fmaf_np(ddy, ddy, (ddx * ddx).astype(f32))).astype(f32)
         rcom = np.where(dc < f32(cd * 4), f32(0.01), f32(0)).astype(f32)
         rang = np.where(np.abs((prev_h - h).astype(f32)) > f32(0.27), f32(-0.01), f32(0.001)).astype(f32)
         rew = ((np.where(coll, f32(-5), f32(0.01)).astype(f32) + rcom).astype(f32) + rang).astype(f32)
