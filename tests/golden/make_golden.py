@@ -193,7 +193,7 @@ def record_edges():
     print("edge_cases", len(cases))
 
 
-def main():
+def main(only=None):
     u15 = lambda rng, N, t: rng.uniform(-1.5, 1.5, (N, 2)).astype(np.float32)      # action_space v2:58
     # BASELINE config 1: main.py defaults (main.py:96-101)
     record_traj("traj_v2_n10_k4", "v2",
@@ -211,6 +211,10 @@ def main():
     record_traj("traj_uw_n32_k3", "uw",
                 dict(agents=32, k=3, collision_distance=0.5, range_start=(0, 200), sensor_range=7),
                 200, uw_act, dt=0.05, seed=3)
+    # dense, fast-moving uw world: collisions (reward -5 branch), wall wraps, dt = 0.5
+    record_traj("traj_uw_n10_k3_dense", "uw",
+                dict(agents=10, k=3, collision_distance=2, range_start=(0, 30), sensor_range=7),
+                400, uw_act, dt=0.5, seed=6)
     # VDN trainer parameters (learners/vdn/train_flock.py:78); ids over the whole dictionary
     ids = lambda rng, N, t: rng.integers(0, 10, N).astype(np.float32)
     record_traj("traj_uwd_n8_k4", "uwd", dict(agents=8, k=4, range_start=[0, 50]), 400, ids, seed=4)
