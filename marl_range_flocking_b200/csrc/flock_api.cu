@@ -43,6 +43,8 @@ struct flock_env {
     float* stage_actions;  // device staging for host-call / step_n(tiled) actions
     float* stage_noise;
     unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
+    int* tile_perm;               // tiled thread-per-row path: spatially sorted row order [E][N]
+    uint32_t perm_age;            // steps since the row order was refreshed
     const void* zc_host[5];       // last host buffers seen by flock_step_host and their device aliases
     void* zc_dev[5];
     bool zc_ok;
@@ -112,6 +114,7 @@ Params make_params(const flock_env* e, float dt) {
     p.ep_len = b.ep_len;
     p.stats = reinterpret_cast<unsigned long long*>(b.stats);
     p.tile_scratch = e->tile_scratch;
+    p.perm = nullptr;
     return p;
 }
 
@@ -133,6 +136,7 @@ int reset_device(flock_env* e, const uint8_t* env_mask, const float* init_state,
     cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s) : flock::launch_reset_tiled(p, s);
     e->launches += 1;
     if (err != cudaSuccess) return cuda_fail(err, "reset kernel launch");
+    if (env_mask == nullptr) e->perm_age = 0; // every env was redrawn: refresh the row order at the next step
     if (e->cfg.range_noise_std > 0.0f) {
         Params q = make_params(e, 0.0f);
         q.env_mask = env_mask;                // only the envs that were reset get a fresh noisy first observation
@@ -171,6 +175,22 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
         e->launches += 1;
     } else {
+        // keep the warps of the thread-per-row kernel spatially coherent: refresh the row order
+        // every kPermRefreshSteps steps (and right after a reset); a stale order only costs speed
+        constexpr uint32_t kPermRefreshSteps = 16;
+        static const bool use_perm = [] {
+            const char* v = getenv("FLOCK_ROW_ORDER");
+            return v == nullptr || v[0] != '0';
+        }();
+        if (use_perm && e->tile_perm != nullptr && flock::tiled_uses_row_order(p, e->sm_count, e->tiled_mode)) {
+            if (e->perm_age % kPermRefreshSteps == 0) {
+                err = flock::launch_perm_refresh(p, e->tile_perm, s);
+                e->launches += 1;
+                if (err != cudaSuccess) return cuda_fail(err, "row order kernel launch");
+            }
+            e->perm_age += 1;
+            p.perm = e->tile_perm;
+        }
         err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, e->sm_count, e->tiled_mode, s);
         e->launches += 1;
         if (err == cudaSuccess) e->slot ^= 1;
@@ -268,9 +288,13 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
     if (err == cudaSuccess && e->path == 1) {
         err = cudaMalloc(&e->tile_scratch, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
         if (err == cudaSuccess) err = cudaMemset(e->tile_scratch, 0, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
+        if (err == cudaSuccess) err = cudaMalloc(&e->tile_perm, (size_t)cfg->num_envs * cfg->num_agents * sizeof(int));
+        if (err == cudaSuccess) err = flock::launch_perm_identity(e->tile_perm, cfg->num_agents, cfg->num_envs, nullptr);
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();
     }
     if (err != cudaSuccess) {
         cudaFree(e->tile_scratch);
+        cudaFree(e->tile_perm);
         cudaFree(e->stage_actions);
         cudaFree(e->stage_noise);
         delete e;
@@ -285,6 +309,7 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->stage_actions);
     cudaFree(e->stage_noise);
     cudaFree(e->tile_scratch);
+    cudaFree(e->tile_perm);
     delete e;
 }
 

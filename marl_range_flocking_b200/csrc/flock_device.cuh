@@ -54,6 +54,7 @@ struct Params {
     int32_t* ep_len;
     unsigned long long* stats;
     unsigned int* tile_scratch;   // tiled path: [E] CTA arrival counters, [E] collision counters (self-resetting)
+    const int* perm;              // tiled thread-per-row path: [E][N] row order (spatially sorted), nullable = identity
     // host-call path: device-visible HOST mirrors of the step results (zero-copy), nullable
     float* m_obs;
     float* m_reward;

@@ -15,6 +15,8 @@
 
 namespace flock {
 
+static bool use_rowwarp(const Params& p, int sm_count, int tiled_mode);
+
 constexpr int kMaxTileThreads = 256;   // upper bound of rows per CTA
 constexpr int kCandCap = 8;         // deferred k-NN candidates per row between two merges
 
@@ -220,9 +222,14 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
     const int env = blockIdx.y, tile = blockIdx.x;
     const int rows = blockDim.x;
     const TileSmem sm = carve(smem, N, V == FLOCK_UWD);
-    const int i = tile * rows + threadIdx.x;
-    const bool has_row = i < N;
     const size_t base = (size_t)env * N;
+    // Row assignment. With a row order (p.perm, refreshed every few steps by
+    // flock_perm_refresh_kernel) the 32 rows of a warp are spatial neighbours, so their k-NN
+    // candidates coincide and the candidate-append path below is entered far less often. Any
+    // permutation gives the same results: every row is computed independently.
+    const int slot = tile * rows + threadIdx.x;
+    const bool has_row = slot < N;
+    const int i = has_row ? (p.perm != nullptr ? p.perm[base + slot] : slot) : N;
     // last step's neighbour list of this thread's row: the hint that bounds this step's k-th distance
     int hint[K];
 #pragma unroll
@@ -232,11 +239,34 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         ep = (uint32_t)p.ep_len[env];
         repoch = p.reset_epoch[env];
     }
+    // this thread's own row, integrated from global (same inputs and code as the shared-memory pass
+    // below, hence bit-identical), so that the row can be any agent of the env
+    float x = 0.f, y = 0.f, h = 0.f, vx = 0.f, vy = 0.f;
+    if (has_row) {
+        x = p.x[base + i];
+        y = p.y[base + i];
+        h = p.h[base + i];
+        float a0, a1 = 0.0f, nzu = 0.f, nzw = 0.f;
+        if (V == FLOCK_UWD) {
+            a0 = p.actions[base + i];
+            if (p.noise != nullptr) {
+                const float2 nz = reinterpret_cast<const float2*>(p.noise)[base + i];
+                nzu = nz.x;
+                nzw = nz.y;
+            } else if (p.noise_std > 0.0f) {
+                act_noise(p, p.env_offset + env, i, ep, repoch, nzu, nzw);
+            }
+        } else {
+            const float2 act = reinterpret_cast<const float2*>(p.actions)[base + i];
+            a0 = act.x;
+            a1 = act.y;
+        }
+        integrate_agent<V>(p, a0, a1, nzu, nzw, x, y, h, vx, vy);
+    }
     stage_xy(p, sm, &bar, env);
 
     // integrate every agent of the env in place in shared memory (headings / actions come straight
-    // from global, coalesced); keep this thread's own row in registers
-    float x = 0.f, y = 0.f, h = 0.f, vx = 0.f, vy = 0.f;
+    // from global, coalesced)
 #pragma unroll 4
     for (int a = threadIdx.x; a < N; a += rows) {
         float ax = sm.sx[a], ay = sm.sy[a], ah = p.h[base + a];
@@ -263,9 +293,6 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         sm.sx[a] = ax;
         sm.sy[a] = ay;
         if (V == FLOCK_UWD) sm.sh[a] = ah;
-        if (a == i) {
-            x = ax; y = ay; h = ah; vx = avx; vy = avy;
-        }
     }
     if (threadIdx.x < padded_agents(N) - N) {
         sm.sx[N + threadIdx.x] = kInf;
@@ -348,6 +375,67 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         }
     }
 }
+
+// Row order for the thread-per-row kernel: agents sorted by the Morton index of their cell on a
+// 16 x 16 grid (counting sort, one CTA per env). Positions drift slowly (<= 0.25 per step), so the
+// order is refreshed only every few steps; the order within a cell is whatever the atomics give --
+// only speed depends on it, never results.
+__device__ __forceinline__ unsigned morton8(unsigned cx, unsigned cy) {   // interleave two 4-bit numbers
+    unsigned m = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) m |= ((cx >> b) & 1u) << (2 * b) | ((cy >> b) & 1u) << (2 * b + 1);
+    return m;
+}
+
+__global__ void __launch_bounds__(256) flock_perm_refresh_kernel(const __grid_constant__ Params p, int* perm) {
+    __shared__ int count[256];
+    __shared__ int start[256];
+    extern __shared__ __align__(16) float smem[];
+    unsigned short* key = reinterpret_cast<unsigned short*>(smem);      // [N]
+    unsigned short* pos = key + p.N;                                     // [N]
+    const int env = blockIdx.x, N = p.N;
+    const size_t base = (size_t)env * N;
+    count[threadIdx.x] = 0;
+    __syncthreads();
+    const float scale = 16.0f / p.B;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        const float fx = p.x[base + a] * scale, fy = p.y[base + a] * scale;
+        const unsigned cx = (unsigned)min(15, max(0, (int)fx)), cy = (unsigned)min(15, max(0, (int)fy));
+        const unsigned c = morton8(cx, cy);
+        key[a] = (unsigned short)c;
+        pos[a] = (unsigned short)atomicAdd(&count[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 0; c < 256; ++c) {
+            start[c] = acc;
+            acc += count[c];
+        }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < N; a += blockDim.x) perm[base + start[key[a]] + pos[a]] = a;
+}
+
+cudaError_t launch_perm_refresh(const Params& p, int* perm, cudaStream_t s) {
+    flock_perm_refresh_kernel<<<p.E, 256, (size_t)p.N * 2 * sizeof(unsigned short), s>>>(p, perm);
+    return cudaGetLastError();
+}
+
+__global__ void flock_perm_identity_kernel(int* perm, int N, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        perm[i] = (int)(i % (size_t)N);
+}
+
+cudaError_t launch_perm_identity(int* perm, int N, int E, cudaStream_t s) {
+    const size_t total = (size_t)N * E;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    flock_perm_identity_kernel<<<grid, 256, 0, s>>>(perm, N, total);
+    return cudaGetLastError();
+}
+
+bool tiled_uses_row_order(const Params& p, int sm_count, int tiled_mode) { return !use_rowwarp(p, sm_count, tiled_mode); }
 
 // -------------------------------------------------------------------------------------------------
 // Few envs x large swarm (fewer row tiles than SMs): one WARP per row instead of one thread per row.
