@@ -183,6 +183,12 @@ FLOCK_API uint64_t flock_launch_count(const flock_env_t *env);
 /* 0: warp-per-env-group path (N <= 32), 1: tiled path (N > 32). */
 FLOCK_API int flock_path(const flock_env_t *env);
 
+/* Row x neighbour pairs actually evaluated so far by the pruned large-swarm kernel (v2, N > 32, many
+ * envs: blocks of neighbours that provably cannot contain a k-nearest neighbour are skipped; results
+ * are identical to the all-pairs scan). Synchronises the device; `reset` != 0 zeroes the counter.
+ * bench.py uses it to report the FP32 roofline on the work really done. */
+FLOCK_API uint64_t flock_pairs_evaluated(flock_env_t *env, int reset);
+
 /* Kernel choice on the tiled path: 0 = automatic (default), 1 = one thread per row (many envs),
  * 2 = one warp per row with a warp-shuffle bitonic top-k merge (few envs x large swarm). Results are
  * identical bit for bit; only speed differs. */

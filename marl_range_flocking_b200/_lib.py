@@ -80,6 +80,7 @@ def load_library() -> ctypes.CDLL:
         "flock_launch_count": (u64, [vp]),
         "flock_path": (i32, [vp]),
         "flock_set_tiled_mode": (i32, [vp, i32]),
+        "flock_pairs_evaluated": (u64, [vp, i32]),
         "flock_set_auto_reset": (i32, [vp, i32, i32]),
         "flock_last_error": (ctypes.c_char_p, []),
         "flock_abi_version": (i32, []),

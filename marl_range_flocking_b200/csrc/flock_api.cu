@@ -44,7 +44,10 @@ struct flock_env {
     float* stage_noise;
     unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
     int* tile_perm;               // tiled thread-per-row path: spatially sorted row order [E][N]
+    int* tile_inv;                // its inverse (agent -> slot)
+    float* sorted_xy;             // pruned path: new positions in slot order [E][2][nblk*32]
     uint32_t perm_age;            // steps since the row order was refreshed
+    unsigned long long* pair_counter;   // device counter of row x neighbour pairs evaluated by the pruned kernel
     const void* zc_host[5];       // last host buffers seen by flock_step_host and their device aliases
     void* zc_dev[5];
     bool zc_ok;
@@ -115,6 +118,9 @@ Params make_params(const flock_env* e, float dt) {
     p.stats = reinterpret_cast<unsigned long long*>(b.stats);
     p.tile_scratch = e->tile_scratch;
     p.perm = nullptr;
+    p.pair_counter = e->pair_counter;
+    p.inv = e->tile_inv;
+    p.sorted_xy = e->sorted_xy;
     return p;
 }
 
@@ -184,7 +190,7 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         }();
         if (use_perm && e->tile_perm != nullptr && flock::tiled_uses_row_order(p, e->sm_count, e->tiled_mode)) {
             if (e->perm_age % kPermRefreshSteps == 0) {
-                err = flock::launch_perm_refresh(p, e->tile_perm, s);
+                err = flock::launch_perm_refresh(p, e->tile_perm, e->tile_inv, s);
                 e->launches += 1;
                 if (err != cudaSuccess) return cuda_fail(err, "row order kernel launch");
             }
@@ -192,7 +198,7 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
             p.perm = e->tile_perm;
         }
         err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, e->sm_count, e->tiled_mode, s);
-        e->launches += 1;
+        e->launches += flock::tiled_step_launches(e->cfg.variant, p, e->sm_count, e->tiled_mode);
         if (err == cudaSuccess) e->slot ^= 1;
     }
     if (err != cudaSuccess) return cuda_fail(err, "step kernel launch");
@@ -289,12 +295,19 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         err = cudaMalloc(&e->tile_scratch, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
         if (err == cudaSuccess) err = cudaMemset(e->tile_scratch, 0, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
         if (err == cudaSuccess) err = cudaMalloc(&e->tile_perm, (size_t)cfg->num_envs * cfg->num_agents * sizeof(int));
-        if (err == cudaSuccess) err = flock::launch_perm_identity(e->tile_perm, cfg->num_agents, cfg->num_envs, nullptr);
+        if (err == cudaSuccess) err = cudaMalloc(&e->tile_inv, (size_t)cfg->num_envs * cfg->num_agents * sizeof(int));
+        if (err == cudaSuccess)
+            err = cudaMalloc(&e->sorted_xy, flock::pruned_scratch_floats(cfg->num_agents, cfg->num_envs) * sizeof(float));
+        if (err == cudaSuccess)
+            err = flock::launch_perm_identity(e->tile_perm, e->tile_inv, cfg->num_agents, cfg->num_envs, nullptr);
         if (err == cudaSuccess) err = cudaDeviceSynchronize();
     }
     if (err != cudaSuccess) {
         cudaFree(e->tile_scratch);
         cudaFree(e->tile_perm);
+        cudaFree(e->tile_inv);
+        cudaFree(e->sorted_xy);
+        cudaFree(e->pair_counter);
         cudaFree(e->stage_actions);
         cudaFree(e->stage_noise);
         delete e;
@@ -310,6 +323,9 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->stage_noise);
     cudaFree(e->tile_scratch);
     cudaFree(e->tile_perm);
+    cudaFree(e->tile_inv);
+    cudaFree(e->sorted_xy);
+    cudaFree(e->pair_counter);
     delete e;
 }
 
@@ -464,6 +480,18 @@ int flock_set_step_index(flock_env_t* e, uint32_t step_index) {
 }
 uint64_t flock_launch_count(const flock_env_t* e) { return e ? e->launches : 0ULL; }
 int flock_path(const flock_env_t* e) { return e ? e->path : 0; }
+uint64_t flock_pairs_evaluated(flock_env_t* e, int reset) {
+    if (e == nullptr) return 0ULL;
+    if (e->pair_counter == nullptr) {   // counting costs one atomic per warp: enabled by the first query
+        if (cudaMalloc(&e->pair_counter, sizeof(unsigned long long)) != cudaSuccess) return 0ULL;
+        cudaMemset(e->pair_counter, 0, sizeof(unsigned long long));
+        return 0ULL;
+    }
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, e->pair_counter, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0ULL;
+    if (reset) cudaMemset(e->pair_counter, 0, sizeof(v));
+    return v;
+}
 int flock_set_tiled_mode(flock_env_t* e, int mode) {
     if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
     if (mode < 0 || mode > 2) return fail(FLOCK_E_INVALID, "tiled mode %d not in {0,1,2}", mode);

@@ -55,6 +55,9 @@ struct Params {
     unsigned long long* stats;
     unsigned int* tile_scratch;   // tiled path: [E] CTA arrival counters, [E] collision counters (self-resetting)
     const int* perm;              // tiled thread-per-row path: [E][N] row order (spatially sorted), nullable = identity
+    unsigned long long* pair_counter;   // pruned kernel: row x neighbour pairs actually evaluated (nullable)
+    const int* inv;               // inverse of perm (agent -> slot)
+    float* sorted_xy;             // pruned path: [E][2][nblk*32] new positions in slot order
     // host-call path: device-visible HOST mirrors of the step results (zero-copy), nullable
     float* m_obs;
     float* m_reward;
@@ -321,6 +324,22 @@ struct TopK {
         }
         idx[0] = (c < d[0]) ? j : idx[0];
         d[0] = fminf(d[0], c);
+    }
+    // insertion by the full (d2, j) key, for candidates that do NOT arrive in ascending j: d2 >= 0
+    // (never NaN), so (bits(d2) << 32 | j) orders like (d2, j); empty slots hold (+inf, 0xffffffff)
+    __device__ __forceinline__ void insert_lex(float c, int j) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned)j;
+        bool lt[K];
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+            lt[s] = key < (((unsigned long long)__float_as_uint(d[s]) << 32) | (unsigned)idx[s]);
+#pragma unroll
+        for (int s = K - 1; s > 0; --s) {
+            idx[s] = lt[s - 1] ? idx[s - 1] : (lt[s] ? j : idx[s]);
+            d[s] = lt[s - 1] ? d[s - 1] : (lt[s] ? c : d[s]);
+        }
+        idx[0] = lt[0] ? j : idx[0];
+        d[0] = lt[0] ? c : d[0];
     }
     __device__ __forceinline__ float worst() const { return d[K - 1]; }
 };

@@ -16,6 +16,7 @@
 namespace flock {
 
 static bool use_rowwarp(const Params& p, int sm_count, int tiled_mode);
+static int choose_rows(int N, int E, int sm_count);
 
 constexpr int kMaxTileThreads = 256;   // upper bound of rows per CTA
 constexpr int kCandCap = 8;         // deferred k-NN candidates per row between two merges
@@ -376,62 +377,386 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
     }
 }
 
-// Row order for the thread-per-row kernel: agents sorted by the Morton index of their cell on a
-// 16 x 16 grid (counting sort, one CTA per env). Positions drift slowly (<= 0.25 per step), so the
-// order is refreshed only every few steps; the order within a cell is whatever the atomics give --
-// only speed depends on it, never results.
-__device__ __forceinline__ unsigned morton8(unsigned cx, unsigned cy) {   // interleave two 4-bit numbers
-    unsigned m = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) m |= ((cx >> b) & 1u) << (2 * b) | ((cy >> b) & 1u) << (2 * b + 1);
-    return m;
+// -------------------------------------------------------------------------------------------------
+// v2, many envs x large swarm: thread-per-row kernel with EXACT spatial pruning.
+//
+// The env is staged in the spatially sorted row order (p.perm: Morton cells), so both the 32 rows of a
+// warp and every block of 32 consecutive neighbour slots are compact in space. For each block the
+// warp compares a conservative lower bound of the (min-image) distance between its rows' bounding
+// box and the block's bounding box with the largest per-row threshold in the warp; blocks that
+// cannot contain a k-nearest neighbour of any of the 32 rows are skipped, the others run the same
+// 9-FP32-instruction pair loop as the all-pairs kernel. The thresholds come from the previous
+// step's neighbour lists (an upper bound of the k-th distance, see hint_bound), so typically ~10 %
+// of the blocks are evaluated. Results are identical to the all-pairs kernels bit for bit:
+// pruning only removes candidates that provably lose, and candidates are merged by the full
+// (d2, agent index) key because they no longer arrive in index order.
+// -------------------------------------------------------------------------------------------------
+size_t pruned_smem_bytes(int N, int rows) {
+    const size_t PS = (size_t)((N + 31) / 32) * 32;
+    return (2 * PS + PS / 2) * sizeof(float) + (size_t)kCandCap * rows * sizeof(uint2);
+}
+size_t pruned_scratch_floats(int N, int E) {   // per env: x by slot | y by slot | one box per 8 slots
+    const size_t PS = (size_t)((N + 31) / 32) * 32;
+    return (size_t)E * (2 * PS + PS / 2);
 }
 
-__global__ void __launch_bounds__(256) flock_perm_refresh_kernel(const __grid_constant__ Params p, int* perm) {
-    __shared__ int count[256];
-    __shared__ int start[256];
-    extern __shared__ __align__(16) float smem[];
-    unsigned short* key = reinterpret_cast<unsigned short*>(smem);      // [N]
-    unsigned short* pos = key + p.N;                                     // [N]
-    const int env = blockIdx.x, N = p.N;
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
+// conservative lower bound of the per-axis (min-image) distance between intervals [a0,a1], [b0,b1]
+template <bool PER>
+__device__ __forceinline__ float axis_gap(float a0, float a1, float b0, float b1, float B, float slack) {
+    float g = fmaxf(b0 - a1, a0 - b1);                  // direct gap (negative when overlapping)
+    if (PER) {
+        const float span = fmaxf(a1 - b0, b1 - a0);     // largest |dx| over the two intervals
+        g = fminf(g, B - span);                         // the wrapped image can be closer
+    }
+    return fmaxf(g - slack, 0.0f);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Pruned path for v2 large swarms. Two launches per step:
+//  1. flock_integrate_sorted_kernel: one thread per sorted SLOT integrates its agent ONCE (same code
+//     as everywhere else), writes the new state at the agent's index and, per env, a staging record
+//     [x by slot | y by slot | bounding boxes of every 8 consecutive slots] that is contiguous in memory.
+//  2. flock_step_pruned_kernel: one thread per row (in slot order); the CTA stages the env's record
+//     with ONE TMA bulk copy, each warp tests its 32-row bounding box against the 8-slot boxes (one
+//     box per lane, ballot) and evaluates only boxes whose conservative distance lower bound does not
+//     exceed the warp's largest current k-th-neighbour threshold. Exact: a skipped box cannot hold
+//     a candidate that any row of the warp would accept; ties are resolved by (d2, agent index).
+// -------------------------------------------------------------------------------------------------
+constexpr int kBoxSlots = 8;
+
+__device__ __forceinline__ size_t sorted_record_floats(int PS) { return (size_t)PS * 2 + (size_t)PS / 2; }
+
+__global__ void __launch_bounds__(256) flock_integrate_sorted_kernel(const __grid_constant__ Params p) {
+    const int N = p.N, env = blockIdx.y;
+    const int PS = ((N + 31) / 32) * 32;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= PS) return;                       // PS is a multiple of 32: whole warps leave together
     const size_t base = (size_t)env * N;
-    count[threadIdx.x] = 0;
+    const bool real = slot < N;
+    float x = kInf, y = 0.0f;                     // padding slots: never selected, never collide
+    if (real) {
+        const size_t i = base + (size_t)p.perm[base + slot];
+        float h = p.h[i], vx, vy;
+        x = p.x[i];
+        y = p.y[i];
+        const float2 act = reinterpret_cast<const float2*>(p.actions)[i];
+        integrate_agent<FLOCK_V2>(p, act.x, act.y, 0.f, 0.f, x, y, h, vx, vy);
+        p.xo[i] = x;
+        p.yo[i] = y;
+        p.ho[i] = h;
+        if (p.vx != nullptr) {
+            p.vx[i] = vx;
+            p.vy[i] = vy;
+        }
+    }
+    float* rec = p.sorted_xy + (size_t)env * sorted_record_floats(PS);
+    rec[slot] = x;
+    rec[PS + slot] = y;
+    float x0 = real ? x : kFltMax, x1 = real ? x : -kFltMax, y0 = real ? y : kFltMax, y1 = real ? y : -kFltMax;
+#pragma unroll
+    for (int m = 1; m < kBoxSlots; m <<= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, m));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, m));
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, m));
+        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, m));
+    }
+    if ((slot & (kBoxSlots - 1)) == 0)
+        reinterpret_cast<float4*>(rec + 2 * (size_t)PS)[slot / kBoxSlots] = make_float4(x0, x1, y0, y1);
+}
+
+template <int K, bool PER>
+__global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int N = p.N, k = p.k;
+    const int env = blockIdx.y, tile = blockIdx.x, rows = blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int PS = ((N + 31) / 32) * 32, nbox = PS / kBoxSlots;
+    float* ss_x = smem;                 // new positions by sorted SLOT (padded to whole warps)
+    float* ss_y = ss_x + PS;
+    const float4* bb = reinterpret_cast<const float4*>(ss_y + PS);      // [nbox] (x0, x1, y0, y1)
+    uint2* cand = reinterpret_cast<uint2*>(ss_y + PS + 4 * nbox) + threadIdx.x;
+    const size_t base = (size_t)env * N;
+    const int slot = tile * rows + threadIdx.x;
+    const bool has_row = slot < N;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        const uint32_t bytes = (uint32_t)(sorted_record_floats(PS) * sizeof(float));
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(smem, p.sorted_xy + (size_t)env * sorted_record_floats(PS), bytes, &bar);
+    }
+    const int i = has_row ? p.perm[base + slot] : N;    // this thread's agent
+    int hslot[K];                                        // last step's neighbours, as slots (-1: unusable)
+    bool hint_ok = has_row && p.nn != nullptr;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        hslot[s] = 0;
+        if (s < k) {
+            const int j = hint_ok ? p.nn[(base + i) * k + s] : -1;
+            const bool in = j >= 0 && j < N && j != i;
+            hint_ok = hint_ok && in;
+            hslot[s] = in ? p.inv[base + j] : 0;
+        }
+    }
+#pragma unroll
+    for (int s = 1; s < K; ++s)
+#pragma unroll
+        for (int u = 0; u < s; ++u)
+            if (s < k) hint_ok = hint_ok && (hslot[u] != hslot[s]);
     __syncthreads();
-    const float scale = 16.0f / p.B;
+    mbar_wait(&bar, 0);
+
+    const float x = has_row ? ss_x[slot] : 0.f, y = has_row ? ss_y[slot] : 0.f;
+    // per-row threshold: the largest CURRENT distance to last step's neighbours bounds the k-th best
+    float thr = -1.0f;                                     // lanes without a row accept nothing
+    if (has_row) {
+        float bound = 0.0f;
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+            if (s < k) bound = fmaxf(bound, pair_d2<PER>(x, y, ss_x[hslot[s]], ss_y[hslot[s]], p.B));
+        thr = hint_ok ? bound : kFltMax;
+    }
+    const float wx0 = warp_min(has_row ? x : kFltMax), wx1 = warp_max(has_row ? x : -kFltMax);
+    const float wy0 = warp_min(has_row ? y : kFltMax), wy1 = warp_max(has_row ? y : -kFltMax);
+    // thresholds are non-negative floats: their bit patterns order like unsigned integers
+    float thr_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fmaxf(thr, 0.0f))));
+    const float slack = p.B * 1.0e-6f + 1.0e-30f;
+
+    TopK<K> t;
+    t.init();
+    int cnt = 0;
+    const int cstride = rows;
+    auto merge = [&]() {
+        int js[kCandCap];
+        float ds[kCandCap];
+#pragma unroll
+        for (int c = 0; c < kCandCap; ++c) {          // all slot -> agent lookups in flight together
+            const uint2 e = cand[c * cstride];
+            ds[c] = __uint_as_float(e.x);
+            js[c] = (c < cnt) ? p.perm[base + e.y] : i;
+        }
+#pragma unroll
+        for (int c = 0; c < kCandCap; ++c) {
+            if (__any_sync(kFull, c < cnt)) {
+                if (c < cnt && js[c] != i) t.insert_lex(ds[c], js[c]);
+            }
+        }
+        cnt = 0;
+        thr = fminf(thr, t.worst());
+        thr_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fmaxf(thr, 0.0f))));
+    };
+    const int ngroups = (nbox + 31) / 32;
+    const int own_g = slot / (kBoxSlots * 32);            // group of 32 boxes holding this warp's first row
+    unsigned long long evaluated = 0;
+    if (__any_sync(kFull, has_row)) {
+        for (int o = 0; o < ngroups; ++o) {
+            int g = __shfl_sync(kFull, own_g, 0) + o;
+            if (g >= ngroups) g -= ngroups;
+            const int bl = g * 32 + lane;                 // this lane's box
+            bool take = false;
+            if (bl < nbox) {
+                const float4 q = bb[bl];
+                const float gx = axis_gap<PER>(wx0, wx1, q.x, q.y, p.B, slack);
+                const float gy = axis_gap<PER>(wy0, wy1, q.z, q.w, p.B, slack);
+                take = (gx * gx + gy * gy) * 0.9999f <= thr_max;   // some row of the warp may gain from it
+            }
+            unsigned mask = __ballot_sync(kFull, take);
+            while (mask != 0u) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const int s0 = (g * 32 + bit) * kBoxSlots;
+                evaluated += 1;
+                uint32_t ax = smem_u32(ss_x + s0), ay = smem_u32(ss_y + s0);
+#pragma unroll
+                for (int j4 = 0; j4 < kBoxSlots / 4; ++j4, ax += 16u, ay += 16u) {
+                    const float4 X = lds128(ax);
+                    const float4 Y = lds128(ay);
+                    const float d0 = pair_d2<PER>(x, y, X.x, Y.x, p.B);
+                    const float d1 = pair_d2<PER>(x, y, X.y, Y.y, p.B);
+                    const float d2 = pair_d2<PER>(x, y, X.z, Y.z, p.B);
+                    const float d3 = pair_d2<PER>(x, y, X.w, Y.w, p.B);
+                    const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+                    if (__any_sync(kFull, m <= thr)) {
+                        const unsigned sj = (unsigned)(s0 + (j4 << 2));
+                        if (d0 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d0), sj); ++cnt; }
+                        if (d1 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d1), sj + 1u); ++cnt; }
+                        if (d2 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d2), sj + 2u); ++cnt; }
+                        if (d3 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d3), sj + 3u); ++cnt; }
+                        if (__any_sync(kFull, cnt > kCandCap - 4)) merge();
+                    }
+                }
+            }
+        }
+        merge();
+    }
+
+    long long fx = 0;
+    bool coll = false;
+    if (has_row) {
+        float dist[K];
+        coll = finish_row<K, TopK<K>>(t, k, p.sensor_range, p.cd, dist);
+        const size_t idx = base + i;
+        const float rew = reward_from_flags<FLOCK_V2>(coll, false, false);
+        fx = reward_fx(rew);
+        write_obs_t<K>(p, idx, dist, false);
+        if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
+        p.reward[idx] = rew;
+        p.agent_done[idx] = coll ? 1 : 0;
+    }
+    const bool warp_coll = __any_sync(kFull, coll);
+    const unsigned lo = (unsigned)fx & 0xffffu, mid = (unsigned)(fx >> 16) & 0xffffu;
+    const int hi = (int)(fx >> 32);
+    const unsigned slo = __reduce_add_sync(kFull, lo);
+    const unsigned smid = __reduce_add_sync(kFull, mid);
+    const int shi = __reduce_add_sync(kFull, hi);
+    unsigned int* arrive = p.tile_scratch + env;
+    unsigned int* collide = p.tile_scratch + p.E + env;
+    if (lane == 0) {
+        if (warp_coll) atomicAdd(collide, 1u);
+        if (p.ep_return_fx != nullptr) {
+            const long long sum = ((long long)shi << 32) + ((long long)smid << 16) + (long long)slo;
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.ep_return_fx + env), (unsigned long long)sum);
+        }
+        if (p.pair_counter != nullptr) atomicAdd(p.pair_counter, evaluated * (unsigned long long)(kBoxSlots * 32));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(arrive, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            const unsigned c = atomicExch(collide, 0u);
+            p.env_done[env] = c != 0u ? 1 : 0;
+            p.ep_len[env] += 1;
+            *arrive = 0u;
+        }
+    }
+    (void)wid;
+}
+
+template <int K, bool PER>
+static cudaError_t launch_pruned(const Params& p, int sm_count, cudaStream_t s) {
+    {   // launch 1 of 2: integrate every agent once, in slot order
+        const int PS = ((p.N + 31) / 32) * 32;
+        flock_integrate_sorted_kernel<<<dim3((PS + 255) / 256, p.E), 256, 0, s>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const int rows = choose_rows(p.N, p.E, sm_count);
+    const dim3 grid((p.N + rows - 1) / rows, p.E);
+    flock_step_pruned_kernel<K, PER><<<grid, rows, pruned_smem_bytes(p.N, rows), s>>>(p);
+    return cudaGetLastError();
+}
+
+// Row order for the thread-per-row kernels: agents sorted by the Hilbert index of their cell on a
+// G x G grid with about two agents per cell (counting sort, one CTA per env), so any run of
+// consecutive slots is a compact, connected patch of the world. Positions drift slowly (<= 0.25 per
+// step), so the order is refreshed only every few steps; the order within a cell is whatever the
+// atomics give -- only speed depends on the order, never results.
+__device__ __forceinline__ unsigned hilbert_index(unsigned n, unsigned x, unsigned y) {   // n = grid side, power of two
+    unsigned d = 0;
+    for (unsigned s = n >> 1; s > 0; s >>= 1) {
+        const unsigned rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0u) {
+            if (rx == 1u) {
+                x = n - 1u - x;
+                y = n - 1u - y;
+            }
+            const unsigned tmp = x;
+            x = y;
+            y = tmp;
+        }
+    }
+    return d;
+}
+
+static int order_grid_side(int N) {   // power of two, cells of ~2 agents, 4 <= G <= 64
+    int g = 4;
+    while (g < 64 && g * g * 2 < N) g <<= 1;
+    return g;
+}
+
+__global__ void __launch_bounds__(256) flock_perm_refresh_kernel(const __grid_constant__ Params p, int* perm, int* inv, int G) {
+    __shared__ int part[256];
+    extern __shared__ __align__(16) float smem[];
+    const int env = blockIdx.x, N = p.N, cells = G * G;
+    int* count = reinterpret_cast<int*>(smem);                            // [cells] counts, then start offsets
+    unsigned short* key = reinterpret_cast<unsigned short*>(count + cells);   // [N]
+    unsigned short* pos = key + N;                                         // [N]
+    const size_t base = (size_t)env * N;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) count[c] = 0;
+    __syncthreads();
+    const float scale = (float)G / p.B;
     for (int a = threadIdx.x; a < N; a += blockDim.x) {
         const float fx = p.x[base + a] * scale, fy = p.y[base + a] * scale;
-        const unsigned cx = (unsigned)min(15, max(0, (int)fx)), cy = (unsigned)min(15, max(0, (int)fy));
-        const unsigned c = morton8(cx, cy);
+        const unsigned cx = (unsigned)min(G - 1, max(0, (int)fx)), cy = (unsigned)min(G - 1, max(0, (int)fy));
+        const unsigned c = hilbert_index((unsigned)G, cx, cy);
         key[a] = (unsigned short)c;
         pos[a] = (unsigned short)atomicAdd(&count[c], 1);
     }
     __syncthreads();
+    // exclusive prefix sum over the cells: per-thread chunk sums, serial scan of the 256 partials
+    const int chunk = (cells + 255) / 256;
+    const int c0 = threadIdx.x * chunk, c1 = min(cells, c0 + chunk);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += count[c];
+    part[threadIdx.x] = sum;
+    __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int c = 0; c < 256; ++c) {
-            start[c] = acc;
-            acc += count[c];
+        for (int t = 0; t < 256; ++t) {
+            const int v = part[t];
+            part[t] = acc;
+            acc += v;
         }
     }
     __syncthreads();
-    for (int a = threadIdx.x; a < N; a += blockDim.x) perm[base + start[key[a]] + pos[a]] = a;
+    int acc = part[threadIdx.x];
+    for (int c = c0; c < c1; ++c) {
+        const int v = count[c];
+        count[c] = acc;
+        acc += v;
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        const int s = count[key[a]] + pos[a];
+        perm[base + s] = a;
+        inv[base + a] = s;
+    }
 }
 
-cudaError_t launch_perm_refresh(const Params& p, int* perm, cudaStream_t s) {
-    flock_perm_refresh_kernel<<<p.E, 256, (size_t)p.N * 2 * sizeof(unsigned short), s>>>(p, perm);
+cudaError_t launch_perm_refresh(const Params& p, int* perm, int* inv, cudaStream_t s) {
+    const int G = order_grid_side(p.N);
+    const size_t bytes = (size_t)G * G * sizeof(int) + (size_t)p.N * 2 * sizeof(unsigned short);
+    flock_perm_refresh_kernel<<<p.E, 256, bytes, s>>>(p, perm, inv, G);
     return cudaGetLastError();
 }
 
-__global__ void flock_perm_identity_kernel(int* perm, int N, size_t total) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+__global__ void flock_perm_identity_kernel(int* perm, int* inv, int N, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         perm[i] = (int)(i % (size_t)N);
+        inv[i] = (int)(i % (size_t)N);
+    }
 }
 
-cudaError_t launch_perm_identity(int* perm, int N, int E, cudaStream_t s) {
+cudaError_t launch_perm_identity(int* perm, int* inv, int N, int E, cudaStream_t s) {
     const size_t total = (size_t)N * E;
     int grid = (int)((total + 255) / 256);
     if (grid > 1024) grid = 1024;
-    flock_perm_identity_kernel<<<grid, 256, 0, s>>>(perm, N, total);
+    flock_perm_identity_kernel<<<grid, 256, 0, s>>>(perm, inv, N, total);
     return cudaGetLastError();
 }
 
@@ -763,8 +1088,24 @@ static bool use_rowwarp(const Params& p, int sm_count, int tiled_mode) {
     return (long long)p.N * p.E <= 55LL * sm_count;
 }
 
+static bool prune_enabled() {   // FLOCK_PRUNE=0: plain all-pairs scan (same results, for comparison)
+    static const bool prune = [] {
+        const char* v = getenv("FLOCK_PRUNE");
+        return v == nullptr || v[0] != '0';
+    }();
+    return prune;
+}
+static bool use_pruned(int variant, const Params& p, int sm_count, int tiled_mode) {
+    return variant == FLOCK_V2 && prune_enabled() && p.perm != nullptr && p.sorted_xy != nullptr &&
+           !use_rowwarp(p, sm_count, tiled_mode);
+}
+int tiled_step_launches(int variant, const Params& p, int sm_count, int tiled_mode) {
+    return use_pruned(variant, p, sm_count, tiled_mode) ? 2 : 1;
+}
+
 template <int V, int K, bool PER>
 static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, int tiled_mode, cudaStream_t s) {
+    if (use_pruned(V, p, sm_count, tiled_mode)) return launch_pruned<(K < 4 ? 4 : K), PER>(p, sm_count, s);
     if (use_rowwarp(p, sm_count, tiled_mode)) return launch_rowwarp<V, (K < 4 ? 4 : K), PER>(p, sm_count, s);
     const int rows = choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);
@@ -807,8 +1148,20 @@ static cudaError_t opt_in(Kern kern, size_t bytes) {
 
 cudaError_t tiled_configure(int num_agents) {
     const size_t b = tiled_smem_bytes(num_agents, kMaxTileThreads, true);
-    if (b <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaSuccess;
+    {
+        const size_t bp = pruned_smem_bytes(num_agents, kMaxTileThreads);
+        if (bp > 47 * 1024) {
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<4, true>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<8, true>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<4, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<8, false>, bp);
+        }
+        const int G = order_grid_side(num_agents);
+        const size_t br = (size_t)G * G * sizeof(int) + (size_t)num_agents * 2 * sizeof(unsigned short);
+        if (br > 46 * 1024 && e == cudaSuccess) e = opt_in(flock_perm_refresh_kernel, br);
+    }
+    if (b <= 48 * 1024) return e;
 #define FLOCK_OPT(V, K, PER) \
     if (e == cudaSuccess) e = opt_in(flock_step_tiled_kernel<V, K, PER>, b);
     FLOCK_OPT(FLOCK_V2, 3, true) FLOCK_OPT(FLOCK_V2, 4, true) FLOCK_OPT(FLOCK_V2, 8, true)

@@ -248,6 +248,10 @@ class VecEnv:
     def step_index(self, v: int):
         check(self.lib.flock_set_step_index(self._h, int(v) & 0xFFFFFFFF))
 
+    def pairs_evaluated(self, reset: bool = False) -> int:
+        """Row x neighbour pairs evaluated by the pruned large-swarm kernel so far (synchronises)."""
+        return int(self.lib.flock_pairs_evaluated(self._h, int(reset)))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.flock_launch_count(self._h))
