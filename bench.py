@@ -37,7 +37,7 @@ WORKLOADS = {
                  env_kw=dict(track_neighbors=False),   # ... and in uw_discrete (gym_flock_uw_discrete.py:189-192)
                  desc="gym_flock_uw_discrete 8192 envs x 16 agents, k=4, random action ids, Philox actuation noise"),
     "cfg5": dict(variant="v2", E=64, N=2048, k=8, cd=0.05, rs=(0, 2000), sr=100.0, kw={}, bytes=69,
-                 desc="gym_flock_v2 large swarm 64 envs x 2048 agents, k=8 (tiled all-pairs path)"),
+                 desc="gym_flock_v2 large swarm 64 envs x 2048 agents, k=8 (tiled path, exact box-pruned k-NN)"),
 }
 L2_BYTES = 126 * 1024 * 1024
 DT = 0.1
@@ -161,6 +161,26 @@ def run_reference(args, w):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+def pairs_evaluated_fraction(w, E, device, steps=32):
+    """Share of the N*(N-1) pairs per row the sensing kernel evaluates (1.0 for the all-pairs kernels),
+    counted by the kernel itself on a separate env (the counter costs an atomic per warp)."""
+    import torch
+    from marl_range_flocking_b200 import VecEnv
+
+    env = VecEnv(w["variant"], E, w["N"], w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"], seed=0xC0,
+                 device=device, **w["kw"], **w.get("env_kw", {}))
+    env.reset()
+    env.pairs_evaluated()                       # first query switches the counter on
+    acts = [env.random_actions(i) for i in range(2)]
+    for t in range(steps):
+        env.step(acts[t & 1], DT)
+    torch.cuda.synchronize(device)
+    pairs = env.pairs_evaluated()
+    if pairs == 0:                              # a kernel without pruning evaluates everything
+        return 1.0
+    return pairs / (steps * E * w["N"] * (w["N"] - 1))
+
+
 def build_ring(w, E, ring, device, env_offset, seed=0x5EED):
     import torch
     from marl_range_flocking_b200 import VecEnv
@@ -182,10 +202,11 @@ def capture(envs, acts, n, start):
 
     g = torch.cuda.CUDAGraph()
     R = len(envs)
+    before = sum(e.launch_count for e in envs)
     with torch.cuda.graph(g):
         for s in range(start, start + n):
             envs[s % R].step(acts[s % R][(s // R) & 1], DT)
-    return g
+    return g, sum(e.launch_count for e in envs) - before       # kernel nodes in the graph
 
 
 def timed_graph_steps(envs, acts, steps, warmup, device, dist_barrier):
@@ -193,10 +214,10 @@ def timed_graph_steps(envs, acts, steps, warmup, device, dist_barrier):
 
     chunk = min(steps, 1024)
     full, rem = divmod(steps, chunk)
-    g_full = capture(envs, acts, chunk, 0)
-    g_rem = capture(envs, acts, rem, 0) if rem else None
+    g_full, n_full = capture(envs, acts, chunk, 0)
+    g_rem, n_rem = capture(envs, acts, rem, 0) if rem else (None, 0)
     wfull, wrem = divmod(warmup, chunk)
-    g_w = capture(envs, acts, wrem, 0) if wrem else None
+    g_w, _ = capture(envs, acts, wrem, 0) if wrem else (None, 0)
     for _ in range(wfull):
         g_full.replay()
     if g_w is not None:
@@ -213,8 +234,10 @@ def timed_graph_steps(envs, acts, steps, warmup, device, dist_barrier):
     ev1.record()
     torch.cuda.synchronize(device)
     dist_barrier()
-    # graph replays do not go through flock_step again: launches = one fused kernel node per step
-    return ev0.elapsed_time(ev1), steps
+    # graph replays do not go through flock_step again: launches = kernel nodes of the replayed graphs
+    # (one fused kernel per step for N <= 32; integrate pre-pass + sensing kernel, and a row-order
+    # refresh every 16 steps of an env, for larger swarms)
+    return ev0.elapsed_time(ev1), steps, full * n_full + n_rem
 
 
 def timed_e2e(env, w, steps, warmup, device):
@@ -281,7 +304,7 @@ def run_gpu(args, w):
     except Exception:
         pass
     sampler.start()
-    ms, steps = timed_graph_steps(envs, acts, args.steps, args.warmup, device, barrier)
+    ms, steps, launches = timed_graph_steps(envs, acts, args.steps, args.warmup, device, barrier)
     clocks = sampler.stop()
 
     t = torch.tensor([ms], dtype=torch.float64, device=device)
@@ -382,14 +405,22 @@ def run_gpu(args, w):
         if envs[0].tiled:
             # large swarms are FP32-pipe bound, not HBM bound: E*N*(N-1) pair evaluations x 9
             # FP32 operations (no FMA: parity forbids contraction) against 128 lanes x SMs x max clock
+            # The v2 sensing kernel prunes exactly (box test against the warp's k-th-distance bound), so
+            # the flops it needs are those of the pairs it evaluates: counted on a separate untimed env.
             props = torch.cuda.get_device_properties(device)
-            flops = E * N * (N - 1) * 9.0
+            all_pairs = E * N * (N - 1) * 9.0
+            frac_eval = pairs_evaluated_fraction(w, E, device)
+            flops = all_pairs * frac_eval
             peak_tf = props.multi_processor_count * 128 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
             ach_tf = flops / per_launch_s / 1e12
             roof = {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                     "traffic": TRAFFIC_PER_LAUNCH.get(args.workload),
                     "peak_source": "SMs x 128 FP32 lanes x max SM clock, one non-fused FP32 op per lane per clock",
-                    "algorithmic_flops_per_launch": flops,
+                    "algorithmic_flops_per_launch": flops, "pairs_evaluated_frac": frac_eval,
+                    "all_pairs_equivalent": {"flops_per_launch": all_pairs, "achieved": all_pairs / per_launch_s / 1e12,
+                                             "frac": all_pairs / per_launch_s / 1e12 / peak_tf,
+                                             "note": "what an all-pairs scan (the reference's cdist) would need for this step rate"},
+                    "note": "time = whole step (integrate pre-pass + sensing kernel), flops = 9 per evaluated pair",
                     "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}}
         line = {
             "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
@@ -398,12 +429,14 @@ def run_gpu(args, w):
             "config": {"workload": args.workload + ": " + w["desc"], "envs_per_gpu": E, "agents": N, "k": w["k"],
                        "l2_policy": f"inputs larger than L2: ring of {ring} independent env batches "
                                     f"({ring * bytes_per_batch / 2**20:.0f} MiB), step s touches batch s % {ring}",
-                       "launch": "CUDA graph replay, one fused kernel per step, single stream"},
+                       "launch": ("CUDA graph replay, integrate pre-pass + sensing kernel per step (+ row-order refresh "
+                                  "every 16 steps), single stream") if envs[0].tiled else
+                                 "CUDA graph replay, one fused kernel per step, single stream"},
             "roofline": roof,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "VecEnv.step_host -> flock_step_host (pinned host buffers, sync per step)"},
-            "gpu_launches": steps * world,
+            "gpu_launches": launches * world,
             "stats_allreduce": {"backend": "nccl" if use_dist else "none", "episodes": int(stats[0].item())},
         }
         line.update(extra)

@@ -77,8 +77,8 @@ typedef struct flock_cfg_t {
  * the tiled (N > 32) path, which ping-pongs between the two copies every step; they may be NULL
  * when N <= 32. Nullable outputs are skipped by the kernels. */
 typedef struct flock_buffers_t {
-    float *x, *y, *h;               /* [E][N] positions and headings (current copy = slot 0) */
-    float *x_alt, *y_alt, *h_alt;   /* [E][N] slot 1 (tiled path only) */
+    float *x, *y, *h;               /* [E][N] positions and headings, updated in place */
+    float *x_alt, *y_alt, *h_alt;   /* unused (kept for layout compatibility), may be NULL */
     float *prev_h;                  /* [E][N] `prev_headings` (uw reward term, gym_flock_uw.py:201) */
     float *vx, *vy;                 /* [E][N] last displacement = reference `velocities`; nullable */
     float *obs;                     /* [E][N][obs_hist][k] newest first (gym_flock_uw.py:120-123) */
@@ -170,7 +170,7 @@ FLOCK_API int flock_step_host(flock_env_t *env, const float *h_actions, float dt
                     float *h_obs, float *h_reward, uint8_t *h_agent_done, uint8_t *h_env_done,
                     void *stream);
 
-/* Which state copy is current (0: x/y/h, 1: x_alt/y_alt/h_alt). Always 0 when N <= 32. */
+/* Which state copy is current: always 0 (the state is updated in place; kept for ABI compatibility). */
 FLOCK_API int flock_state_slot(const flock_env_t *env);
 
 /* Host-side count of steps issued through this handle (informational). */

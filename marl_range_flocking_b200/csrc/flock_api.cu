@@ -103,13 +103,8 @@ Params make_params(const flock_env* e, float dt) {
     p.step_offset = 0;
     p.num_steps = 1;
     p.max_attempts = 1;
-    const bool alt = e->path == 1 && e->slot == 1;
-    p.x = alt ? b.x_alt : b.x; p.y = alt ? b.y_alt : b.y; p.h = alt ? b.h_alt : b.h;
-    if (e->path == 1) {   // write the other copy
-        p.xo = alt ? b.x : b.x_alt; p.yo = alt ? b.y : b.y_alt; p.ho = alt ? b.h : b.h_alt;
-    } else {
-        p.xo = b.x; p.yo = b.y; p.ho = b.h;
-    }
+    p.x = b.x; p.y = b.y; p.h = b.h;       // the state is updated in place on both paths
+    p.xo = b.x; p.yo = b.y; p.ho = b.h;
     p.prev_h = b.prev_h; p.vx = b.vx; p.vy = b.vy; p.obs = b.obs; p.nn = b.nn_idx;
     p.reward = b.reward; p.agent_done = b.agent_done; p.env_done = b.env_done;
     p.reset_epoch = b.reset_epoch;
@@ -199,7 +194,6 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         }
         err = flock::launch_step_tiled(e->cfg.variant, e->cfg.periodic != 0, p, e->sm_count, e->tiled_mode, s);
         e->launches += flock::tiled_step_launches(e->cfg.variant, p, e->sm_count, e->tiled_mode);
-        if (err == cudaSuccess) e->slot ^= 1;
     }
     if (err != cudaSuccess) return cuda_fail(err, "step kernel launch");
     e->step_index += 1;
@@ -334,8 +328,6 @@ int flock_bind(flock_env_t* e, const flock_buffers_t* b) {
     if (!b->x || !b->y || !b->h || !b->prev_h || !b->obs || !b->reward || !b->agent_done || !b->env_done ||
         !b->reset_epoch || !b->ep_len)
         return fail(FLOCK_E_UNBOUND, "a required buffer pointer is NULL");
-    if (e->path == 1 && (!b->x_alt || !b->y_alt || !b->h_alt))
-        return fail(FLOCK_E_UNBOUND, "tiled path (N > 32) needs x_alt / y_alt / h_alt");
     e->b = *b;
     e->bound = true;
     e->slot = 0;

@@ -80,7 +80,7 @@ __device__ __forceinline__ TileSmem carve(float* base, int N, bool need_sh) {
     return TileSmem{base, base + P, need_sh ? base + 2 * P : nullptr, reinterpret_cast<uint2*>(after)};
 }
 
-// stage the env's old positions: TMA bulk copies when rows are 16-byte multiples, plain loads otherwise
+// stage the env's positions: TMA bulk copies when rows are 16-byte multiples, plain loads otherwise
 __device__ __forceinline__ void stage_xy(const Params& p, const TileSmem& sm, uint64_t* bar, int env) {
     const int N = p.N;
     const size_t base = (size_t)env * N;
@@ -235,71 +235,21 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
     int hint[K];
 #pragma unroll
     for (int s = 0; s < K; ++s) hint[s] = (p.nn != nullptr && has_row && s < k) ? p.nn[(base + i) * k + s] : -1;
-    uint32_t ep = 0u, repoch = 0u;
-    if (V == FLOCK_UWD) {
-        ep = (uint32_t)p.ep_len[env];
-        repoch = p.reset_epoch[env];
-    }
-    // this thread's own row, integrated from global (same inputs and code as the shared-memory pass
-    // below, hence bit-identical), so that the row can be any agent of the env
-    float x = 0.f, y = 0.f, h = 0.f, vx = 0.f, vy = 0.f;
-    if (has_row) {
-        x = p.x[base + i];
-        y = p.y[base + i];
-        h = p.h[base + i];
-        float a0, a1 = 0.0f, nzu = 0.f, nzw = 0.f;
-        if (V == FLOCK_UWD) {
-            a0 = p.actions[base + i];
-            if (p.noise != nullptr) {
-                const float2 nz = reinterpret_cast<const float2*>(p.noise)[base + i];
-                nzu = nz.x;
-                nzw = nz.y;
-            } else if (p.noise_std > 0.0f) {
-                act_noise(p, p.env_offset + env, i, ep, repoch, nzu, nzw);
-            }
-        } else {
-            const float2 act = reinterpret_cast<const float2*>(p.actions)[base + i];
-            a0 = act.x;
-            a1 = act.y;
-        }
-        integrate_agent<V>(p, a0, a1, nzu, nzw, x, y, h, vx, vy);
-    }
+    // the state was integrated in place by the pre-pass (flock_integrate_kernel): stage the NEW positions
     stage_xy(p, sm, &bar, env);
-
-    // integrate every agent of the env in place in shared memory (headings / actions come straight
-    // from global, coalesced)
-#pragma unroll 4
-    for (int a = threadIdx.x; a < N; a += rows) {
-        float ax = sm.sx[a], ay = sm.sy[a], ah = p.h[base + a];
-        float a0, a1 = 0.0f;
-        if (V == FLOCK_UWD) {
-            a0 = p.actions[base + a];
-        } else {
-            const float2 act = reinterpret_cast<const float2*>(p.actions)[base + a];
-            a0 = act.x;
-            a1 = act.y;
-        }
-        float nzu = 0.f, nzw = 0.f;
-        if (V == FLOCK_UWD) {
-            if (p.noise != nullptr) {
-                const float2 nz = reinterpret_cast<const float2*>(p.noise)[base + a];
-                nzu = nz.x;
-                nzw = nz.y;
-            } else if (p.noise_std > 0.0f) {
-                act_noise(p, p.env_offset + env, a, ep, repoch, nzu, nzw);
-            }
-        }
-        float avx, avy;
-        integrate_agent<V>(p, a0, a1, nzu, nzw, ax, ay, ah, avx, avy);
-        sm.sx[a] = ax;
-        sm.sy[a] = ay;
-        if (V == FLOCK_UWD) sm.sh[a] = ah;
-    }
+    if (V == FLOCK_UWD)
+        for (int a = threadIdx.x; a < N; a += rows) sm.sh[a] = p.h[base + a];
     if (threadIdx.x < padded_agents(N) - N) {
         sm.sx[N + threadIdx.x] = kInf;
         sm.sy[N + threadIdx.x] = 0.0f;
     }
     __syncthreads();
+    float x = 0.f, y = 0.f, h = 0.f;
+    if (has_row) {
+        x = sm.sx[i];
+        y = sm.sy[i];
+        h = p.h[base + i];
+    }
 
     float comx = 0.f, comy = 0.f, hmean = 0.f;
     if (V == FLOCK_UW) {
@@ -331,14 +281,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         if (V == FLOCK_UW) prev_h = p.prev_h[idx];
         const float rew = agent_reward<V>(p, coll, x, y, h, prev_h, comx, comy, hmean);
         fx = reward_fx(rew);
-        p.xo[idx] = x;
-        p.yo[idx] = y;
-        p.ho[idx] = h;
         if (V == FLOCK_UW && !(prev_h == h)) p.prev_h[idx] = h;
-        if (p.vx != nullptr) {
-            p.vx[idx] = vx;
-            p.vy[idx] = vy;
-        }
         write_obs_t<K>(p, idx, dist, false);
         if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
         p.reward[idx] = rew;
@@ -424,7 +367,7 @@ __device__ __forceinline__ float axis_gap(float a0, float a1, float b0, float b1
 
 // -------------------------------------------------------------------------------------------------
 // Pruned path for v2 large swarms. Two launches per step:
-//  1. flock_integrate_sorted_kernel: one thread per sorted SLOT integrates its agent ONCE (same code
+//  1. flock_integrate_kernel<V2, SORTED>: one thread per sorted SLOT integrates its agent ONCE (same code
 //     as everywhere else), writes the new state at the agent's index and, per env, a staging record
 //     [x by slot | y by slot | bounding boxes of every 8 consecutive slots] that is contiguous in memory.
 //  2. flock_step_pruned_kernel: one thread per row (in slot order); the CTA stages the env's record
@@ -437,22 +380,39 @@ constexpr int kBoxSlots = 8;
 
 __device__ __forceinline__ size_t sorted_record_floats(int PS) { return (size_t)PS * 2 + (size_t)PS / 2; }
 
-__global__ void __launch_bounds__(256) flock_integrate_sorted_kernel(const __grid_constant__ Params p) {
+template <int V, bool SORTED>
+__global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_constant__ Params p) {
     const int N = p.N, env = blockIdx.y;
     const int PS = ((N + 31) / 32) * 32;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= PS) return;                       // PS is a multiple of 32: whole warps leave together
     const size_t base = (size_t)env * N;
     const bool real = slot < N;
+    if (!SORTED && !real) return;
     float x = kInf, y = 0.0f;                     // padding slots: never selected, never collide
     if (real) {
-        const size_t i = base + (size_t)p.perm[base + slot];
+        const int a = SORTED ? p.perm[base + slot] : slot;
+        const size_t i = base + (size_t)a;
         float h = p.h[i], vx, vy;
         x = p.x[i];
         y = p.y[i];
-        const float2 act = reinterpret_cast<const float2*>(p.actions)[i];
-        integrate_agent<FLOCK_V2>(p, act.x, act.y, 0.f, 0.f, x, y, h, vx, vy);
-        p.xo[i] = x;
+        float a0, a1 = 0.0f, nzu = 0.f, nzw = 0.f;
+        if (V == FLOCK_UWD) {
+            a0 = p.actions[i];
+            if (p.noise != nullptr) {
+                const float2 nz = reinterpret_cast<const float2*>(p.noise)[i];
+                nzu = nz.x;
+                nzw = nz.y;
+            } else if (p.noise_std > 0.0f) {
+                act_noise(p, p.env_offset + env, a, (uint32_t)p.ep_len[env], p.reset_epoch[env], nzu, nzw);
+            }
+        } else {
+            const float2 act = reinterpret_cast<const float2*>(p.actions)[i];
+            a0 = act.x;
+            a1 = act.y;
+        }
+        integrate_agent<V>(p, a0, a1, nzu, nzw, x, y, h, vx, vy);
+        p.xo[i] = x;                              // in place: xo/yo/ho alias x/y/h on the tiled path
         p.yo[i] = y;
         p.ho[i] = h;
         if (p.vx != nullptr) {
@@ -460,19 +420,28 @@ __global__ void __launch_bounds__(256) flock_integrate_sorted_kernel(const __gri
             p.vy[i] = vy;
         }
     }
-    float* rec = p.sorted_xy + (size_t)env * sorted_record_floats(PS);
-    rec[slot] = x;
-    rec[PS + slot] = y;
-    float x0 = real ? x : kFltMax, x1 = real ? x : -kFltMax, y0 = real ? y : kFltMax, y1 = real ? y : -kFltMax;
+    if (SORTED) {
+        float* rec = p.sorted_xy + (size_t)env * sorted_record_floats(PS);
+        rec[slot] = x;
+        rec[PS + slot] = y;
+        float x0 = real ? x : kFltMax, x1 = real ? x : -kFltMax, y0 = real ? y : kFltMax, y1 = real ? y : -kFltMax;
 #pragma unroll
-    for (int m = 1; m < kBoxSlots; m <<= 1) {
-        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, m));
-        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, m));
-        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, m));
-        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, m));
+        for (int m = 1; m < kBoxSlots; m <<= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, m));
+            x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, m));
+            y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, m));
+            y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, m));
+        }
+        if ((slot & (kBoxSlots - 1)) == 0)
+            reinterpret_cast<float4*>(rec + 2 * (size_t)PS)[slot / kBoxSlots] = make_float4(x0, x1, y0, y1);
     }
-    if ((slot & (kBoxSlots - 1)) == 0)
-        reinterpret_cast<float4*>(rec + 2 * (size_t)PS)[slot / kBoxSlots] = make_float4(x0, x1, y0, y1);
+}
+
+template <int V, bool SORTED>
+static cudaError_t launch_integrate(const Params& p, cudaStream_t s) {
+    const int PS = ((p.N + 31) / 32) * 32;
+    flock_integrate_kernel<V, SORTED><<<dim3((PS + 255) / 256, p.E), 256, 0, s>>>(p);
+    return cudaGetLastError();
 }
 
 template <int K, bool PER>
@@ -649,9 +618,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
 template <int K, bool PER>
 static cudaError_t launch_pruned(const Params& p, int sm_count, cudaStream_t s) {
     {   // launch 1 of 2: integrate every agent once, in slot order
-        const int PS = ((p.N + 31) / 32) * 32;
-        flock_integrate_sorted_kernel<<<dim3((PS + 255) / 256, p.E), 256, 0, s>>>(p);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_integrate<FLOCK_V2, true>(p, s);
         if (e != cudaSuccess) return e;
     }
     const int rows = choose_rows(p.N, p.E, sm_count);
@@ -816,50 +783,9 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(con
     const int row0 = tile * rows_per_cta;
     const TileSmem sm = carve(smem, N, true);
     const size_t base = (size_t)env * N;
-    uint32_t ep = 0u, repoch = 0u;
-    if (V == FLOCK_UWD) {
-        ep = (uint32_t)p.ep_len[env];
-        repoch = p.reset_epoch[env];
-    }
+    // the state was integrated in place by the pre-pass: stage the NEW positions and headings
     stage_xy(p, sm, &bar, env);
-
-    // integrate every agent in place; the thread that integrates one of this CTA's rows also writes
-    // its state (other copy) and displacement
-    for (int a = threadIdx.x; a < N; a += blockDim.x) {
-        float ax = sm.sx[a], ay = sm.sy[a], ah = p.h[base + a];
-        float a0, a1 = 0.0f;
-        if (V == FLOCK_UWD) {
-            a0 = p.actions[base + a];
-        } else {
-            const float2 act = reinterpret_cast<const float2*>(p.actions)[base + a];
-            a0 = act.x;
-            a1 = act.y;
-        }
-        float nzu = 0.f, nzw = 0.f;
-        if (V == FLOCK_UWD) {
-            if (p.noise != nullptr) {
-                const float2 nz = reinterpret_cast<const float2*>(p.noise)[base + a];
-                nzu = nz.x;
-                nzw = nz.y;
-            } else if (p.noise_std > 0.0f) {
-                act_noise(p, p.env_offset + env, a, ep, repoch, nzu, nzw);
-            }
-        }
-        float avx, avy;
-        integrate_agent<V>(p, a0, a1, nzu, nzw, ax, ay, ah, avx, avy);
-        sm.sx[a] = ax;
-        sm.sy[a] = ay;
-        sm.sh[a] = ah;
-        if (a >= row0 && a < row0 + rows_per_cta) {
-            p.xo[base + a] = ax;
-            p.yo[base + a] = ay;
-            p.ho[base + a] = ah;
-            if (p.vx != nullptr) {
-                p.vx[base + a] = avx;
-                p.vy[base + a] = avy;
-            }
-        }
-    }
+    for (int a = threadIdx.x; a < N; a += blockDim.x) sm.sh[a] = p.h[base + a];
     __syncthreads();
 
     float comx = 0.f, comy = 0.f, hmean = 0.f;
@@ -1099,13 +1025,15 @@ static bool use_pruned(int variant, const Params& p, int sm_count, int tiled_mod
     return variant == FLOCK_V2 && prune_enabled() && p.perm != nullptr && p.sorted_xy != nullptr &&
            !use_rowwarp(p, sm_count, tiled_mode);
 }
-int tiled_step_launches(int variant, const Params& p, int sm_count, int tiled_mode) {
-    return use_pruned(variant, p, sm_count, tiled_mode) ? 2 : 1;
-}
+int tiled_step_launches(int, const Params&, int, int) { return 2; }   // integrate pre-pass + sensing kernel
 
 template <int V, int K, bool PER>
 static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, int tiled_mode, cudaStream_t s) {
     if (use_pruned(V, p, sm_count, tiled_mode)) return launch_pruned<(K < 4 ? 4 : K), PER>(p, sm_count, s);
+    {   // launch 1 of 2: integrate every agent once, in place
+        cudaError_t e = launch_integrate<V, false>(p, s);
+        if (e != cudaSuccess) return e;
+    }
     if (use_rowwarp(p, sm_count, tiled_mode)) return launch_rowwarp<V, (K < 4 ? 4 : K), PER>(p, sm_count, s);
     const int rows = choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);

@@ -101,9 +101,7 @@ class VecEnv:
         E, N, H = self.num_envs, self.num_particles, self.obs_hist
         f32 = dict(dtype=torch.float32, device=self.device)
         z = lambda *shape, **kw: torch.zeros(*shape, **{**f32, **kw})
-        self._x = [z(E, N)] + ([z(E, N)] if self.tiled else [])
-        self._y = [z(E, N)] + ([z(E, N)] if self.tiled else [])
-        self._hd = [z(E, N)] + ([z(E, N)] if self.tiled else [])
+        self._x, self._y, self._hd = z(E, N), z(E, N), z(E, N)    # updated in place on both kernel paths
         self._prev_h = z(E, N)
         self._vx = z(E, N) if track_velocities else None
         self._vy = z(E, N) if track_velocities else None
@@ -117,9 +115,7 @@ class VecEnv:
         self._stats = z(8, dtype=torch.int64)
         ptr = lambda t: None if t is None else t.data_ptr()
         bufs = FlockBuffers(
-            ptr(self._x[0]), ptr(self._y[0]), ptr(self._hd[0]),
-            ptr(self._x[1]) if self.tiled else None, ptr(self._y[1]) if self.tiled else None,
-            ptr(self._hd[1]) if self.tiled else None,
+            ptr(self._x), ptr(self._y), ptr(self._hd), None, None, None,    # x_alt / y_alt / h_alt: unused (ABI v1 slots)
             ptr(self._prev_h), ptr(self._vx), ptr(self._vy), ptr(self._obs), ptr(self._nn), ptr(self._reward),
             ptr(self._agent_done), ptr(self._env_done), ptr(self._reset_epoch), ptr(self._ep_return_fx),
             ptr(self._ep_len), ptr(self._stats))
@@ -158,9 +154,6 @@ class VecEnv:
         # raw handle of torch's current stream on our device (follows stream contexts and graph capture)
         return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
-    def _slot(self) -> int:
-        return self.lib.flock_state_slot(self._h) if self.tiled else 0
-
     def _dev_guard(self):
         # kernels must be launched with our device current; the common single-GPU-per-process case
         # needs no switch at all
@@ -184,15 +177,15 @@ class VecEnv:
     # ---- views of the device state (zero copy; overwritten by the next step) ------------------
     @property
     def x(self) -> torch.Tensor:
-        return self._x[self._slot()]
+        return self._x
 
     @property
     def y(self) -> torch.Tensor:
-        return self._y[self._slot()]
+        return self._y
 
     @property
     def headings(self) -> torch.Tensor:
-        return self._hd[self._slot()]
+        return self._hd
 
     @property
     def positions(self) -> torch.Tensor:
@@ -332,8 +325,7 @@ class VecEnv:
                     step_index=torch.tensor(self.step_index, dtype=torch.int64))
 
     def set_state(self, state: Dict[str, torch.Tensor]) -> None:
-        s = self._slot()
-        self._x[s].copy_(state["x"]); self._y[s].copy_(state["y"]); self._hd[s].copy_(state["headings"])
+        self._x.copy_(state["x"]); self._y.copy_(state["y"]); self._hd.copy_(state["headings"])
         if "prev_headings" in state:
             self._prev_h.copy_(state["prev_headings"])
         if "obs" in state:
