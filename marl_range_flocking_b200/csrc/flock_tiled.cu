@@ -336,11 +336,11 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
 // -------------------------------------------------------------------------------------------------
 size_t pruned_smem_bytes(int N, int rows) {
     const size_t PS = (size_t)((N + 31) / 32) * 32;
-    return (2 * PS + PS / 2) * sizeof(float) + (size_t)kCandCap * rows * sizeof(uint2);
+    return 3 * PS * sizeof(float) + (size_t)16 * rows * sizeof(unsigned short);   // record + kPrunedCandCap slots per row
 }
-size_t pruned_scratch_floats(int N, int E) {   // per env: x by slot | y by slot | one box per 8 slots
+size_t pruned_scratch_floats(int N, int E) {   // per env: x by slot | y by slot | boxes | agent ids (3 * PS floats)
     const size_t PS = (size_t)((N + 31) / 32) * 32;
-    return (size_t)E * (2 * PS + PS / 2);
+    return (size_t)E * 3 * PS;
 }
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -378,7 +378,9 @@ __device__ __forceinline__ float axis_gap(float a0, float a1, float b0, float b1
 // -------------------------------------------------------------------------------------------------
 constexpr int kBoxSlots = 8;
 
-__device__ __forceinline__ size_t sorted_record_floats(int PS) { return (size_t)PS * 2 + (size_t)PS / 2; }
+constexpr int kPrunedCandCap = 16;   // deferred candidates (slots) per row between two merges
+// per env: x by slot | y by slot | one (x0, x1, y0, y1) box per 8 slots | agent id (u16) by slot
+__host__ __device__ __forceinline__ size_t sorted_record_floats(int PS) { return (size_t)PS * 3; }
 
 template <int V, bool SORTED>
 __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_constant__ Params p) {
@@ -390,8 +392,10 @@ __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_const
     const bool real = slot < N;
     if (!SORTED && !real) return;
     float x = kInf, y = 0.0f;                     // padding slots: never selected, never collide
+    int agent = 0;
     if (real) {
         const int a = SORTED ? p.perm[base + slot] : slot;
+        agent = a;
         const size_t i = base + (size_t)a;
         float h = p.h[i], vx, vy;
         x = p.x[i];
@@ -434,6 +438,7 @@ __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_const
         }
         if ((slot & (kBoxSlots - 1)) == 0)
             reinterpret_cast<float4*>(rec + 2 * (size_t)PS)[slot / kBoxSlots] = make_float4(x0, x1, y0, y1);
+        reinterpret_cast<unsigned short*>(rec + 2 * (size_t)PS + PS / 2)[slot] = (unsigned short)(real ? agent : 0xffff);
     }
 }
 
@@ -456,7 +461,8 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     float* ss_x = smem;                 // new positions by sorted SLOT (padded to whole warps)
     float* ss_y = ss_x + PS;
     const float4* bb = reinterpret_cast<const float4*>(ss_y + PS);      // [nbox] (x0, x1, y0, y1)
-    uint2* cand = reinterpret_cast<uint2*>(ss_y + PS + 4 * nbox) + threadIdx.x;
+    const unsigned short* sid = reinterpret_cast<const unsigned short*>(ss_y + PS + 4 * nbox);   // agent id by slot
+    unsigned short* cand = reinterpret_cast<unsigned short*>(smem + sorted_record_floats(PS)) + threadIdx.x;
     const size_t base = (size_t)env * N;
     const int slot = tile * rows + threadIdx.x;
     const bool has_row = slot < N;
@@ -469,11 +475,29 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     const int i = has_row ? p.perm[base + slot] : N;    // this thread's agent
     int hslot[K];                                        // last step's neighbours, as slots (-1: unusable)
     bool hint_ok = has_row && p.nn != nullptr;
+    int hj[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) hj[s] = -1;
+    if (hint_ok) {
+        const int* row = p.nn + (base + i) * k;
+        if (K == 8 && k == 8) {                          // 32-byte rows: two 128-bit loads
+            const int4 a = reinterpret_cast<const int4*>(row)[0], b = reinterpret_cast<const int4*>(row)[1];
+            hj[0] = a.x; hj[1] = a.y; hj[2] = a.z; hj[3] = a.w;
+            hj[K - 4] = b.x; hj[K - 3] = b.y; hj[K - 2] = b.z; hj[K - 1] = b.w;
+        } else if (k == 4) {
+            const int4 a = reinterpret_cast<const int4*>(row)[0];
+            hj[0] = a.x; hj[1] = a.y; hj[2] = a.z; hj[3] = a.w;
+        } else {
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                if (s < k) hj[s] = row[s];
+        }
+    }
 #pragma unroll
     for (int s = 0; s < K; ++s) {
         hslot[s] = 0;
         if (s < k) {
-            const int j = hint_ok ? p.nn[(base + i) * k + s] : -1;
+            const int j = hj[s];
             const bool in = j >= 0 && j < N && j != i;
             hint_ok = hint_ok && in;
             hslot[s] = in ? p.inv[base + j] : 0;
@@ -507,19 +531,16 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     t.init();
     int cnt = 0;
     const int cstride = rows;
+    // Candidates are appended as SLOTS (2 bytes each); the merge recomputes their distance (same
+    // inputs, same code: same bits) and inserts them by the full (d2, agent id) key, because they
+    // do not arrive in index order. The row's own slot is dropped here, not in the pair loop.
     auto merge = [&]() {
-        int js[kCandCap];
-        float ds[kCandCap];
-#pragma unroll
-        for (int c = 0; c < kCandCap; ++c) {          // all slot -> agent lookups in flight together
-            const uint2 e = cand[c * cstride];
-            ds[c] = __uint_as_float(e.x);
-            js[c] = (c < cnt) ? p.perm[base + e.y] : i;
-        }
-#pragma unroll
-        for (int c = 0; c < kCandCap; ++c) {
-            if (__any_sync(kFull, c < cnt)) {
-                if (c < cnt && js[c] != i) t.insert_lex(ds[c], js[c]);
+        const int maxc = __reduce_max_sync(kFull, cnt);
+#pragma unroll 1
+        for (int c = 0; c < maxc; ++c) {
+            if (c < cnt) {
+                const int sj = cand[c * cstride];
+                if (sj != slot) t.insert_lex(pair_d2<PER>(x, y, ss_x[sj], ss_y[sj], p.B), (int)sid[sj]);
             }
         }
         cnt = 0;
@@ -559,11 +580,11 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
                     const float m = fminf(fminf(d0, d1), fminf(d2, d3));
                     if (__any_sync(kFull, m <= thr)) {
                         const unsigned sj = (unsigned)(s0 + (j4 << 2));
-                        if (d0 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d0), sj); ++cnt; }
-                        if (d1 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d1), sj + 1u); ++cnt; }
-                        if (d2 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d2), sj + 2u); ++cnt; }
-                        if (d3 <= thr) { cand[cnt * cstride] = make_uint2(__float_as_uint(d3), sj + 3u); ++cnt; }
-                        if (__any_sync(kFull, cnt > kCandCap - 4)) merge();
+                        if (d0 <= thr) { cand[cnt * cstride] = (unsigned short)sj; ++cnt; }
+                        if (d1 <= thr) { cand[cnt * cstride] = (unsigned short)(sj + 1u); ++cnt; }
+                        if (d2 <= thr) { cand[cnt * cstride] = (unsigned short)(sj + 2u); ++cnt; }
+                        if (d3 <= thr) { cand[cnt * cstride] = (unsigned short)(sj + 3u); ++cnt; }
+                        if (__any_sync(kFull, cnt > kPrunedCandCap - 4)) merge();
                     }
                 }
             }
@@ -615,13 +636,22 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     (void)wid;
 }
 
+static int pruned_rows_override() {   // FLOCK_PRUNED_ROWS=64|128|256: rows per CTA of the pruned kernel (tuning knob)
+    static const int v = [] {
+        const char* e = getenv("FLOCK_PRUNED_ROWS");
+        const int r = e != nullptr ? atoi(e) : 0;
+        return (r >= 32 && r <= kMaxTileThreads && r % 32 == 0) ? r : 0;
+    }();
+    return v;
+}
+
 template <int K, bool PER>
 static cudaError_t launch_pruned(const Params& p, int sm_count, cudaStream_t s) {
     {   // launch 1 of 2: integrate every agent once, in slot order
         cudaError_t e = launch_integrate<FLOCK_V2, true>(p, s);
         if (e != cudaSuccess) return e;
     }
-    const int rows = choose_rows(p.N, p.E, sm_count);
+    const int rows = pruned_rows_override() ? pruned_rows_override() : choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);
     flock_step_pruned_kernel<K, PER><<<grid, rows, pruned_smem_bytes(p.N, rows), s>>>(p);
     return cudaGetLastError();
