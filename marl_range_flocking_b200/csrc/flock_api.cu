@@ -45,7 +45,8 @@ struct flock_env {
     unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
     int* tile_perm;               // tiled thread-per-row path: spatially sorted row order [E][N]
     int* tile_inv;                // its inverse (agent -> slot)
-    float* sorted_xy;             // pruned path: new positions in slot order [E][2][nblk*32]
+    float* sorted_xy;             // pruned path: per-env staging record (positions by slot, boxes, ids)
+    unsigned short* hint_slots;   // pruned path: last step's neighbour slots per row
     uint32_t perm_age;            // steps since the row order was refreshed
     unsigned long long* pair_counter;   // device counter of row x neighbour pairs evaluated by the pruned kernel
     const void* zc_host[5];       // last host buffers seen by flock_step_host and their device aliases
@@ -116,6 +117,7 @@ Params make_params(const flock_env* e, float dt) {
     p.pair_counter = e->pair_counter;
     p.inv = e->tile_inv;
     p.sorted_xy = e->sorted_xy;
+    p.hint_slots = e->hint_slots;
     return p;
 }
 
@@ -292,6 +294,9 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         if (err == cudaSuccess) err = cudaMalloc(&e->tile_inv, (size_t)cfg->num_envs * cfg->num_agents * sizeof(int));
         if (err == cudaSuccess)
             err = cudaMalloc(&e->sorted_xy, flock::pruned_scratch_floats(cfg->num_agents, cfg->num_envs) * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&e->hint_slots, flock::pruned_hint_bytes(cfg->num_agents, cfg->num_envs));
+        if (err == cudaSuccess)
+            err = cudaMemset(e->hint_slots, 0xff, flock::pruned_hint_bytes(cfg->num_agents, cfg->num_envs));
         if (err == cudaSuccess)
             err = flock::launch_perm_identity(e->tile_perm, e->tile_inv, cfg->num_agents, cfg->num_envs, nullptr);
         if (err == cudaSuccess) err = cudaDeviceSynchronize();
@@ -301,6 +306,8 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         cudaFree(e->tile_perm);
         cudaFree(e->tile_inv);
         cudaFree(e->sorted_xy);
+    cudaFree(e->hint_slots);
+        cudaFree(e->hint_slots);
         cudaFree(e->pair_counter);
         cudaFree(e->stage_actions);
         cudaFree(e->stage_noise);
@@ -319,6 +326,7 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->tile_perm);
     cudaFree(e->tile_inv);
     cudaFree(e->sorted_xy);
+    cudaFree(e->hint_slots);
     cudaFree(e->pair_counter);
     delete e;
 }

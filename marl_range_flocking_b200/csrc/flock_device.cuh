@@ -57,7 +57,8 @@ struct Params {
     const int* perm;              // tiled thread-per-row path: [E][N] row order (spatially sorted), nullable = identity
     unsigned long long* pair_counter;   // pruned kernel: row x neighbour pairs actually evaluated (nullable)
     const int* inv;               // inverse of perm (agent -> slot)
-    float* sorted_xy;             // pruned path: [E][2][nblk*32] new positions in slot order
+    float* sorted_xy;             // pruned path: per env x | y by slot, boxes, agent ids (3 * PS floats)
+    unsigned short* hint_slots;   // pruned path: [E][PS][8] slots of last step's neighbours (0xffff: none)
     // host-call path: device-visible HOST mirrors of the step results (zero-copy), nullable
     float* m_obs;
     float* m_reward;

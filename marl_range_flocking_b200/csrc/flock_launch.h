@@ -22,6 +22,7 @@ cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int s
 cudaError_t launch_reset_tiled(const Params& p, cudaStream_t s);
 cudaError_t launch_perm_refresh(const Params& p, int* perm, int* inv, cudaStream_t s);   // spatial row order
 size_t pruned_scratch_floats(int N, int E);
+size_t pruned_hint_bytes(int N, int E);
 int tiled_step_launches(int variant, const Params& p, int sm_count, int tiled_mode);   // kernels per tiled step
 cudaError_t launch_perm_identity(int* perm, int* inv, int N, int E, cudaStream_t s);
 bool tiled_uses_row_order(const Params& p, int sm_count, int tiled_mode);

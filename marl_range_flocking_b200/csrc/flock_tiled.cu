@@ -338,6 +338,9 @@ size_t pruned_smem_bytes(int N, int rows) {
     const size_t PS = (size_t)((N + 31) / 32) * 32;
     return 3 * PS * sizeof(float) + (size_t)16 * rows * sizeof(unsigned short);   // record + kPrunedCandCap slots per row
 }
+size_t pruned_hint_bytes(int N, int E) {   // [E][PS] rows of 8 two-byte slots
+    return (size_t)E * ((size_t)((N + 31) / 32) * 32) * 16;
+}
 size_t pruned_scratch_floats(int N, int E) {   // per env: x by slot | y by slot | boxes | agent ids (3 * PS floats)
     const size_t PS = (size_t)((N + 31) / 32) * 32;
     return (size_t)E * 3 * PS;
@@ -473,36 +476,38 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         tma_load_1d(smem, p.sorted_xy + (size_t)env * sorted_record_floats(PS), bytes, &bar);
     }
     const int i = has_row ? p.perm[base + slot] : N;    // this thread's agent
-    int hslot[K];                                        // last step's neighbours, as slots (-1: unusable)
-    bool hint_ok = has_row && p.nn != nullptr;
-    int hj[K];
+    // Threshold hints: the slots of last step's k neighbours, kept by this kernel in slot order (one
+    // coalesced 16-byte row per agent). Any k distinct other slots bound the k-th distance, so stale
+    // rows are harmless; rows invalidated by a row-order refresh or a reset (0xffff) fall back to the
+    // neighbour list in agent ids (p.nn) translated through p.inv.
+    int hslot[K];
+    bool hint_ok = has_row;
+    {
+        uint4 hv = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (has_row) hv = reinterpret_cast<const uint4*>(p.hint_slots)[(size_t)env * PS + slot];
+        const unsigned w[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-    for (int s = 0; s < K; ++s) hj[s] = -1;
-    if (hint_ok) {
+        for (int s = 0; s < K; ++s) {
+            hslot[s] = (int)((w[(s >> 1) & 3] >> ((s & 1) * 16)) & 0xffffu);
+            if (s < k) hint_ok = hint_ok && hslot[s] < N && hslot[s] != slot;
+        }
+    }
+    if (has_row && !hint_ok && p.nn != nullptr) {
+        hint_ok = true;
         const int* row = p.nn + (base + i) * k;
-        if (K == 8 && k == 8) {                          // 32-byte rows: two 128-bit loads
-            const int4 a = reinterpret_cast<const int4*>(row)[0], b = reinterpret_cast<const int4*>(row)[1];
-            hj[0] = a.x; hj[1] = a.y; hj[2] = a.z; hj[3] = a.w;
-            hj[K - 4] = b.x; hj[K - 3] = b.y; hj[K - 2] = b.z; hj[K - 1] = b.w;
-        } else if (k == 4) {
-            const int4 a = reinterpret_cast<const int4*>(row)[0];
-            hj[0] = a.x; hj[1] = a.y; hj[2] = a.z; hj[3] = a.w;
-        } else {
 #pragma unroll
-            for (int s = 0; s < K; ++s)
-                if (s < k) hj[s] = row[s];
+        for (int s = 0; s < K; ++s) {
+            if (s < k) {
+                const int j = row[s];
+                const bool in = j >= 0 && j < N && j != i;
+                hint_ok = hint_ok && in;
+                hslot[s] = in ? p.inv[base + j] : 0;
+            }
         }
     }
 #pragma unroll
-    for (int s = 0; s < K; ++s) {
-        hslot[s] = 0;
-        if (s < k) {
-            const int j = hj[s];
-            const bool in = j >= 0 && j < N && j != i;
-            hint_ok = hint_ok && in;
-            hslot[s] = in ? p.inv[base + j] : 0;
-        }
-    }
+    for (int s = 0; s < K; ++s)
+        if (s >= k || !hint_ok) hslot[s] = 0;
 #pragma unroll
     for (int s = 1; s < K; ++s)
 #pragma unroll
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         for (int c = 0; c < maxc; ++c) {
             if (c < cnt) {
                 const int sj = cand[c * cstride];
-                if (sj != slot) t.insert_lex(pair_d2<PER>(x, y, ss_x[sj], ss_y[sj], p.B), (int)sid[sj]);
+                if (sj != slot) t.insert_lex(pair_d2<PER>(x, y, ss_x[sj], ss_y[sj], p.B), ((int)sid[sj] << 16) | sj);
             }
         }
         cnt = 0;
@@ -601,7 +606,17 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         const float rew = reward_from_flags<FLOCK_V2>(coll, false, false);
         fx = reward_fx(rew);
         write_obs_t<K>(p, idx, dist, false);
-        if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
+        // list entries are (agent id << 16 | slot): ids go to the neighbour list, slots to next step's hints
+        int ids[K];
+        unsigned hw[4] = {~0u, ~0u, ~0u, ~0u};
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            ids[s] = t.idx[s] >> 16;
+            const unsigned sl = (unsigned)t.idx[s] & 0xffffu;
+            hw[(s >> 1) & 3] = (s & 1) ? ((hw[(s >> 1) & 3] & 0xffffu) | (sl << 16)) : ((hw[(s >> 1) & 3] & 0xffff0000u) | sl);
+        }
+        if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, ids, k);
+        reinterpret_cast<uint4*>(p.hint_slots)[(size_t)env * PS + slot] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         p.reward[idx] = rew;
         p.agent_done[idx] = coll ? 1 : 0;
     }
@@ -732,6 +747,11 @@ __global__ void __launch_bounds__(256) flock_perm_refresh_kernel(const __grid_co
         const int s = count[key[a]] + pos[a];
         perm[base + s] = a;
         inv[base + a] = s;
+    }
+    if (p.hint_slots != nullptr) {   // slots changed meaning: next step takes its hints from the neighbour list
+        const int PS = ((N + 31) / 32) * 32;
+        uint4* hs = reinterpret_cast<uint4*>(p.hint_slots) + (size_t)env * PS;
+        for (int t = threadIdx.x; t < PS; t += blockDim.x) hs[t] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
 }
 
@@ -982,6 +1002,11 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(cons
             }
         }
         env_coll = __syncthreads_or(coll_any);
+    }
+    if (p.hint_slots != nullptr) {   // the pruned kernel's slot hints describe the old episode: drop them
+        const int PS = ((N + 31) / 32) * 32;
+        uint4* hs = reinterpret_cast<uint4*>(p.hint_slots) + (size_t)env * PS;
+        for (int t = threadIdx.x; t < PS; t += blockDim.x) hs[t] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     if (threadIdx.x == 0) {
         if (!keep) p.env_done[env] = env_coll ? 1 : 0;
