@@ -197,6 +197,24 @@ FLOCK_API int flock_set_tiled_mode(flock_env_t *env, int mode);
 FLOCK_API const char *flock_last_error(void);
 FLOCK_API int flock_abi_version(void);
 
+/* Fused per-agent actor MLP for the batched rollout ("MADDPG actor rollout", BASELINE configs[2]): the
+ * N ActorNetworks of learners/maddpg_shared_critic/ddpg_network.py:85-141 (fc1 -> LayerNorm -> ReLU ->
+ * fc2 -> LayerNorm -> ReLU -> mu -> tanh, 400 / 300 hidden units, 2 actions, input_dims <= 16) evaluated
+ * for all envs in one launch on the tensor cores (tcgen05, bf16 operands, fp32 accumulation), replacing
+ * the per-agent Python loop of learners/maddpg_shared_critic/train_flock.py:114-115.
+ *   flock_actor_packed_bytes: size of the packed parameter image for `num_agents` agents.
+ *   flock_actor_pack: `params` = 10 DEVICE pointers {w1 [A][in][400], b1 [A][400], ln1.weight, ln1.bias,
+ *     w2 [A][400][300], b2 [A][300], ln2.weight, ln2.bias, w3 [A][300][2], b3 [A][2]}, float32, weights
+ *     stored input-major (the transpose of torch.nn.Linear.weight); writes `packed` (device, 16-byte
+ *     aligned). Call again after every parameter update.
+ *   flock_actor_forward: obs [E][A][input_dims] float32 (the env's observation buffer) -> actions
+ *     [E][A][2] float32 (what flock_step consumes). Asynchronous on `stream`. */
+FLOCK_API size_t flock_actor_packed_bytes(int num_agents);
+FLOCK_API int flock_actor_pack(int num_agents, int input_dims, int fc1_dims, int fc2_dims, int n_actions,
+                     const float *const *params, void *packed, void *stream);
+FLOCK_API int flock_actor_forward(const void *packed, const float *obs, float *actions, int num_envs, int num_agents,
+                        int input_dims, void *stream);
+
 /* Debug / test hooks for the canonical arithmetic (device arrays, n elements). */
 FLOCK_API int flock_debug_sincos(const float *h, int n, float *sn, float *cs, void *stream);
 FLOCK_API int flock_debug_normal2(const uint32_t *words, int n_pairs, float *z, void *stream);

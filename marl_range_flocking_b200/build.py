@@ -16,7 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libflock_b200.so")
 SOURCES = ["flock_small_v2p.cu", "flock_small_v2e.cu", "flock_small_v2pn.cu", "flock_small_v2en.cu", "flock_small_uw.cu", "flock_small_uwn.cu", "flock_small_uwd.cu",
-           "flock_small_uwdn.cu", "flock_small.cu", "flock_tiled.cu", "flock_api.cu"]
+           "flock_small_uwdn.cu", "flock_small.cu", "flock_tiled.cu", "flock_actor.cu", "flock_api.cu"]
+FAST_MATH_OK = {"flock_actor.cu"}
 HEADERS = ["flock_device.cuh", "flock_small_impl.cuh", "flock_launch.h", os.path.join("..", "..", "include", "flock_b200.h")]
 
 # -fmad=false: no implicit FMA contraction (canonical arithmetic); explicit fmaf()/fma()
@@ -49,7 +50,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ_DIR, src[:-3] + ".o")
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            flags = NVCC_FLAGS
+            if src in FAST_MATH_OK:      # tensor-core policy kernel: not part of the bit-exact env path
+                flags = [f for f in NVCC_FLAGS if f != "-fmad=false"]
+            cmd = [nvcc, *flags, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

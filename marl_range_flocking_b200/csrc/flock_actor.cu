@@ -1,0 +1,442 @@
+// flock_actor.cu -- fused per-agent actor MLP for the batched rollout (BASELINE configs[2]
+// "MADDPG actor rollout"): the N per-agent ActorNetworks of
+// learners/maddpg_shared_critic/ddpg_network.py:85-141
+//     fc1(in -> 400) -> LayerNorm -> ReLU -> fc2(400 -> 300) -> LayerNorm -> ReLU -> mu(300 -> 2) -> tanh
+// evaluated for all envs in ONE launch, straight from the env's observation buffer into the action
+// buffer flock_step consumes. This IS GEMM-shaped work (250 kFLOP per agent-step, 40x the env step),
+// so it runs on the 5th-generation tensor cores:
+//   * CTA = 128 envs x one agent; both matrix layers are tcgen05.mma (kind::f16, bf16 operands, fp32
+//     accumulators in TMEM, M = 128), issued by one thread; operands sit in shared memory in the
+//     no-swizzle K-major canonical layout (8-row x 16-byte core matrices);
+//   * the per-agent weights are pre-packed once (flock_actor_pack) into exactly the shared-memory
+//     image the MMA wants, so they stream from L2 with plain 1-D TMA bulk copies (cp.async.bulk +
+//     mbarrier complete_tx) through an 8-stage ring -- no tensor maps;
+//   * four epilogue warps read the accumulators back with tcgen05.ld (warp w owns TMEM lanes
+//     32w..32w+31 = 32 env rows), apply bias + LayerNorm + ReLU in fp32 and write the layer-2 A operand
+//     back to shared memory as bf16; the 300 -> 2 head and tanh run in the second epilogue on CUDA
+//     cores, so the activations never touch global memory.
+// Accumulation and LayerNorm are fp32; operands are bf16 (tested against the fp32 PyTorch module).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "flock_launch.h"
+
+namespace flock {
+namespace actor {
+
+constexpr int kRows = 128;                   // env rows per CTA = UMMA M
+constexpr int kInPad = 16;                   // layer-1 K, one UMMA K step of bf16
+constexpr int kFc1 = 400, kFc2 = 300, kFc2Pad = 304, kAct = 2;
+constexpr int kSteps2 = kFc1 / 16;           // 25 K steps of layer 2
+constexpr int kStages = 8;                   // W2 ring depth
+constexpr int kW1Bytes = 2 * kFc1 * 16;      // 2 k-groups x 400 rows x 16 B
+constexpr int kChunkBytes = 2 * kFc2Pad * 16;   // one K step of W2: 2 k-groups x 304 rows x 16 B
+// fp32 parameters: b1 g1 be1 [400] | b2 g2 be2 [304] | w3[:,0] w3[:,1] [304] | b3[2] + 2 pad
+constexpr int kParamFloats = 3 * kFc1 + 5 * kFc2Pad + 4;
+constexpr int kParamBytes = kParamFloats * 4;
+constexpr int kBlobBytes = kW1Bytes + kParamBytes + kSteps2 * kChunkBytes;
+static_assert(kParamBytes % 16 == 0 && kBlobBytes % 16 == 0, "bulk copies move 16-byte units");
+
+// shared-memory carve-up (offsets from a 128-byte aligned base)
+constexpr int kOffA2 = 0;                                  // layer-2 A: 50 k-groups x 128 rows x 16 B
+constexpr int kA2Bytes = (kFc1 / 8) * kRows * 16;
+constexpr int kOffA1 = kOffA2 + kA2Bytes;                  // layer-1 A: 2 k-groups x 128 rows x 16 B
+constexpr int kA1Bytes = 2 * kRows * 16;
+constexpr int kOffW1 = kOffA1 + kA1Bytes;
+constexpr int kOffPar = kOffW1 + kW1Bytes;
+constexpr int kOffRing = (kOffPar + kParamBytes + 127) & ~127;
+constexpr int kOffBar = kOffRing + kStages * kChunkBytes;
+constexpr int kNumBars = 2 * kStages + 5;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 128;   // + tmem pointer + alignment slack
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+constexpr int kThreads = 160;               // warps 0-3: rows / epilogues, warp 4: TMA + MMA issue
+constexpr int kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B contiguous;
+// SBO = byte distance between consecutive 8-row groups, LBO = between the two 8-element K halves of
+// one K = 16 step (cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30), SBO [32,46) in 16-byte
+// units, version [46,48) = 1 on sm_100, layout type [61,64) = 0).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = BF16 [7,10) / [10,13) = 1,
+// both K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when all MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane (warp-collective)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    // the wait takes the registers as in/out operands so that no use can be scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);   // .x = lo (low half), .y = hi
+    return *reinterpret_cast<const uint32_t*>(&b);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// grid = (agents, ceil(E / 128)); obs [E][N][in_dims] fp32, out [E][N][2] fp32
+__global__ void __launch_bounds__(kThreads, 1)
+flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ obs, float* __restrict__ out, int E, int N,
+                   int in_dims) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 127u) & ~127u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int agent = blockIdx.x, tile = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint8_t* blob = blobs + (size_t)agent * kBlobBytes;
+
+    const uint32_t sA2 = base + kOffA2, sA1 = base + kOffA1, sW1 = base + kOffW1, sPar = base + kOffPar;
+    const uint32_t sRing = base + kOffRing, sBar = base + kOffBar;
+    auto bar_full = [&](int s) { return sBar + 8u * s; };
+    auto bar_empty = [&](int s) { return sBar + 8u * (kStages + s); };
+    const uint32_t bar_w1 = sBar + 8u * (2 * kStages), bar_a1 = bar_w1 + 8u, bar_mma1 = bar_w1 + 16u, bar_a2 = bar_w1 + 24u,
+                   bar_mma2 = bar_w1 + 32u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + kNumBars * 8);
+    const float* par = reinterpret_cast<const float*>(sm + kOffPar);
+
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                mbar_init(bar_full(s), 1);
+                mbar_init(bar_empty(s), 1);
+            }
+            mbar_init(bar_w1, 1);
+            mbar_init(bar_a1, kRows);
+            mbar_init(bar_mma1, 1);
+            mbar_init(bar_a2, kRows);
+            mbar_init(bar_mma2, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---- producer + MMA issuer (one thread) ----
+            mbar_expect_tx(bar_w1, kW1Bytes + kParamBytes);
+            bulk_g2s(sW1, blob, kW1Bytes, bar_w1);
+            bulk_g2s(sPar, blob + kW1Bytes, kParamBytes, bar_w1);
+            const uint8_t* w2 = blob + kW1Bytes + kParamBytes;
+            for (int c = 0; c < kStages; ++c) {
+                mbar_expect_tx(bar_full(c), kChunkBytes);
+                bulk_g2s(sRing + c * kChunkBytes, w2 + (size_t)c * kChunkBytes, kChunkBytes, bar_full(c));
+            }
+            // layer 1: [128 x 16] x [16 x 400] -> TMEM columns [0, 400)
+            mbar_wait(bar_a1, 0);
+            mbar_wait(bar_w1, 0);
+            tc_fence_after();
+            {
+                const uint64_t da = umma_desc(sA1, kRows * 16, 128);
+                umma_bf16(tmem + 0, da, umma_desc(sW1, kFc1 * 16, 128), umma_idesc(kRows, 256), 0u);
+                umma_bf16(tmem + 256, da, umma_desc(sW1 + 256 * 16, kFc1 * 16, 128), umma_idesc(kRows, 144), 0u);
+            }
+            umma_commit(bar_mma1);
+            // layer 2: [128 x 400] x [400 x 304] -> TMEM columns [0, 304) (layer-1 accumulators are dead by then)
+            mbar_wait(bar_a2, 0);
+            tc_fence_after();
+            for (int s = 0; s < kSteps2; ++s) {
+                const int st = s % kStages;
+                mbar_wait(bar_full(st), (uint32_t)(s / kStages) & 1u);
+                tc_fence_after();
+                const uint64_t da = umma_desc(sA2 + s * (2 * kRows * 16), kRows * 16, 128);
+                const uint32_t sb = sRing + st * kChunkBytes;
+                umma_bf16(tmem + 0, da, umma_desc(sb, kFc2Pad * 16, 128), umma_idesc(kRows, 160), s > 0 ? 1u : 0u);
+                umma_bf16(tmem + 160, da, umma_desc(sb + 160 * 16, kFc2Pad * 16, 128), umma_idesc(kRows, 144), s > 0 ? 1u : 0u);
+                umma_commit(bar_empty(st));
+                // refill the slot of chunk s-2 (its MMAs are normally done by now) with chunk s+6
+                const int r = s - 2;
+                if (r >= 0 && r + kStages < kSteps2) {
+                    const int rs = r % kStages;
+                    mbar_wait(bar_empty(rs), (uint32_t)(r / kStages) & 1u);
+                    mbar_expect_tx(bar_full(rs), kChunkBytes);
+                    bulk_g2s(sRing + rs * kChunkBytes, w2 + (size_t)(r + kStages) * kChunkBytes, kChunkBytes, bar_full(rs));
+                }
+            }
+            umma_commit(bar_mma2);
+        }
+    } else {
+        // ---- rows: one thread per env ----
+        const int row = threadIdx.x;                       // 0..127 = TMEM lane
+        const int env = tile * kRows + row;
+        const bool valid = env < E;
+        float xin[kInPad];
+#pragma unroll
+        for (int i = 0; i < kInPad; ++i) xin[i] = 0.0f;
+        if (valid) {
+            const float* src = obs + ((size_t)env * N + agent) * in_dims;
+            if (in_dims == 12) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                const float4 a = s4[0], b = s4[1], c = s4[2];
+                xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w;
+                xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
+                xin[8] = c.x; xin[9] = c.y; xin[10] = c.z; xin[11] = c.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < kInPad; ++i)
+                    if (i < in_dims) xin[i] = src[i];
+            }
+        }
+        sts128(sA1 + row * 16, pack_bf16(xin[0], xin[1]), pack_bf16(xin[2], xin[3]), pack_bf16(xin[4], xin[5]),
+               pack_bf16(xin[6], xin[7]));
+        sts128(sA1 + kRows * 16 + row * 16, pack_bf16(xin[8], xin[9]), pack_bf16(xin[10], xin[11]),
+               pack_bf16(xin[12], xin[13]), pack_bf16(xin[14], xin[15]));
+        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(bar_a1);
+
+        mbar_wait(bar_w1, 0);           // fp32 parameters have landed
+        const float* b1 = par;
+        const float* g1 = par + kFc1;
+        const float* be1 = par + 2 * kFc1;
+        const float* b2 = par + 3 * kFc1;
+        const float* g2 = b2 + kFc2Pad;
+        const float* be2 = b2 + 2 * kFc2Pad;
+        const float* w3a = b2 + 3 * kFc2Pad;
+        const float* w3b = b2 + 4 * kFc2Pad;
+        const float* b3 = b2 + 5 * kFc2Pad;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+
+        // ---- epilogue 1: bias + LayerNorm(400) + ReLU -> bf16 A operand of layer 2 ----
+        mbar_wait(bar_mma1, 0);
+        tc_fence_after();
+        float sum = 0.0f, sq = 0.0f;
+        for (int c0 = 0; c0 < kFc1; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = v[i] + b1[c0 + i];
+                sum += t;
+                sq = fmaf(t, t, sq);
+            }
+        }
+        float mean = sum * (1.0f / kFc1);
+        float rstd = rsqrtf(fmaxf(sq * (1.0f / kFc1) - mean * mean, 0.0f) + 1.0e-5f);
+        for (int c0 = 0; c0 < kFc1; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = (v[i] + b1[c0 + i] - mean) * rstd;
+                v[i] = fmaxf(fmaf(t, g1[c0 + i], be1[c0 + i]), 0.0f);
+            }
+            const uint32_t dst = sA2 + (c0 >> 3) * (kRows * 16) + row * 16;
+            sts128(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            sts128(dst + kRows * 16, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                   pack_bf16(v[14], v[15]));
+        }
+        fence_proxy_async();
+        tc_fence_before();              // our tcgen05.ld of columns [0,400) precede the layer-2 MMAs that overwrite them
+        mbar_arrive(bar_a2);
+
+        // ---- epilogue 2: bias + LayerNorm(300) + ReLU, mu head (300 -> 2), tanh ----
+        mbar_wait(bar_mma2, 0);
+        tc_fence_after();
+        sum = 0.0f;
+        sq = 0.0f;
+        for (int c0 = 0; c0 < kFc2Pad; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = (c0 + i < kFc2) ? v[i] + b2[c0 + i] : 0.0f;
+                sum += t;
+                sq = fmaf(t, t, sq);
+            }
+        }
+        mean = sum * (1.0f / kFc2);
+        rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean * mean, 0.0f) + 1.0e-5f);
+        float o0 = 0.0f, o1 = 0.0f;
+        for (int c0 = 0; c0 < kFc2Pad; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = (v[i] + b2[c0 + i] - mean) * rstd;
+                const float yv = fmaxf(fmaf(t, g2[c0 + i], be2[c0 + i]), 0.0f);   // padded columns: w3 = 0
+                o0 = fmaf(yv, w3a[c0 + i], o0);
+                o1 = fmaf(yv, w3b[c0 + i], o1);
+            }
+        }
+        if (valid) {
+            float2 a;
+            a.x = tanhf(o0 + b3[0]);
+            a.y = tanhf(o1 + b3[1]);
+            reinterpret_cast<float2*>(out)[(size_t)env * N + agent] = a;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// Pre-pack the per-agent parameters (fp32, the layout of policies.BatchedActors: w [A][in][out],
+// vectors [A][out]) into the shared-memory images of the kernel above. One thread per 16 bytes.
+struct PackArgs {
+    const float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *w3, *b3;
+    int agents, in_dims;
+};
+
+__global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs) {
+    const int units = kBlobBytes / 16;
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (gid >= (size_t)units * a.agents) return;
+    const int ag = (int)(gid / units);
+    int u = (int)(gid % units);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (u < kW1Bytes / 16) {                       // W1 image: [k-group][n] x 8 bf16
+        const int kg = u / kFc1, n = u % kFc1;
+        float v[8];
+        for (int j = 0; j < 8; ++j) {
+            const int k = kg * 8 + j;
+            v[j] = k < a.in_dims ? a.w1[((size_t)ag * a.in_dims + k) * kFc1 + n] : 0.0f;
+        }
+        o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    } else if (u < (kW1Bytes + kParamBytes) / 16) {   // fp32 parameters
+        const int f0 = (u - kW1Bytes / 16) * 4;
+        float v[4];
+        for (int j = 0; j < 4; ++j) {
+            int f = f0 + j;
+            float x = 0.0f;
+            if (f < 3 * kFc1) {
+                const float* src = f < kFc1 ? a.b1 : (f < 2 * kFc1 ? a.g1 : a.be1);
+                x = src[(size_t)ag * kFc1 + f % kFc1];
+            } else {
+                f -= 3 * kFc1;
+                const int which = f / kFc2Pad, c = f % kFc2Pad;
+                if (which < 3) {
+                    const float* src = which == 0 ? a.b2 : (which == 1 ? a.g2 : a.be2);
+                    x = c < kFc2 ? src[(size_t)ag * kFc2 + c] : 0.0f;
+                } else if (which < 5) {
+                    x = c < kFc2 ? a.w3[((size_t)ag * kFc2 + c) * kAct + (which - 3)] : 0.0f;
+                } else {
+                    x = c < kAct ? a.b3[(size_t)ag * kAct + c] : 0.0f;
+                }
+            }
+            v[j] = x;
+        }
+        o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    } else {                                        // W2 images: [K step][k-group][n] x 8 bf16
+        u -= (kW1Bytes + kParamBytes) / 16;
+        const int s = u / (2 * kFc2Pad), rem = u % (2 * kFc2Pad);
+        const int kg = rem / kFc2Pad, n = rem % kFc2Pad;
+        float v[8];
+        for (int j = 0; j < 8; ++j) {
+            const int k = s * 16 + kg * 8 + j;
+            v[j] = n < kFc2 ? a.w2[((size_t)ag * kFc1 + k) * kFc2 + n] : 0.0f;
+        }
+        o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    reinterpret_cast<uint4*>(blobs)[gid] = o;
+}
+
+}  // namespace actor
+
+size_t actor_blob_bytes() { return (size_t)actor::kBlobBytes; }
+int actor_max_in_dims() { return actor::kInPad; }
+void actor_dims(int* fc1, int* fc2, int* n_actions) {
+    *fc1 = actor::kFc1;
+    *fc2 = actor::kFc2;
+    *n_actions = actor::kAct;
+}
+
+cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s) {
+    actor::PackArgs a{ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6], ptrs[7], ptrs[8], ptrs[9], agents, in_dims};
+    const size_t total = (size_t)(actor::kBlobBytes / 16) * agents;
+    actor::flock_actor_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, static_cast<uint8_t*>(blobs));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
+                                 cudaStream_t s) {
+    static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         actor::kSmemBytes);
+    if (configured != cudaSuccess) return configured;
+    const dim3 grid((unsigned)N, (unsigned)((E + actor::kRows - 1) / actor::kRows));
+    actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(static_cast<const uint8_t*>(blobs), obs, actions,
+                                                                            E, N, in_dims);
+    return cudaGetLastError();
+}
+
+}  // namespace flock

@@ -499,6 +499,47 @@ int flock_set_tiled_mode(flock_env_t* e, int mode) {
     return FLOCK_OK;
 }
 
+size_t flock_actor_packed_bytes(int num_agents) {
+    return num_agents > 0 ? (size_t)num_agents * flock::actor_blob_bytes() : 0;
+}
+
+static int actor_check_dims(int num_agents, int in_dims, int fc1_dims, int fc2_dims, int n_actions) {
+    int fc1, fc2, na;
+    flock::actor_dims(&fc1, &fc2, &na);
+    if (num_agents < 1 || num_agents > 65535) return fail(FLOCK_E_INVALID, "num_agents %d not in [1, 65535]", num_agents);
+    if (in_dims < 1 || in_dims > flock::actor_max_in_dims())
+        return fail(FLOCK_E_INVALID, "actor input_dims %d not in [1, %d]", in_dims, flock::actor_max_in_dims());
+    if (fc1_dims != fc1 || fc2_dims != fc2 || n_actions != na)
+        return fail(FLOCK_E_INVALID, "fused actor is built for %d-%d-%d (got %d-%d-%d)", fc1, fc2, na, fc1_dims, fc2_dims,
+                    n_actions);
+    return FLOCK_OK;
+}
+
+int flock_actor_pack(int num_agents, int in_dims, int fc1_dims, int fc2_dims, int n_actions, const float* const* params,
+                     void* packed, void* stream) {
+    int rc = actor_check_dims(num_agents, in_dims, fc1_dims, fc2_dims, n_actions);
+    if (rc != FLOCK_OK) return rc;
+    if (params == nullptr || packed == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    for (int i = 0; i < 10; ++i)
+        if (params[i] == nullptr) return fail(FLOCK_E_INVALID, "actor parameter %d is NULL", i);
+    cudaError_t err = flock::launch_actor_pack(num_agents, in_dims, params, packed, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor pack kernel launch");
+}
+
+int flock_actor_forward(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
+                        void* stream) {
+    int rc = actor_check_dims(num_agents, in_dims, 400, 300, 2);
+    if (rc != FLOCK_OK) return rc;
+    if (packed == nullptr || obs == nullptr || actions == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    if (num_envs < 1 || (num_envs + 127) / 128 > 65535) return fail(FLOCK_E_INVALID, "num_envs %d out of range", num_envs);
+    if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(obs) & 15u) ||
+        (reinterpret_cast<uintptr_t>(actions) & 7u))
+        return fail(FLOCK_E_INVALID, "actor buffers must be 16-byte aligned");
+    cudaError_t err = flock::launch_actor_forward(packed, obs, actions, num_envs, num_agents, in_dims,
+                                                  static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor forward kernel launch");
+}
+
 int flock_debug_sincos(const float* h, int n, float* sn, float* cs, void* stream) {
     cudaError_t err = flock::launch_debug_sincos(h, n, sn, cs, static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "debug_sincos");

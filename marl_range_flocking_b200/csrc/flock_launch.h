@@ -26,4 +26,12 @@ size_t pruned_hint_bytes(int N, int E);
 int tiled_step_launches(int variant, const Params& p, int sm_count, int tiled_mode);   // kernels per tiled step
 cudaError_t launch_perm_identity(int* perm, int* inv, int N, int E, cudaStream_t s);
 bool tiled_uses_row_order(const Params& p, int sm_count, int tiled_mode);
+
+// flock_actor.cu (fused per-agent actor MLP on the tensor cores)
+size_t actor_blob_bytes();
+int actor_max_in_dims();
+void actor_dims(int* fc1, int* fc2, int* n_actions);
+cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s);
+cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
+                                 cudaStream_t s);
 }  // namespace flock

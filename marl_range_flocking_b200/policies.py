@@ -43,6 +43,7 @@ class BatchedActors(torch.nn.Module):
         self.be2 = torch.nn.Parameter(torch.zeros(n, 1, fc2_dims, **kw))
         self.w3, self.b3 = uni((n, fc2_dims, n_actions), f3), uni((n, 1, n_actions), f3)
         self.num_agents, self.input_dims = n, input_dims
+        self._packed = None
 
     @classmethod
     def from_state_dicts(cls, sds: Sequence[Dict[str, torch.Tensor]], device=None, dtype=torch.float32):
@@ -58,6 +59,47 @@ class BatchedActors(torch.nn.Module):
                 g.copy_(_stack(sds, name + ".weight").unsqueeze(1))
                 be.copy_(_stack(sds, name + ".bias").unsqueeze(1))
         return self
+
+    # ---- fused tensor-core path (csrc/flock_actor.cu through the C ABI) ----
+    def pack_fused(self) -> torch.Tensor:
+        """(Re)build the packed parameter image of `flock_actor_forward` from the current parameters
+        (call after every optimiser step). No fallback: raises if the CUDA library is missing."""
+        import ctypes
+
+        from . import _lib
+        lib = _lib.load_library()
+        if self.w1.device.type != "cuda":
+            raise RuntimeError("the fused actor kernel needs CUDA parameters (there is no CPU path)")
+        fc1, fc2, na = self.w1.shape[2], self.w2.shape[2], self.w3.shape[2]
+        srcs = [t.detach().float().contiguous() for t in (self.w1, self.b1, self.g1, self.be1, self.w2, self.b2, self.g2,
+                                                          self.be2, self.w3, self.b3)]
+        ptrs = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in srcs])
+        packed = torch.empty(lib.flock_actor_packed_bytes(self.num_agents), dtype=torch.uint8, device=self.w1.device)
+        with torch.cuda.device(self.w1.device):
+            _lib.check(lib.flock_actor_pack(self.num_agents, self.input_dims, fc1, fc2, na, ptrs, packed.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+        self._packed = packed
+        self._packed_srcs = srcs      # keep the fp32 sources alive until the pack kernel has run
+        return packed
+
+    @torch.no_grad()
+    def forward_fused(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same function as `forward` in ONE kernel launch on the tensor cores (bf16 operands, fp32
+        accumulation / LayerNorm): `(E, N, ...)` float32 CUDA observations -> `(E, N, 2)` actions."""
+        from . import _lib
+        lib = _lib.load_library()
+        if getattr(self, "_packed", None) is None:
+            self.pack_fused()
+        E, N = obs.shape[0], obs.shape[1]
+        x = obs.reshape(E, N, -1)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        if out is None:
+            out = torch.empty(E, N, 2, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.flock_actor_forward(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2],
+                                               torch.cuda.current_stream().cuda_stream))
+        return out
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         E, N = obs.shape[0], obs.shape[1]

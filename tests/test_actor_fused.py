@@ -1,0 +1,100 @@
+"""Fused tensor-core actor kernel (csrc/flock_actor.cu, flock_actor_forward through the C ABI) against
+plain PyTorch references of the same op: the fp32 module (`policies.BatchedActors.forward`, itself
+CPU-tested against the reference's ActorNetwork layout) and an fp32 emulation of the kernel's
+arithmetic (bf16-rounded matrix operands, fp32 accumulation / LayerNorm / head).
+
+Tolerances (floating-point kernel; outputs are tanh values in [-1, 1]):
+  * vs. the bf16-operand emulation: 4e-3 absolute -- only summation order and rsqrt/tanh
+    implementation differ; a wrong operand layout gives O(1) errors;
+  * vs. the fp32 module: 4e-2 absolute -- the cost of bf16 operands (2^-9 relative per operand)
+    through two 400/300-wide layers.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _actors(N, in_dims, seed, device):
+    from marl_range_flocking_b200.policies import BatchedActors
+    torch.manual_seed(seed)
+    a = BatchedActors(N, in_dims, 400, 300, 2, device=device)
+    with torch.no_grad():                      # non-trivial LayerNorm affine and an O(1) head
+        a.g1.uniform_(0.5, 1.5)
+        a.be1.uniform_(-0.3, 0.3)
+        a.g2.uniform_(0.5, 1.5)
+        a.be2.uniform_(-0.3, 0.3)
+        a.w3.uniform_(-0.15, 0.15)
+        a.b3.uniform_(-0.2, 0.2)
+        a.w1.mul_(4.0)
+    return a
+
+
+def _emulate_bf16_operands(a, obs):
+    r = lambda t: t.bfloat16().float()
+    E, N = obs.shape[:2]
+    x = r(obs.reshape(E, N, -1).transpose(0, 1))
+    x = torch.baddbmm(a.b1, x, r(a.w1))
+    x = F.relu(F.layer_norm(x, x.shape[-1:]) * a.g1 + a.be1)
+    x = torch.baddbmm(a.b2, r(x), r(a.w2))
+    x = F.relu(F.layer_norm(x, x.shape[-1:]) * a.g2 + a.be2)
+    return torch.tanh(torch.baddbmm(a.b3, x, a.w3)).transpose(0, 1).contiguous()
+
+
+@pytest.mark.parametrize("E,N,in_dims", [(128, 1, 12), (300, 5, 12), (4096, 32, 12), (77, 3, 16), (200, 4, 9), (1, 2, 12)])
+def test_fused_actor_matches_pytorch(E, N, in_dims):
+    dev = torch.device("cuda:0")
+    a = _actors(N, in_dims, 11 + E, dev)
+    torch.manual_seed(E * 7 + N)
+    obs = torch.rand(E, N, in_dims, device=dev) * 7.0          # ranges in [0, sensor_range]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want32 = a(obs)
+            want16 = _emulate_bf16_operands(a, obs)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    got = a.forward_fused(obs)
+    torch.cuda.synchronize()
+    assert got.shape == (E, N, 2) and got.dtype == torch.float32
+    assert torch.isfinite(got).all()
+    assert want32.abs().max() > 0.2                              # the comparison is not vacuous
+    err16 = (got - want16).abs().max().item()
+    err32 = (got - want32).abs().max().item()
+    assert err16 <= 4e-3, (err16, err32)
+    assert err32 <= 4e-2, (err16, err32)
+
+
+def test_fused_actor_drives_the_env_and_repacks_after_an_update():
+    from marl_range_flocking_b200 import VecEnv
+    dev = torch.device("cuda:0")
+    E, N, k = 256, 32, 3
+    env = VecEnv("uw", E, N, k, 0.5, range_start=(0, 200), sensor_range=7.0, seed=5, device="cuda:0")
+    obs = env.reset()
+    a = _actors(N, 4 * k, 3, dev)
+    acts = torch.empty(E, N, 2, device=dev)
+    for _ in range(4):
+        a.forward_fused(obs, out=acts)
+        obs, reward, dones, _ = env.step(acts, 0.1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs).all() and acts.abs().max() <= 1.0
+    with torch.no_grad():
+        before = a.forward_fused(obs).clone()
+        a.w3.mul_(-1.0)
+        a.b3.mul_(-1.0)
+        a.pack_fused()
+        after = a.forward_fused(obs)
+    torch.cuda.synchronize()
+    assert torch.allclose(after, -before, atol=1e-6)             # tanh is odd: the new parameters are in use
+
+
+def test_fused_actor_rejects_unsupported_shapes():
+    from marl_range_flocking_b200 import _lib
+    from marl_range_flocking_b200.policies import BatchedActors
+    dev = torch.device("cuda:0")
+    with pytest.raises(_lib.FlockError):
+        BatchedActors(2, 12, 256, 128, 2, device=dev).pack_fused()
+    with pytest.raises(_lib.FlockError):
+        BatchedActors(2, 24, 400, 300, 2, device=dev).pack_fused()
