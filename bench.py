@@ -43,6 +43,15 @@ L2_BYTES = 126 * 1024 * 1024
 DT = 0.1
 
 
+def _bf16_peak():
+    """dense bf16 TFLOP/s: measured cuBLAS burst figure of MEASURED_PEAKS.json, else the 2250 nominal"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except Exception:
+        return 2250.0
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -392,6 +401,42 @@ def run_gpu(args, w):
             extra.setdefault("actor_rollout", {})[name] = {
                 "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
                 "policy": f"{N} per-agent MLPs {in_dims}-400-300-2 (LayerNorm, ReLU, tanh) as baddbmm over the agent dim"}
+        # the same closed loop with the fused tcgen05 actor kernel (flock_actor_forward): one policy launch
+        # + one env launch per step, CUDA-graph replay, actions written straight into the env's input
+        actors = BatchedActors(N, in_dims, 400, 300, 2, device=device)
+        actors.pack_fused()
+        acts = torch.empty(E, N, 2, device=device)
+        flops = 2.0 * E * N * (in_dims * 400 + 400 * 300 + 300 * 2)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                actors.forward_fused(env.observation, out=acts)
+                env.step(acts, DT)
+            side.synchronize()
+            reps, inner = 20, 50
+            for label, with_env in (("policy_only", False), ("closed_loop", True)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(inner):
+                        actors.forward_fused(env.observation, out=acts)
+                        if with_env:
+                            env.step(acts, DT)
+                g.replay()
+                side.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(side)
+                for _ in range(reps):
+                    g.replay()
+                ev1.record(side)
+                side.synchronize()
+                t = ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
+                extra["actor_rollout"]["fused_tcgen05_" + label] = {
+                    "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t, "policy_tflops": flops / t / 1e12,
+                    "frac_of_bf16_peak": flops / t / 1e12 / _bf16_peak(),
+                    "policy": "flock_actor_forward: tcgen05.mma bf16 / fp32 accumulate, LayerNorm + ReLU + tanh fused, "
+                              "one launch for all envs and agents"}
+        torch.cuda.current_stream(device).wait_stream(side)
 
     if rank == 0:
         peak, peak_src = _peaks()

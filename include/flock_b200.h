@@ -199,7 +199,7 @@ FLOCK_API int flock_abi_version(void);
 
 /* Fused per-agent actor MLP for the batched rollout ("MADDPG actor rollout", BASELINE configs[2]): the
  * N ActorNetworks of learners/maddpg_shared_critic/ddpg_network.py:85-141 (fc1 -> LayerNorm -> ReLU ->
- * fc2 -> LayerNorm -> ReLU -> mu -> tanh, 400 / 300 hidden units, 2 actions, input_dims <= 16) evaluated
+ * fc2 -> LayerNorm -> ReLU -> mu -> tanh, 400 / 300 hidden units, 2 actions, input_dims <= 14) evaluated
  * for all envs in one launch on the tensor cores (tcgen05, bf16 operands, fp32 accumulation), replacing
  * the per-agent Python loop of learners/maddpg_shared_critic/train_flock.py:114-115.
  *   flock_actor_packed_bytes: size of the packed parameter image for `num_agents` agents.

@@ -11,14 +11,21 @@
 //   * the per-agent weights are pre-packed once (flock_actor_pack) into exactly the shared-memory
 //     image the MMA wants, so they stream from L2 with plain 1-D TMA bulk copies (cp.async.bulk +
 //     mbarrier complete_tx) through an 8-stage ring -- no tensor maps;
-//   * four epilogue warps read the accumulators back with tcgen05.ld (warp w owns TMEM lanes
-//     32w..32w+31 = 32 env rows), apply bias + LayerNorm + ReLU in fp32 and write the layer-2 A operand
-//     back to shared memory as bf16; the 300 -> 2 head and tanh run in the second epilogue on CUDA
-//     cores, so the activations never touch global memory.
+//   * CTAs run as clusters of two (same agent, neighbouring env tiles): each CTA fetches half of every
+//     W2 chunk and multicasts it to both, and tcgen05.commit multicasts the "slot free" arrival, so the
+//     L2 -> SM weight traffic (the bound of the first version) is halved;
+//   * sixteen epilogue warps read the accumulators back with tcgen05.ld (warp w owns TMEM lanes
+//     32(w%4)..+31 = 32 env rows and the column group w/4), apply bias + LayerNorm + ReLU in fp32
+//     (row statistics combined across the four column groups through shared memory) and write the
+//     layer-2 A operand back to shared memory as bf16; the 300 -> 2 head and tanh run in the second
+//     epilogue on CUDA cores, so the activations never touch global memory.
 // Accumulation and LayerNorm are fp32; operands are bf16 (tested against the fp32 PyTorch module).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "flock_launch.h"
 
@@ -27,20 +34,22 @@ namespace actor {
 
 constexpr int kRows = 128;                   // env rows per CTA = UMMA M
 constexpr int kInPad = 16;                   // layer-1 K, one UMMA K step of bf16
+constexpr int kMaxIn = kInPad - 2;           // two K slots carry the bias (hi + lo bf16 parts) against constant-1 inputs
 constexpr int kFc1 = 400, kFc2 = 300, kFc2Pad = 304, kAct = 2;
-constexpr int kSteps2 = kFc1 / 16;           // 25 K steps of layer 2
+constexpr int kK2 = kFc1 + 16;               // layer-2 K: 400 activations + one K step whose first two slots are the bias
+constexpr int kSteps2 = kK2 / 16;            // 26 K steps of layer 2
 constexpr int kStages = 8;                   // W2 ring depth
 constexpr int kW1Bytes = 2 * kFc1 * 16;      // 2 k-groups x 400 rows x 16 B
 constexpr int kChunkBytes = 2 * kFc2Pad * 16;   // one K step of W2: 2 k-groups x 304 rows x 16 B
-// fp32 parameters: b1 g1 be1 [400] | b2 g2 be2 [304] | w3[:,0] w3[:,1] [304] | b3[2] + 2 pad
-constexpr int kParamFloats = 3 * kFc1 + 5 * kFc2Pad + 4;
+// fp32 parameters: g1 be1 [400] | g2 be2 [304] | w3[:,0] w3[:,1] [304] | b3[2] + 2 pad
+constexpr int kParamFloats = 2 * kFc1 + 4 * kFc2Pad + 4;
 constexpr int kParamBytes = kParamFloats * 4;
 constexpr int kBlobBytes = kW1Bytes + kParamBytes + kSteps2 * kChunkBytes;
 static_assert(kParamBytes % 16 == 0 && kBlobBytes % 16 == 0, "bulk copies move 16-byte units");
 
 // shared-memory carve-up (offsets from a 128-byte aligned base)
-constexpr int kOffA2 = 0;                                  // layer-2 A: 50 k-groups x 128 rows x 16 B
-constexpr int kA2Bytes = (kFc1 / 8) * kRows * 16;
+constexpr int kOffA2 = 0;                                  // layer-2 A: 52 k-groups x 128 rows x 16 B
+constexpr int kA2Bytes = (kK2 / 8) * kRows * 16;
 constexpr int kOffA1 = kOffA2 + kA2Bytes;                  // layer-1 A: 2 k-groups x 128 rows x 16 B
 constexpr int kA1Bytes = 2 * kRows * 16;
 constexpr int kOffW1 = kOffA1 + kA1Bytes;
@@ -48,10 +57,17 @@ constexpr int kOffPar = kOffW1 + kW1Bytes;
 constexpr int kOffRing = (kOffPar + kParamBytes + 127) & ~127;
 constexpr int kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr int kNumBars = 2 * kStages + 5;
-constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 128;   // + tmem pointer + alignment slack
+constexpr int kOffRed = kOffBar + kNumBars * 8 + 16;       // + tmem pointer; then row-statistic / head partials
+constexpr int kColGroups = 4;
+constexpr int kRedBytes = 2 * kColGroups * kRows * 8;       // two float2 [4][128] buffers
+constexpr int kSmemBytes = kOffRed + kRedBytes + 128;       // + alignment slack
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-constexpr int kThreads = 160;               // warps 0-3: rows / epilogues, warp 4: TMA + MMA issue
+constexpr int kEpiWarps = 4 * kColGroups;     // warps 0-15: epilogues (TMEM lane quarter = w % 4, column group = w / 4)
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps;           // warp 16: TMEM allocation + MMA issue (one thread)
+constexpr int kTmaWarp = kEpiWarps + 1;       // warp 17: TMA producer (one thread)
+constexpr int kThreads = kEpiThreads + 64;
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +99,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (fully active) warp
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0u;
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -112,6 +155,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {   // same, on `bar` of every CTA in mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when all MMAs issued so far are done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -145,17 +193,30 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// grid = (agents, ceil(E / 128)); obs [E][N][in_dims] fp32, out [E][N][2] fp32
+// column units (16 accumulator columns each) owned by column group g: layer 1 has 25 units, layer 2 has 19
+__device__ __forceinline__ int unit_begin(int units, int g) { return (units * g + kColGroups - 1) / kColGroups; }
+
+// grid = (agents, env tiles rounded up to a multiple of CL), cluster = (1, CL, 1);
+// obs [E][N][in_dims] fp32, out [E][N][2] fp32
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ obs, float* __restrict__ out, int E, int N,
-                   int in_dims) {
+                   int in_dims, long long* __restrict__ dbg, int dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
+    // phase timestamps (FLOCK_ACTOR_TIMING=1, see launch_actor_forward): 16 clock64 slots per CTA
+    long long* const dbg_cta = dbg != nullptr ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+    auto stamp = [&](int slot) {
+        if (dbg_cta != nullptr) dbg_cta[slot] = clock64();
+    };
+    if (threadIdx.x == 0) stamp(0);
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 127u) & ~127u;
+    const uint32_t base = (raw + 127u) & ~127u;     // the same offset in every CTA of the cluster
     uint8_t* sm = smem_raw + (base - raw);
     const int agent = blockIdx.x, tile = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint8_t* blob = blobs + (size_t)agent * kBlobBytes;
+    const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
+    constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
 
     const uint32_t sA2 = base + kOffA2, sA1 = base + kOffA1, sW1 = base + kOffW1, sPar = base + kOffPar;
     const uint32_t sRing = base + kOffRing, sBar = base + kOffBar;
@@ -165,139 +226,205 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                    bar_mma2 = bar_w1 + 32u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + kNumBars * 8);
     const float* par = reinterpret_cast<const float*>(sm + kOffPar);
+    float2* red_stat = reinterpret_cast<float2*>(sm + kOffRed);               // [4][128] (sum, sum of squares)
+    float2* red_head = red_stat + kColGroups * kRows;                          // [4][128] (o0, o1)
 
-    if (warp == 4) {
+    // epilogue-thread coordinates; the observation loads are issued before the set-up so that their
+    // DRAM latency overlaps the TMEM allocation and the barrier initialisation
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane;                     // TMEM lane
+    const int env = tile * kRows + row;
+    const bool valid = env < E;
+    float xin[kInPad];
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) xin[i] = 0.0f;
+    if (warp < 4 && valid) {
+        const float* src = obs + ((size_t)env * N + agent) * in_dims;
+        if (in_dims == 12) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            const float4 a = s4[0], b = s4[1], c = s4[2];
+            xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w;
+            xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
+            xin[8] = c.x; xin[9] = c.y; xin[10] = c.z; xin[11] = c.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kMaxIn; ++i)
+                if (i < in_dims) xin[i] = src[i];
+        }
+    }
+
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) {
-                mbar_init(bar_full(s), 1);
-                mbar_init(bar_empty(s), 1);
-            }
-            mbar_init(bar_w1, 1);
-            mbar_init(bar_a1, kRows);
-            mbar_init(bar_mma1, 1);
-            mbar_init(bar_a2, kRows);
-            mbar_init(bar_mma2, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == kTmaWarp && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), CL);          // one tcgen05.commit arrival per CTA of the cluster
         }
+        mbar_init(bar_w1, 1);
+        mbar_init(bar_a1, kRows);
+        mbar_init(bar_mma1, 1);
+        mbar_init(bar_a2, kEpiThreads);
+        mbar_init(bar_mma2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any multicast copy / arrival targets them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x == 0) stamp(1);
 
-    if (warp == 4) {
-        if (lane == 0) {
-            // ---- producer + MMA issuer (one thread) ----
+    // The two single-thread roles run warp-uniformly (all 32 lanes execute the control flow and the
+    // address arithmetic, so it stays in uniform registers); only the issuing instructions are
+    // predicated on one elected lane. Under `if (lane == 0)` every descriptor went through a
+    // per-thread -> uniform register waterfall and the issue loop, not the tensor core, set the pace
+    // (316 cycles per K step instead of 152).
+    if (warp == kTmaWarp) {
+        // ---- TMA producer: W1 + parameters, then the W2 chunks through the ring ----
+        const bool leader = elect_one();
+        if (leader) {
             mbar_expect_tx(bar_w1, kW1Bytes + kParamBytes);
             bulk_g2s(sW1, blob, kW1Bytes, bar_w1);
             bulk_g2s(sPar, blob + kW1Bytes, kParamBytes, bar_w1);
-            const uint8_t* w2 = blob + kW1Bytes + kParamBytes;
-            for (int c = 0; c < kStages; ++c) {
-                mbar_expect_tx(bar_full(c), kChunkBytes);
-                bulk_g2s(sRing + c * kChunkBytes, w2 + (size_t)c * kChunkBytes, kChunkBytes, bar_full(c));
+        }
+        const uint8_t* w2 = blob + kW1Bytes + kParamBytes;
+        // chunk c -> ring slot c % kStages of EVERY CTA of the cluster: this CTA fetches its 1/CL share
+        constexpr uint32_t kShare = kChunkBytes / CL;
+        static_assert(kShare % 16 == 0, "share must be a 16-byte multiple");
+        const int nchunks = (dbg_mode & 1) ? kStages : kSteps2;     // (timing experiment 1: no weight streaming)
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+            const int slot = c % kStages;
+            if (c >= kStages) mbar_wait(bar_empty(slot), (uint32_t)(c / kStages - 1) & 1u);   // MMAs of chunk c-8 are done
+            if (leader) {
+                mbar_expect_tx(bar_full(slot), kChunkBytes);
+                const uint32_t dst = sRing + slot * kChunkBytes + crank * kShare;
+                const uint8_t* src = w2 + (size_t)c * kChunkBytes + crank * kShare;
+                if (CL > 1) bulk_g2s_mc(dst, src, kShare, bar_full(slot), kAllCtas);
+                else bulk_g2s(dst, src, kShare, bar_full(slot));
             }
-            // layer 1: [128 x 16] x [16 x 400] -> TMEM columns [0, 400)
-            mbar_wait(bar_a1, 0);
-            mbar_wait(bar_w1, 0);
-            tc_fence_after();
-            {
-                const uint64_t da = umma_desc(sA1, kRows * 16, 128);
-                umma_bf16(tmem + 0, da, umma_desc(sW1, kFc1 * 16, 128), umma_idesc(kRows, 256), 0u);
-                umma_bf16(tmem + 256, da, umma_desc(sW1 + 256 * 16, kFc1 * 16, 128), umma_idesc(kRows, 144), 0u);
-            }
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp) {
+        // ---- MMA issuer ----
+        const bool leader = elect_one();
+        // layer 1: [128 x 16] x [16 x 400] -> TMEM columns [0, 400)
+        mbar_wait(bar_a1, 0);
+        if (lane == 0) stamp(8);
+        mbar_wait(bar_w1, 0);
+        if (lane == 0) stamp(9);
+        tc_fence_after();
+        if (leader) {
+            const uint64_t da = umma_desc(sA1, kRows * 16, 128);
+            umma_bf16(tmem + 0, da, umma_desc(sW1, kFc1 * 16, 128), umma_idesc(kRows, 256), 0u);
+            umma_bf16(tmem + 256, da, umma_desc(sW1 + 256 * 16, kFc1 * 16, 128), umma_idesc(kRows, 144), 0u);
             umma_commit(bar_mma1);
-            // layer 2: [128 x 400] x [400 x 304] -> TMEM columns [0, 304) (layer-1 accumulators are dead by then)
-            mbar_wait(bar_a2, 0);
+        }
+        __syncwarp();
+        // layer 2: [128 x 416] x [416 x 304] -> TMEM columns [0, 304) (layer-1 accumulators are dead by then)
+        mbar_wait(bar_a2, 0);
+        if (lane == 0) stamp(10);
+        tc_fence_after();
+        const uint64_t da0 = umma_desc(sA2, kRows * 16, 128);
+        const uint64_t db0 = umma_desc(sRing, kFc2Pad * 16, 128);
+        const int var = dbg_mode >> 2;   // timing experiments (results invalid): see FLOCK_ACTOR_EXPERIMENT
+#pragma unroll
+        for (int s = 0; s < kSteps2; ++s) {
+            constexpr int kAStep = (2 * kRows * 16) >> 4, kBSlot = kChunkBytes >> 4, kBHalf = (160 * 16) >> 4;   // 16-byte units
+            const int st = s % kStages;
+            if (!(dbg_mode & 1) || s < kStages) mbar_wait(bar_full(st), (uint32_t)(s / kStages) & 1u);
             tc_fence_after();
-            for (int s = 0; s < kSteps2; ++s) {
-                const int st = s % kStages;
-                mbar_wait(bar_full(st), (uint32_t)(s / kStages) & 1u);
-                tc_fence_after();
-                const uint64_t da = umma_desc(sA2 + s * (2 * kRows * 16), kRows * 16, 128);
-                const uint32_t sb = sRing + st * kChunkBytes;
-                umma_bf16(tmem + 0, da, umma_desc(sb, kFc2Pad * 16, 128), umma_idesc(kRows, 160), s > 0 ? 1u : 0u);
-                umma_bf16(tmem + 160, da, umma_desc(sb + 160 * 16, kFc2Pad * 16, 128), umma_idesc(kRows, 144), s > 0 ? 1u : 0u);
-                umma_commit(bar_empty(st));
-                // refill the slot of chunk s-2 (its MMAs are normally done by now) with chunk s+6
-                const int r = s - 2;
-                if (r >= 0 && r + kStages < kSteps2) {
-                    const int rs = r % kStages;
-                    mbar_wait(bar_empty(rs), (uint32_t)(r / kStages) & 1u);
-                    mbar_expect_tx(bar_full(rs), kChunkBytes);
-                    bulk_g2s(sRing + rs * kChunkBytes, w2 + (size_t)(r + kStages) * kChunkBytes, kChunkBytes, bar_full(rs));
+            if (leader) {
+                const uint64_t da = da0 + (uint64_t)(s * kAStep);          // start-address field: no carry out of 14 bits
+                const uint64_t db = db0 + (uint64_t)(st * kBSlot);
+                const uint32_t acc = s > 0 ? 1u : 0u;
+                if (!(dbg_mode & 2)) {
+                    if (var == 3) {
+                        umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 256), acc);
+                        umma_bf16(tmem + 256, da, db + (256 * 16 >> 4), umma_idesc(kRows, 48), acc);
+                    } else if (var == 4) {
+                        umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 256), acc);
+                    } else {
+                        umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 160), acc);
+                        if (var != 1) umma_bf16(tmem + 160, da, db + kBHalf, umma_idesc(kRows, 144), acc);
+                    }
                 }
+                if (CL > 1) umma_commit_mc(bar_empty(st), kAllCtas);   // slot st is free once EVERY CTA has said so
+                else umma_commit(bar_empty(st));
             }
-            umma_commit(bar_mma2);
+            __syncwarp();
         }
+        if (leader) umma_commit(bar_mma2);
+        __syncwarp();
+        if (lane == 0) stamp(11);
     } else {
-        // ---- rows: one thread per env ----
-        const int row = threadIdx.x;                       // 0..127 = TMEM lane
-        const int env = tile * kRows + row;
-        const bool valid = env < E;
-        float xin[kInPad];
+        // ---- epilogue warps: thread = (env row, column group) ----
+        if (cg == 0) {
+            // this row's observation = the layer-1 A operand; the two slots after the inputs are the
+            // constant 1 that multiplies the bias rows of the packed W1
 #pragma unroll
-        for (int i = 0; i < kInPad; ++i) xin[i] = 0.0f;
-        if (valid) {
-            const float* src = obs + ((size_t)env * N + agent) * in_dims;
-            if (in_dims == 12) {
-                const float4* s4 = reinterpret_cast<const float4*>(src);
-                const float4 a = s4[0], b = s4[1], c = s4[2];
-                xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w;
-                xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
-                xin[8] = c.x; xin[9] = c.y; xin[10] = c.z; xin[11] = c.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < kInPad; ++i)
-                    if (i < in_dims) xin[i] = src[i];
-            }
+            for (int i = 0; i < kInPad; ++i)
+                if (i == in_dims || i == in_dims + 1) xin[i] = 1.0f;
+            sts128(sA1 + row * 16, pack_bf16(xin[0], xin[1]), pack_bf16(xin[2], xin[3]), pack_bf16(xin[4], xin[5]),
+                   pack_bf16(xin[6], xin[7]));
+            sts128(sA1 + kRows * 16 + row * 16, pack_bf16(xin[8], xin[9]), pack_bf16(xin[10], xin[11]),
+                   pack_bf16(xin[12], xin[13]), pack_bf16(xin[14], xin[15]));
+            fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(bar_a1);
+            if (threadIdx.x == 0) stamp(2);
+        } else if (cg == 1) {
+            // the bias K step of layer 2: A2[:, 400] = A2[:, 401] = 1, A2[:, 402..415] = 0
+            sts128(sA2 + (kFc1 / 8) * (kRows * 16) + row * 16, pack_bf16(1.0f, 1.0f), 0u, 0u, 0u);
+            sts128(sA2 + (kFc1 / 8 + 1) * (kRows * 16) + row * 16, 0u, 0u, 0u, 0u);
         }
-        sts128(sA1 + row * 16, pack_bf16(xin[0], xin[1]), pack_bf16(xin[2], xin[3]), pack_bf16(xin[4], xin[5]),
-               pack_bf16(xin[6], xin[7]));
-        sts128(sA1 + kRows * 16 + row * 16, pack_bf16(xin[8], xin[9]), pack_bf16(xin[10], xin[11]),
-               pack_bf16(xin[12], xin[13]), pack_bf16(xin[14], xin[15]));
-        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(bar_a1);
 
         mbar_wait(bar_w1, 0);           // fp32 parameters have landed
-        const float* b1 = par;
-        const float* g1 = par + kFc1;
-        const float* be1 = par + 2 * kFc1;
-        const float* b2 = par + 3 * kFc1;
-        const float* g2 = b2 + kFc2Pad;
-        const float* be2 = b2 + 2 * kFc2Pad;
-        const float* w3a = b2 + 3 * kFc2Pad;
-        const float* w3b = b2 + 4 * kFc2Pad;
-        const float* b3 = b2 + 5 * kFc2Pad;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const float* g1 = par;
+        const float* be1 = par + kFc1;
+        const float* g2 = par + 2 * kFc1;
+        const float* be2 = g2 + kFc2Pad;
+        const float* w3a = g2 + 2 * kFc2Pad;
+        const float* w3b = g2 + 3 * kFc2Pad;
+        const float* b3 = g2 + 4 * kFc2Pad;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
 
-        // ---- epilogue 1: bias + LayerNorm(400) + ReLU -> bf16 A operand of layer 2 ----
+        // ---- epilogue 1: LayerNorm(400) + ReLU -> bf16 A operand of layer 2 (the bias came with the MMA) ----
+        const int c1b = unit_begin(kFc1 / 16, cg) * 16, c1e = unit_begin(kFc1 / 16, cg + 1) * 16;
         mbar_wait(bar_mma1, 0);
         tc_fence_after();
+        if (threadIdx.x == 0) stamp(3);
         float sum = 0.0f, sq = 0.0f;
-        for (int c0 = 0; c0 < kFc1; c0 += 16) {
+        for (int c0 = c1b; c0 < c1e; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float t = v[i] + b1[c0 + i];
-                sum += t;
-                sq = fmaf(t, t, sq);
+                sum += v[i];
+                sq = fmaf(v[i], v[i], sq);
             }
+        }
+        red_stat[cg * kRows + row] = make_float2(sum, sq);
+        epi_sync();
+        if (threadIdx.x == 0) stamp(4);
+        sum = 0.0f;
+        sq = 0.0f;
+#pragma unroll
+        for (int g = 0; g < kColGroups; ++g) {
+            const float2 pr = red_stat[g * kRows + row];
+            sum += pr.x;
+            sq += pr.y;
         }
         float mean = sum * (1.0f / kFc1);
         float rstd = rsqrtf(fmaxf(sq * (1.0f / kFc1) - mean * mean, 0.0f) + 1.0e-5f);
-        for (int c0 = 0; c0 < kFc1; c0 += 16) {
+        float nmr = -mean * rstd;
+        for (int c0 = c1b; c0 < c1e; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float t = (v[i] + b1[c0 + i] - mean) * rstd;
-                v[i] = fmaxf(fmaf(t, g1[c0 + i], be1[c0 + i]), 0.0f);
-            }
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(fmaf(v[i], rstd, nmr), g1[c0 + i], be1[c0 + i]), 0.0f);
             const uint32_t dst = sA2 + (c0 >> 3) * (kRows * 16) + row * 16;
             sts128(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             sts128(dst + kRows * 16, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
@@ -306,48 +433,75 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         fence_proxy_async();
         tc_fence_before();              // our tcgen05.ld of columns [0,400) precede the layer-2 MMAs that overwrite them
         mbar_arrive(bar_a2);
+        if (threadIdx.x == 0) stamp(5);
 
-        // ---- epilogue 2: bias + LayerNorm(300) + ReLU, mu head (300 -> 2), tanh ----
+        // ---- epilogue 2: LayerNorm(300) + ReLU, mu head (300 -> 2), tanh ----
+        // (the four padded columns 300..303 are exactly 0: zero weights, zero bias)
+        const int c2b = unit_begin(kFc2Pad / 16, cg) * 16, c2e = unit_begin(kFc2Pad / 16, cg + 1) * 16;
         mbar_wait(bar_mma2, 0);
         tc_fence_after();
+        if (threadIdx.x == 0) stamp(6);
         sum = 0.0f;
         sq = 0.0f;
-        for (int c0 = 0; c0 < kFc2Pad; c0 += 16) {
+        for (int c0 = c2b; c0 < c2e; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float t = (c0 + i < kFc2) ? v[i] + b2[c0 + i] : 0.0f;
-                sum += t;
-                sq = fmaf(t, t, sq);
+                sum += v[i];
+                sq = fmaf(v[i], v[i], sq);
             }
+        }
+        red_stat[cg * kRows + row] = make_float2(sum, sq);   // (all epilogue-1 reads happened before bar_a2 completed)
+        epi_sync();
+        sum = 0.0f;
+        sq = 0.0f;
+#pragma unroll
+        for (int g = 0; g < kColGroups; ++g) {
+            const float2 pr = red_stat[g * kRows + row];
+            sum += pr.x;
+            sq += pr.y;
         }
         mean = sum * (1.0f / kFc2);
         rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean * mean, 0.0f) + 1.0e-5f);
+        nmr = -mean * rstd;
         float o0 = 0.0f, o1 = 0.0f;
-        for (int c0 = 0; c0 < kFc2Pad; c0 += 16) {
+        for (int c0 = c2b; c0 < c2e; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float t = (v[i] + b2[c0 + i] - mean) * rstd;
-                const float yv = fmaxf(fmaf(t, g2[c0 + i], be2[c0 + i]), 0.0f);   // padded columns: w3 = 0
+                // padded columns: g2 = be2 = w3 = 0
+                const float yv = fmaxf(fmaf(fmaf(v[i], rstd, nmr), g2[c0 + i], be2[c0 + i]), 0.0f);
                 o0 = fmaf(yv, w3a[c0 + i], o0);
                 o1 = fmaf(yv, w3b[c0 + i], o1);
             }
         }
-        if (valid) {
+        red_head[cg * kRows + row] = make_float2(o0, o1);
+        epi_sync();
+        if (cg == 0 && valid) {
+            o0 = 0.0f;
+            o1 = 0.0f;
+#pragma unroll
+            for (int g = 0; g < kColGroups; ++g) {
+                const float2 pr = red_head[g * kRows + row];
+                o0 += pr.x;
+                o1 += pr.y;
+            }
             float2 a;
             a.x = tanhf(o0 + b3[0]);
             a.y = tanhf(o1 + b3[1]);
             reinterpret_cast<float2*>(out)[(size_t)env * N + agent] = a;
         }
     }
+    if (threadIdx.x == 0) stamp(7);
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into this CTA
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+        if (lane == 0) stamp(12);
     }
 }
 
@@ -358,6 +512,8 @@ struct PackArgs {
     int agents, in_dims;
 };
 
+__device__ __forceinline__ float bf16_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs) {
     const int units = kBlobBytes / 16;
     const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -365,12 +521,14 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
     const int ag = (int)(gid / units);
     int u = (int)(gid % units);
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (u < kW1Bytes / 16) {                       // W1 image: [k-group][n] x 8 bf16
+    if (u < kW1Bytes / 16) {                       // W1 image: [k-group][n] x 8 bf16; K slots in_dims, in_dims+1 = bias hi, lo
         const int kg = u / kFc1, n = u % kFc1;
         float v[8];
         for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            v[j] = k < a.in_dims ? a.w1[((size_t)ag * a.in_dims + k) * kFc1 + n] : 0.0f;
+            const float bias = a.b1[(size_t)ag * kFc1 + n];
+            v[j] = k < a.in_dims ? a.w1[((size_t)ag * a.in_dims + k) * kFc1 + n]
+                 : (k == a.in_dims ? bias : (k == a.in_dims + 1 ? bias - bf16_hi(bias) : 0.0f));
         }
         o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     } else if (u < (kW1Bytes + kParamBytes) / 16) {   // fp32 parameters
@@ -379,17 +537,17 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
         for (int j = 0; j < 4; ++j) {
             int f = f0 + j;
             float x = 0.0f;
-            if (f < 3 * kFc1) {
-                const float* src = f < kFc1 ? a.b1 : (f < 2 * kFc1 ? a.g1 : a.be1);
+            if (f < 2 * kFc1) {
+                const float* src = f < kFc1 ? a.g1 : a.be1;
                 x = src[(size_t)ag * kFc1 + f % kFc1];
             } else {
-                f -= 3 * kFc1;
+                f -= 2 * kFc1;
                 const int which = f / kFc2Pad, c = f % kFc2Pad;
-                if (which < 3) {
-                    const float* src = which == 0 ? a.b2 : (which == 1 ? a.g2 : a.be2);
+                if (which < 2) {
+                    const float* src = which == 0 ? a.g2 : a.be2;
                     x = c < kFc2 ? src[(size_t)ag * kFc2 + c] : 0.0f;
-                } else if (which < 5) {
-                    x = c < kFc2 ? a.w3[((size_t)ag * kFc2 + c) * kAct + (which - 3)] : 0.0f;
+                } else if (which < 4) {
+                    x = c < kFc2 ? a.w3[((size_t)ag * kFc2 + c) * kAct + (which - 2)] : 0.0f;
                 } else {
                     x = c < kAct ? a.b3[(size_t)ag * kAct + c] : 0.0f;
                 }
@@ -397,14 +555,20 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
             v[j] = x;
         }
         o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-    } else {                                        // W2 images: [K step][k-group][n] x 8 bf16
+    } else {                                        // W2 images: [K step][k-group][n] x 8 bf16; K slots 400, 401 = bias hi, lo
         u -= (kW1Bytes + kParamBytes) / 16;
         const int s = u / (2 * kFc2Pad), rem = u % (2 * kFc2Pad);
         const int kg = rem / kFc2Pad, n = rem % kFc2Pad;
         float v[8];
         for (int j = 0; j < 8; ++j) {
             const int k = s * 16 + kg * 8 + j;
-            v[j] = n < kFc2 ? a.w2[((size_t)ag * kFc1 + k) * kFc2 + n] : 0.0f;
+            float x = 0.0f;
+            if (n < kFc2) {
+                if (k < kFc1) x = a.w2[((size_t)ag * kFc1 + k) * kFc2 + n];
+                else if (k == kFc1) x = a.b2[(size_t)ag * kFc2 + n];
+                else if (k == kFc1 + 1) x = a.b2[(size_t)ag * kFc2 + n] - bf16_hi(a.b2[(size_t)ag * kFc2 + n]);
+            }
+            v[j] = x;
         }
         o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
@@ -414,7 +578,7 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
 }  // namespace actor
 
 size_t actor_blob_bytes() { return (size_t)actor::kBlobBytes; }
-int actor_max_in_dims() { return actor::kInPad; }
+int actor_max_in_dims() { return actor::kMaxIn; }
 void actor_dims(int* fc1, int* fc2, int* n_actions) {
     *fc1 = actor::kFc1;
     *fc2 = actor::kFc2;
@@ -428,15 +592,72 @@ cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs,
     return cudaGetLastError();
 }
 
+template <int CL>
+static cudaError_t launch_actor_forward_cl(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
+                                           cudaStream_t s) {
+    static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel<CL>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, actor::kSmemBytes);
+    if (configured != cudaSuccess) return configured;
+    const int tiles = (E + actor::kRows - 1) / actor::kRows;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)N, (unsigned)((tiles + CL - 1) / CL * CL));   // surplus tiles are fully masked
+    cfg.blockDim = dim3(actor::kThreads);
+    cfg.dynamicSmemBytes = actor::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = CL;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // FLOCK_ACTOR_TIMING=1 (developer knob): the first launch records clock64 at the phase boundaries of
+    // every CTA, synchronises and prints the mean phase lengths to stderr
+    static bool timing = getenv("FLOCK_ACTOR_TIMING") != nullptr;
+    static const int dbg_mode = getenv("FLOCK_ACTOR_EXPERIMENT") ? atoi(getenv("FLOCK_ACTOR_EXPERIMENT")) : 0;   // results invalid if != 0
+    long long* dbg = nullptr;
+    if (timing) {
+        timing = false;
+        const size_t ctas = (size_t)cfg.gridDim.x * cfg.gridDim.y;
+        if (cudaMalloc(&dbg, ctas * 16 * sizeof(long long)) == cudaSuccess) {
+            cudaMemsetAsync(dbg, 0, ctas * 16 * sizeof(long long), s);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, actor::flock_actor_kernel<CL>, static_cast<const uint8_t*>(blobs), obs,
+                                               actions, E, N, in_dims, dbg, dbg_mode);
+            cudaStreamSynchronize(s);
+            long long* h = static_cast<long long*>(malloc(ctas * 16 * sizeof(long long)));
+            cudaMemcpy(h, dbg, ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+            static const char* names[12] = {"setup (alloc, barrier init, sync)", "obs -> A1", "wait MMA1", "epilogue-1 pass 1 + sync",
+                                            "epilogue-1 pass 2 -> A2", "wait MMA2", "epilogue 2", "teardown sync + dealloc",
+                                            "[mma thread] start -> A1 ready", "[mma thread] W1 ready", "[mma thread] -> A2 ready",
+                                            "[mma thread] layer-2 issue loop"};
+            static const int from[12] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 8, 9, 10}, to[12] = {1, 2, 3, 4, 5, 6, 7, 12, 8, 9, 10, 11};
+            fprintf(stderr, "flock_actor_kernel<%d> phase means over %zu CTAs (SM clocks):\n", CL, ctas);
+            for (int ph = 0; ph < 12; ++ph) {
+                double acc = 0;
+                for (size_t c = 0; c < ctas; ++c) acc += (double)(h[c * 16 + to[ph]] - h[c * 16 + from[ph]]);
+                fprintf(stderr, "  %-38s %9.0f\n", names[ph], acc / ctas);
+            }
+            double tot = 0;
+            for (size_t c = 0; c < ctas; ++c) tot += (double)(h[c * 16 + 12] - h[c * 16 + 0]);
+            fprintf(stderr, "  %-38s %9.0f\n", "CTA total", tot / ctas);
+            free(h);
+            cudaFree(dbg);
+            return e;
+        }
+    }
+    return cudaLaunchKernelEx(&cfg, actor::flock_actor_kernel<CL>, static_cast<const uint8_t*>(blobs), obs, actions, E, N,
+                              in_dims, dbg, dbg_mode);
+}
+
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
                                  cudaStream_t s) {
-    static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         actor::kSmemBytes);
-    if (configured != cudaSuccess) return configured;
-    const dim3 grid((unsigned)N, (unsigned)((E + actor::kRows - 1) / actor::kRows));
-    actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(static_cast<const uint8_t*>(blobs), obs, actions,
-                                                                            E, N, in_dims);
-    return cudaGetLastError();
+    // FLOCK_ACTOR_CLUSTER=1 disables the cluster-of-two weight multicast (A/B knob)
+    static const int cl = [] {
+        const char* v = getenv("FLOCK_ACTOR_CLUSTER");
+        return (v != nullptr && v[0] == '1') ? 1 : 2;
+    }();
+    if (cl == 2 && E > actor::kRows) return launch_actor_forward_cl<2>(blobs, obs, actions, E, N, in_dims, s);
+    return launch_actor_forward_cl<1>(blobs, obs, actions, E, N, in_dims, s);
 }
 
 }  // namespace flock
