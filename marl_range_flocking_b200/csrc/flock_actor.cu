@@ -10,10 +10,13 @@
 //     no-swizzle K-major canonical layout (8-row x 16-byte core matrices);
 //   * the per-agent weights are pre-packed once (flock_actor_pack) into exactly the shared-memory
 //     image the MMA wants, so they stream from L2 with plain 1-D TMA bulk copies (cp.async.bulk +
-//     mbarrier complete_tx) through an 8-stage ring -- no tensor maps;
-//   * CTAs run as clusters of two (same agent, neighbouring env tiles): each CTA fetches half of every
-//     W2 chunk and multicasts it to both, and tcgen05.commit multicasts the "slot free" arrival, so the
-//     L2 -> SM weight traffic (the bound of the first version) is halved;
+//     mbarrier complete_tx) through a 4-slot ring of two-K-step chunks -- no tensor maps;
+//   * optional (FLOCK_ACTOR_CLUSTER=2): CTAs run as clusters of two (same agent, neighbouring env tiles),
+//     each CTA fetches half of every W2 chunk and multicasts it to both, tcgen05.commit multicasts the
+//     "slot free" arrival -- halves the L2 -> SM weight traffic, but the layer is not L2-bound (see below);
+//   * one warp issues the TMA copies and one the MMAs, both warp-uniformly with a single elected lane
+//     (descriptors stay in uniform registers); biases ride in the MMAs as two extra K slots (hi + lo
+//     bf16 parts against constant-1 inputs);
 //   * sixteen epilogue warps read the accumulators back with tcgen05.ld (warp w owns TMEM lanes
 //     32(w%4)..+31 = 32 env rows and the column group w/4), apply bias + LayerNorm + ReLU in fp32
 //     (row statistics combined across the four column groups through shared memory) and write the
@@ -38,13 +41,17 @@ constexpr int kMaxIn = kInPad - 2;           // two K slots carry the bias (hi +
 constexpr int kFc1 = 400, kFc2 = 300, kFc2Pad = 304, kAct = 2;
 constexpr int kK2 = kFc1 + 16;               // layer-2 K: 400 activations + one K step whose first two slots are the bias
 constexpr int kSteps2 = kK2 / 16;            // 26 K steps of layer 2
-constexpr int kStages = 8;                   // W2 ring depth
 constexpr int kW1Bytes = 2 * kFc1 * 16;      // 2 k-groups x 400 rows x 16 B
-constexpr int kChunkBytes = 2 * kFc2Pad * 16;   // one K step of W2: 2 k-groups x 304 rows x 16 B
+constexpr int kStepBytes = 2 * kFc2Pad * 16; // one K step of W2: 2 k-groups x 304 rows x 16 B
+constexpr int kStepsPerChunk = 2;            // K steps per ring slot: one barrier round trip + commit per 4 MMAs
+constexpr int kChunks = kSteps2 / kStepsPerChunk;
+constexpr int kChunkBytes = kStepsPerChunk * kStepBytes;
+constexpr int kStages = 4;                   // W2 ring depth (chunks)
+static_assert(kSteps2 % kStepsPerChunk == 0, "whole chunks");
 // fp32 parameters: g1 be1 [400] | g2 be2 [304] | w3[:,0] w3[:,1] [304] | b3[2] + 2 pad
 constexpr int kParamFloats = 2 * kFc1 + 4 * kFc2Pad + 4;
 constexpr int kParamBytes = kParamFloats * 4;
-constexpr int kBlobBytes = kW1Bytes + kParamBytes + kSteps2 * kChunkBytes;
+constexpr int kBlobBytes = kW1Bytes + kParamBytes + kSteps2 * kStepBytes;
 static_assert(kParamBytes % 16 == 0 && kBlobBytes % 16 == 0, "bulk copies move 16-byte units");
 
 // shared-memory carve-up (offsets from a 128-byte aligned base)
@@ -165,23 +172,44 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 16 consecutive fp32 accumulator columns of this thread's TMEM lane (warp-collective)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane (warp-collective), split into
+// issue and wait so that the next load is in flight while the current columns are processed
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    // the wait takes the registers as in/out operands so that no use can be scheduled above it
+}
+// waits for ALL outstanding tcgen05.ld of the thread; takes the registers as in/out operands so that
+// no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                  :
                  : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// for (c0 = cb; c0 < ce; c0 += 16) f(c0, the 16 columns at c0), with the load of the next unit overlapped
+template <typename F>
+__device__ __forceinline__ void for_each_unit(uint32_t trow, int cb, int ce, F&& f) {
+    uint32_t r0[16], r1[16];
+    if (cb >= ce) return;
+    tmem_ld16_issue(trow + cb, r0);
+    int c0 = cb;
+    while (true) {
+        tmem_ld16_wait(r0);
+        if (c0 + 16 < ce) tmem_ld16_issue(trow + c0 + 16, r1);
+        f(c0, r0);
+        c0 += 16;
+        if (c0 >= ce) break;
+        tmem_ld16_wait(r1);
+        if (c0 + 16 < ce) tmem_ld16_issue(trow + c0 + 16, r0);
+        f(c0, r1);
+        c0 += 16;
+        if (c0 >= ce) break;
+    }
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -294,11 +322,11 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         // chunk c -> ring slot c % kStages of EVERY CTA of the cluster: this CTA fetches its 1/CL share
         constexpr uint32_t kShare = kChunkBytes / CL;
         static_assert(kShare % 16 == 0, "share must be a 16-byte multiple");
-        const int nchunks = (dbg_mode & 1) ? kStages : kSteps2;     // (timing experiment 1: no weight streaming)
+        const int nchunks = (dbg_mode & 1) ? kStages : kChunks;     // (timing experiment 1: no weight streaming)
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
             const int slot = c % kStages;
-            if (c >= kStages) mbar_wait(bar_empty(slot), (uint32_t)(c / kStages - 1) & 1u);   // MMAs of chunk c-8 are done
+            if (c >= kStages) mbar_wait(bar_empty(slot), (uint32_t)(c / kStages - 1) & 1u);   // MMAs of the chunk that used the slot are done
             if (leader) {
                 mbar_expect_tx(bar_full(slot), kChunkBytes);
                 const uint32_t dst = sRing + slot * kChunkBytes + crank * kShare;
@@ -330,26 +358,23 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         tc_fence_after();
         const uint64_t da0 = umma_desc(sA2, kRows * 16, 128);
         const uint64_t db0 = umma_desc(sRing, kFc2Pad * 16, 128);
-        const int var = dbg_mode >> 2;   // timing experiments (results invalid): see FLOCK_ACTOR_EXPERIMENT
 #pragma unroll
-        for (int s = 0; s < kSteps2; ++s) {
-            constexpr int kAStep = (2 * kRows * 16) >> 4, kBSlot = kChunkBytes >> 4, kBHalf = (160 * 16) >> 4;   // 16-byte units
-            const int st = s % kStages;
-            if (!(dbg_mode & 1) || s < kStages) mbar_wait(bar_full(st), (uint32_t)(s / kStages) & 1u);
+        for (int c = 0; c < kChunks; ++c) {
+            constexpr int kAStep = (2 * kRows * 16) >> 4, kBSlot = kChunkBytes >> 4,
+                          kBStep = kStepBytes >> 4;   // 16-byte units of the descriptor start-address field
+            const int st = c % kStages;
+            if (!(dbg_mode & 1) || c < kStages) mbar_wait(bar_full(st), (uint32_t)(c / kStages) & 1u);
             tc_fence_after();
             if (leader) {
-                const uint64_t da = da0 + (uint64_t)(s * kAStep);          // start-address field: no carry out of 14 bits
-                const uint64_t db = db0 + (uint64_t)(st * kBSlot);
-                const uint32_t acc = s > 0 ? 1u : 0u;
-                if (!(dbg_mode & 2)) {
-                    if (var == 3) {
+#pragma unroll
+                for (int j = 0; j < kStepsPerChunk; ++j) {
+                    const int s = c * kStepsPerChunk + j;
+                    const uint64_t da = da0 + (uint64_t)(s * kAStep);          // no carry out of the 14-bit field
+                    const uint64_t db = db0 + (uint64_t)(st * kBSlot + j * kBStep);
+                    const uint32_t acc = s > 0 ? 1u : 0u;
+                    if (!(dbg_mode & 2)) {   // N = 256 + 48 (measured faster than 160 + 144: 171 vs 194 cycles per K step)
                         umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 256), acc);
-                        umma_bf16(tmem + 256, da, db + (256 * 16 >> 4), umma_idesc(kRows, 48), acc);
-                    } else if (var == 4) {
-                        umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 256), acc);
-                    } else {
-                        umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 160), acc);
-                        if (var != 1) umma_bf16(tmem + 160, da, db + kBHalf, umma_idesc(kRows, 144), acc);
+                        umma_bf16(tmem + 256, da, db + (256 * 16 >> 4), umma_idesc(kRows, kFc2Pad - 256), acc);
                     }
                 }
                 if (CL > 1) umma_commit_mc(bar_empty(st), kAllCtas);   // slot st is free once EVERY CTA has said so
@@ -397,15 +422,15 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         tc_fence_after();
         if (threadIdx.x == 0) stamp(3);
         float sum = 0.0f, sq = 0.0f;
-        for (int c0 = c1b; c0 < c1e; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
+        auto stats = [&](int, const uint32_t (&r)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                sum += v[i];
-                sq = fmaf(v[i], v[i], sq);
+                const float v = __uint_as_float(r[i]);
+                sum += v;
+                sq = fmaf(v, v, sq);
             }
-        }
+        };
+        for_each_unit(trow, c1b, c1e, stats);
         red_stat[cg * kRows + row] = make_float2(sum, sq);
         epi_sync();
         if (threadIdx.x == 0) stamp(4);
@@ -420,16 +445,16 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         float mean = sum * (1.0f / kFc1);
         float rstd = rsqrtf(fmaxf(sq * (1.0f / kFc1) - mean * mean, 0.0f) + 1.0e-5f);
         float nmr = -mean * rstd;
-        for (int c0 = c1b; c0 < c1e; c0 += 16) {
+        for_each_unit(trow, c1b, c1e, [&](int c0, const uint32_t (&r)[16]) {
             float v[16];
-            tmem_ld16(trow + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(fmaf(v[i], rstd, nmr), g1[c0 + i], be1[c0 + i]), 0.0f);
+            for (int i = 0; i < 16; ++i)
+                v[i] = fmaxf(fmaf(fmaf(__uint_as_float(r[i]), rstd, nmr), g1[c0 + i], be1[c0 + i]), 0.0f);
             const uint32_t dst = sA2 + (c0 >> 3) * (kRows * 16) + row * 16;
             sts128(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             sts128(dst + kRows * 16, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
                    pack_bf16(v[14], v[15]));
-        }
+        });
         fence_proxy_async();
         tc_fence_before();              // our tcgen05.ld of columns [0,400) precede the layer-2 MMAs that overwrite them
         mbar_arrive(bar_a2);
@@ -443,15 +468,7 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         if (threadIdx.x == 0) stamp(6);
         sum = 0.0f;
         sq = 0.0f;
-        for (int c0 = c2b; c0 < c2e; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                sum += v[i];
-                sq = fmaf(v[i], v[i], sq);
-            }
-        }
+        for_each_unit(trow, c2b, c2e, stats);
         red_stat[cg * kRows + row] = make_float2(sum, sq);   // (all epilogue-1 reads happened before bar_a2 completed)
         epi_sync();
         sum = 0.0f;
@@ -466,17 +483,15 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean * mean, 0.0f) + 1.0e-5f);
         nmr = -mean * rstd;
         float o0 = 0.0f, o1 = 0.0f;
-        for (int c0 = c2b; c0 < c2e; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
+        for_each_unit(trow, c2b, c2e, [&](int c0, const uint32_t (&r)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 // padded columns: g2 = be2 = w3 = 0
-                const float yv = fmaxf(fmaf(fmaf(v[i], rstd, nmr), g2[c0 + i], be2[c0 + i]), 0.0f);
+                const float yv = fmaxf(fmaf(fmaf(__uint_as_float(r[i]), rstd, nmr), g2[c0 + i], be2[c0 + i]), 0.0f);
                 o0 = fmaf(yv, w3a[c0 + i], o0);
                 o1 = fmaf(yv, w3b[c0 + i], o1);
             }
-        }
+        });
         red_head[cg * kRows + row] = make_float2(o0, o1);
         epi_sync();
         if (cg == 0 && valid) {
@@ -614,7 +629,9 @@ static cudaError_t launch_actor_forward_cl(const void* blobs, const float* obs, 
     // FLOCK_ACTOR_TIMING=1 (developer knob): the first launch records clock64 at the phase boundaries of
     // every CTA, synchronises and prints the mean phase lengths to stderr
     static bool timing = getenv("FLOCK_ACTOR_TIMING") != nullptr;
-    static const int dbg_mode = getenv("FLOCK_ACTOR_EXPERIMENT") ? atoi(getenv("FLOCK_ACTOR_EXPERIMENT")) : 0;   // results invalid if != 0
+    // FLOCK_ACTOR_EXPERIMENT (developer knob, RESULTS INVALID when set): 1 = no weight streaming after the
+    // first ring fill (pure MMA rate), 2 = weight streaming without the MMAs
+    static const int dbg_mode = getenv("FLOCK_ACTOR_EXPERIMENT") ? atoi(getenv("FLOCK_ACTOR_EXPERIMENT")) & 3 : 0;
     long long* dbg = nullptr;
     if (timing) {
         timing = false;
@@ -651,12 +668,12 @@ static cudaError_t launch_actor_forward_cl(const void* blobs, const float* obs, 
 
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
                                  cudaStream_t s) {
-    // FLOCK_ACTOR_CLUSTER=1 disables the cluster-of-two weight multicast (A/B knob)
-    static const int cl = [] {
-        const char* v = getenv("FLOCK_ACTOR_CLUSTER");
-        return (v != nullptr && v[0] == '1') ? 1 : 2;
-    }();
-    if (cl == 2 && E > actor::kRows) return launch_actor_forward_cl<2>(blobs, obs, actions, E, N, in_dims, s);
+    // FLOCK_ACTOR_CLUSTER=2 runs CTAs as clusters of two that share every W2 chunk by TMA multicast (half the
+    // L2 -> SM weight reads). Correct and tested, but measured slower on B200 at 4096 x 32 (84.6 vs 74.6 us): the
+    // layer-2 phase is bound by shared-memory bandwidth (operand reads + TMA writes), not by L2, and the
+    // cluster barriers add ~2.5k cycles per CTA. Default: no clusters.
+    const char* v = getenv("FLOCK_ACTOR_CLUSTER");
+    if (v != nullptr && v[0] == '2' && E > actor::kRows) return launch_actor_forward_cl<2>(blobs, obs, actions, E, N, in_dims, s);
     return launch_actor_forward_cl<1>(blobs, obs, actions, E, N, in_dims, s);
 }
 
