@@ -379,12 +379,15 @@ def run_gpu(args, w):
 
     # optional: closed-loop rollout with the batched per-agent actors of the shared-critic DDPG learner
     # (BASELINE configs[2] "MADDPG actor rollout"; SURVEY 8f-2: the policy, not the env, bounds it)
-    if rank == 0 and args.policy == "actor" and w["variant"] != "uwd":
+    # The fused tcgen05 leg always runs for the uw workload (cfg3 IS the actor-rollout config); the PyTorch
+    # legs it is compared with only under --policy actor (they take seconds).
+    if rank == 0 and w["variant"] != "uwd" and (args.policy == "actor" or w["variant"] == "uw"):
         from marl_range_flocking_b200.policies import BatchedActors
         env = envs[0]
         obs = env.observation
         in_dims = obs[0, 0].numel()
-        for dtype, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        extra["actor_rollout"] = {}
+        for dtype, name in (((torch.float32, "fp32"), (torch.bfloat16, "bf16")) if args.policy == "actor" else ()):
             actors = BatchedActors(N, in_dims, 400, 300, 2, device=device, dtype=dtype)
             with torch.no_grad():
                 for _ in range(5):
@@ -398,7 +401,7 @@ def run_gpu(args, w):
                 ev1.record()
                 torch.cuda.synchronize(device)
             t = ev0.elapsed_time(ev1) * 1e-3 / reps
-            extra.setdefault("actor_rollout", {})[name] = {
+            extra["actor_rollout"][name] = {
                 "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
                 "policy": f"{N} per-agent MLPs {in_dims}-400-300-2 (LayerNorm, ReLU, tanh) as baddbmm over the agent dim"}
         # the same closed loop with the fused tcgen05 actor kernel (flock_actor_forward): one policy launch
@@ -437,6 +440,44 @@ def run_gpu(args, w):
                     "policy": "flock_actor_forward: tcgen05.mma bf16 / fp32 accumulate, LayerNorm + ReLU + tanh fused, "
                               "one launch for all envs and agents"}
         torch.cuda.current_stream(device).wait_stream(side)
+
+    # VDN action selection next to the discrete env (BASELINE configs[3]): the per-agent Q networks of
+    # learners/vdn/net.py (recurrent, as the reference trains them) + per-env epsilon-greedy, closed loop with the
+    # env step; fused fp32 kernel (flock_qnet_forward) vs the same networks as PyTorch baddbmm's
+    if rank == 0 and w["variant"] == "uwd":
+        from marl_range_flocking_b200.policies import BatchedQNet
+        env = envs[0]
+        k_obs = env.observation.shape[-1]
+        qn = BatchedQNet(N, k_obs, k_obs, recurrent=True, device=device)
+        extra["vdn_rollout"] = {}
+        legs = [("fused_fp32", True)] + ([("pytorch_fp32", False)] if args.policy == "actor" else [])
+        for label, fused in legs:
+            hidden = qn.init_hidden(E)
+            obs = env.observation
+            with torch.no_grad():
+                def one(t, obs, hidden):
+                    if fused:
+                        act, hidden = qn.sample_action_fused(obs, hidden, 0.1, step=t, seed=11)
+                    else:
+                        act, hidden = qn.sample_action(obs, hidden, 0.1)
+                    obs, *_ = env.step(act, DT)
+                    return obs, hidden
+                for t in range(5):
+                    obs, hidden = one(t, obs, hidden)
+                torch.cuda.synchronize(device)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 200
+                ev0.record()
+                for t in range(reps):
+                    obs, hidden = one(5 + t, obs, hidden)
+                ev1.record()
+                torch.cuda.synchronize(device)
+            t = ev0.elapsed_time(ev1) * 1e-3 / reps
+            extra["vdn_rollout"][label] = {
+                "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
+                "policy": f"{N} per-agent recurrent Q networks {k_obs}-64-32-GRU32-{k_obs} + per-env epsilon-greedy, "
+                          + ("one fused fp32 launch (flock_qnet_forward)" if fused else "PyTorch baddbmm over the agent dim"),
+                "launch": "eager (one policy launch + one env launch per step)"}
 
     if rank == 0:
         peak, peak_src = _peaks()

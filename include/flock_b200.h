@@ -215,6 +215,21 @@ FLOCK_API int flock_actor_pack(int num_agents, int input_dims, int fc1_dims, int
 FLOCK_API int flock_actor_forward(const void *packed, const float *obs, float *actions, int num_envs, int num_agents,
                         int input_dims, void *stream);
 
+/* Fused VDN action selection ("VDN action selection", BASELINE configs[3]): QNet.forward + QNet.sample_action of
+ * learners/vdn/net.py:11-58 for all envs and agents in one fp32 launch, replacing the per-agent Python loop
+ * (net.py:30-35). Per agent: Linear(n_obs,64)-ReLU-Linear(64,32)-ReLU-[GRUCell(32,32)]-Linear(32,n_actions).
+ *   params: 6 (10 if recurrent) DEVICE pointers {w1 [A][n_obs][64], b1 [A][64], w2 [A][64][32], b2 [A][32],
+ *     wq [A][32][n_actions], bq [A][n_actions], w_ih [A][32][96], b_ih [A][96], w_hh [A][32][96], b_hh [A][96]},
+ *     float32, weights input-major (transposed torch.nn.Linear / GRUCell weights, gate order r|z|n).
+ *   obs [E][A][n_obs]; hidden_in / hidden_out [E][A][32] (recurrent; may alias); q_out [E][A][n_actions] or NULL;
+ *   actions [E][A] float-coded ids or NULL: argmax (first maximum), except that with probability epsilon an env
+ *   explores as a whole (one decision per env, net.py:54) and every agent draws a uniform id. The draws are
+ *   Philox4x32-10 with counter (env_offset + env, agent, step, tag) and key = seed: invariant under sharding.
+ *   n_obs <= 16, n_actions <= 16. Asynchronous on `stream`. */
+FLOCK_API int flock_qnet_forward(const float *const *params, int recurrent, const float *obs, const float *hidden_in,
+                       float *q_out, float *hidden_out, float *actions, int num_envs, int num_agents, int n_obs,
+                       int n_actions, float epsilon, uint64_t seed, uint32_t step, int env_offset, void *stream);
+
 /* Debug / test hooks for the canonical arithmetic (device arrays, n elements). */
 FLOCK_API int flock_debug_sincos(const float *h, int n, float *sn, float *cs, void *stream);
 FLOCK_API int flock_debug_normal2(const uint32_t *words, int n_pairs, float *z, void *stream);

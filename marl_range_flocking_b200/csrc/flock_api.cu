@@ -540,6 +540,25 @@ int flock_actor_forward(const void* packed, const float* obs, float* actions, in
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor forward kernel launch");
 }
 
+int flock_qnet_forward(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
+                       float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, int n_actions,
+                       float epsilon, uint64_t seed, uint32_t step, int env_offset, void* stream) {
+    if (params == nullptr || obs == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    if (num_envs < 1 || num_agents < 1 || num_agents > 65535) return fail(FLOCK_E_INVALID, "bad num_envs / num_agents");
+    if (n_obs < 1 || n_obs > flock::qnet_max_obs()) return fail(FLOCK_E_INVALID, "n_obs %d not in [1, %d]", n_obs, flock::qnet_max_obs());
+    if (n_actions < 1 || n_actions > flock::qnet_max_actions())
+        return fail(FLOCK_E_INVALID, "n_actions %d not in [1, %d]", n_actions, flock::qnet_max_actions());
+    for (int i = 0; i < (recurrent ? 10 : 6); ++i)
+        if (params[i] == nullptr) return fail(FLOCK_E_INVALID, "Q-network parameter %d is NULL", i);
+    if (recurrent && hidden_in == nullptr) return fail(FLOCK_E_INVALID, "recurrent Q-network needs hidden_in");
+    if (recurrent && ((reinterpret_cast<uintptr_t>(hidden_in) & 15u) || (reinterpret_cast<uintptr_t>(hidden_out) & 15u)))
+        return fail(FLOCK_E_INVALID, "hidden state buffers must be 16-byte aligned");
+    if (!(epsilon >= 0.0f)) return fail(FLOCK_E_INVALID, "epsilon must be >= 0");
+    cudaError_t err = flock::launch_qnet(params, recurrent, obs, hidden_in, q_out, hidden_out, actions, num_envs, num_agents,
+                                         n_obs, n_actions, epsilon, seed, step, env_offset, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "qnet kernel launch");
+}
+
 int flock_debug_sincos(const float* h, int n, float* sn, float* cs, void* stream) {
     cudaError_t err = flock::launch_debug_sincos(h, n, sn, cs, static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "debug_sincos");

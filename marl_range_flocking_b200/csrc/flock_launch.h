@@ -34,4 +34,11 @@ void actor_dims(int* fc1, int* fc2, int* n_actions);
 cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s);
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
                                  cudaStream_t s);
+
+// flock_qnet.cu (fused VDN Q-network forward + epsilon-greedy action selection, fp32)
+int qnet_max_obs();
+int qnet_max_actions();
+cudaError_t launch_qnet(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
+                        float* hidden_out, float* actions, int E, int A, int n_obs, int n_act, float epsilon, uint64_t seed,
+                        uint32_t step, int env_offset, cudaStream_t s);
 }  // namespace flock

@@ -177,6 +177,51 @@ class BatchedQNet(torch.nn.Module):
         q = torch.baddbmm(self.bq, x, self.wq).transpose(0, 1).float()             # (E, N, A)
         return q, next_hidden
 
+    # ---- fused path (csrc/flock_qnet.cu through the C ABI): one fp32 launch for all envs and agents ----
+    @torch.no_grad()
+    def _fused(self, obs, hidden, want_q: bool, want_actions: bool, epsilon: float, step: int, seed: int, env_offset: int):
+        import ctypes
+
+        from . import _lib
+        lib = _lib.load_library()
+        if self.w1.device.type != "cuda":
+            raise RuntimeError("the fused Q-network kernel needs CUDA parameters (there is no CPU path)")
+        E, N, n_obs = obs.shape
+        A = self.wq.shape[2]
+        x = obs if (obs.dtype == torch.float32 and obs.is_contiguous()) else obs.float().contiguous()
+        names = ["w1", "b1", "w2", "b2", "wq", "bq"] + (["w_ih", "b_ih", "w_hh", "b_hh"] if self.recurrent else [])
+        srcs = [getattr(self, n).detach() for n in names]
+        srcs = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in srcs]
+        ptrs = (ctypes.c_void_p * 10)(*([t.data_ptr() for t in srcs] + [None] * (10 - len(srcs))))
+        dev = x.device
+        q = torch.empty(E, N, A, dtype=torch.float32, device=dev) if want_q else None
+        act = torch.empty(E, N, dtype=torch.float32, device=dev) if want_actions else None
+        h_in = h_out = None
+        if self.recurrent:
+            h_in = hidden if (hidden.dtype == torch.float32 and hidden.is_contiguous()) else hidden.float().contiguous()
+            h_out = torch.empty(E, N, self.hx_size, dtype=torch.float32, device=dev)
+        p = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.flock_qnet_forward(ptrs, int(self.recurrent), x.data_ptr(), p(h_in), p(q), p(h_out), p(act), E, N,
+                                              n_obs, A, float(epsilon), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
+                                              torch.cuda.current_stream().cuda_stream))
+        if h_out is None:
+            h_out = torch.empty(E, N, self.hx_size, device=dev)      # like `forward`: unused without the GRU
+        return q, h_out, act
+
+    def forward_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`forward` in one kernel launch (fp32, same arithmetic up to summation order)."""
+        q, h, _ = self._fused(obs, hidden, True, False, 0.0, 0, 0, 0)
+        return q, h
+
+    def sample_action_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor], epsilon: float, step: int = 0,
+                            seed: int = 0, env_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`sample_action` (net.py:52-58) in one kernel launch: Q-values, argmax and the per-env epsilon-greedy
+        decision never leave the SM. Exploration draws are Philox(seed; env_offset + env, agent, step), i.e.
+        reproducible and invariant under env sharding -- pass the rollout step as `step`."""
+        _, h, act = self._fused(obs, hidden, False, True, epsilon, step, seed, env_offset)
+        return act, h
+
     @torch.no_grad()
     def sample_action(self, obs: torch.Tensor, hidden: Optional[torch.Tensor], epsilon: float,
                       generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
