@@ -170,6 +170,19 @@ FLOCK_API int flock_step_host(flock_env_t *env, const float *h_actions, float dt
                     float *h_obs, float *h_reward, uint8_t *h_agent_done, uint8_t *h_env_done,
                     void *stream);
 
+/* flock_step_host without the final synchronisation (same transfer policy: zero-copy kernel for small
+ * result sets, otherwise one staged H2D copy and one packed D2H copy): everything is enqueued on
+ * `stream` and the call returns at once. The host buffers must be pinned and must stay untouched until
+ * the caller has synchronised `stream` (or an event recorded on it). Two handles driven on two streams
+ * overlap one env batch's result copy with the other's action copy and step: the pipelined `e2e` leg of
+ * bench.py. Same results as flock_step_host. */
+FLOCK_API int flock_step_host_async(flock_env_t *env, const float *h_actions, float dt, const float *h_noise,
+                          float *h_obs, float *h_reward, uint8_t *h_agent_done, uint8_t *h_env_done,
+                          void *stream);
+/* Blocks until the results of this handle's last flock_step_host_async have landed in the host buffers
+ * (an event recorded behind the result copy; other work on the stream is not waited for). */
+FLOCK_API int flock_wait_host(flock_env_t *env);
+
 /* Which state copy is current: always 0 (the state is updated in place; kept for ABI compatibility). */
 FLOCK_API int flock_state_slot(const flock_env_t *env);
 

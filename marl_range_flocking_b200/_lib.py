@@ -74,6 +74,8 @@ def load_library() -> ctypes.CDLL:
         "flock_step_n": (i32, [vp, i32, f32, vp]),
         "flock_random_actions": (i32, [vp, u32, vp, vp]),
         "flock_step_host": (i32, [vp, vp, f32, vp, vp, vp, vp, vp, vp]),
+        "flock_step_host_async": (i32, [vp, vp, f32, vp, vp, vp, vp, vp, vp]),
+        "flock_wait_host": (i32, [vp]),
         "flock_state_slot": (i32, [vp]),
         "flock_get_step_index": (u32, [vp]),
         "flock_set_step_index": (i32, [vp, u32]),

@@ -53,6 +53,8 @@ struct flock_env {
     void* zc_dev[5];
     bool zc_ok;
     size_t action_floats;
+    cudaEvent_t host_event;       // flock_step_host_async / flock_wait_host
+    bool host_event_live;
 };
 
 namespace {
@@ -213,7 +215,7 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
 }
 
 int copy_results_to_host(flock_env* e, float* h_obs, float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool sync = true) {
     const size_t EN = (size_t)e->cfg.num_envs * e->cfg.num_agents;
     cudaError_t err = cudaSuccess;
     // When the caller laid obs | reward | agent_done | env_done out back to back on BOTH sides (the
@@ -243,6 +245,7 @@ int copy_results_to_host(flock_env* e, float* h_obs, float* h_reward, uint8_t* h
             err = cudaMemcpyAsync(h_env_done, e->b.env_done, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s);
     }
     if (err != cudaSuccess) return cuda_fail(err, "D2H outputs");
+    if (!sync) return FLOCK_OK;
     err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) return cuda_fail(err, "stream synchronize");
     return FLOCK_OK;
@@ -328,6 +331,7 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->sorted_xy);
     cudaFree(e->hint_slots);
     cudaFree(e->pair_counter);
+    if (e->host_event_live) cudaEventDestroy(e->host_event);
     delete e;
 }
 
@@ -400,8 +404,8 @@ int flock_step_n(flock_env_t* e, int num_steps, float dt, void* stream) {
     return rc;
 }
 
-int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
-                    float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done, void* stream) {
+static int step_host_impl(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
+                          float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done, void* stream, bool sync) {
     int rc = check_bound(e);
     if (rc != FLOCK_OK) return rc;
     if (h_actions == nullptr) return fail(FLOCK_E_INVALID, "h_actions is NULL");
@@ -447,6 +451,7 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
             mir.env_done = static_cast<uint8_t*>(e->zc_dev[4]);
             rc = step_device(e, static_cast<const float*>(e->zc_dev[0]), dt, nullptr, s, &mir);
             if (rc != FLOCK_OK) return rc;
+            if (!sync) return FLOCK_OK;
             cudaError_t se = cudaStreamSynchronize(s);
             if (se != cudaSuccess) return cuda_fail(se, "stream synchronize");
             return FLOCK_OK;
@@ -454,7 +459,7 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
         if (zc_inputs) {   // actions read in place, results by one packed DMA copy below
             rc = step_device(e, static_cast<const float*>(e->zc_dev[0]), dt, nullptr, s);
             if (rc != FLOCK_OK) return rc;
-            return copy_results_to_host(e, h_obs, h_reward, h_agent_done, h_env_done, s);
+            return copy_results_to_host(e, h_obs, h_reward, h_agent_done, h_env_done, s, sync);
         }
     }
     cudaError_t err = cudaMemcpyAsync(e->stage_actions, h_actions, e->action_floats * sizeof(float),
@@ -468,7 +473,34 @@ int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const floa
     }
     rc = step_device(e, e->stage_actions, dt, d_noise, s);
     if (rc != FLOCK_OK) return rc;
-    return copy_results_to_host(e, h_obs, h_reward, h_agent_done, h_env_done, s);
+    return copy_results_to_host(e, h_obs, h_reward, h_agent_done, h_env_done, s, sync);
+}
+
+int flock_step_host(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
+                    float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done, void* stream) {
+    return step_host_impl(e, h_actions, dt, h_noise, h_obs, h_reward, h_agent_done, h_env_done, stream, true);
+}
+
+int flock_step_host_async(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
+                          float* h_reward, uint8_t* h_agent_done, uint8_t* h_env_done, void* stream) {
+    // same transfer policy as flock_step_host (zero-copy kernel for small result sets, copy engines otherwise)
+    int rc = step_host_impl(e, h_actions, dt, h_noise, h_obs, h_reward, h_agent_done, h_env_done, stream, false);
+    if (rc != FLOCK_OK) return rc;
+    cudaError_t err;
+    if (!e->host_event_live) {
+        err = cudaEventCreateWithFlags(&e->host_event, cudaEventDisableTiming);
+        if (err != cudaSuccess) return cuda_fail(err, "event create");
+        e->host_event_live = true;
+    }
+    err = cudaEventRecord(e->host_event, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "event record");
+}
+
+int flock_wait_host(flock_env_t* e) {
+    if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
+    if (!e->host_event_live) return fail(FLOCK_E_INVALID, "flock_wait_host without a flock_step_host_async");
+    cudaError_t err = cudaEventSynchronize(e->host_event);
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "event synchronize");
 }
 
 int flock_state_slot(const flock_env_t* e) { return e ? e->slot : 0; }

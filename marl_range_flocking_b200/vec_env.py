@@ -121,6 +121,7 @@ class VecEnv:
             ptr(self._ep_len), ptr(self._stats))
         check(self.lib.flock_bind(self._h, ctypes.byref(bufs)))
         self._host = None   # pinned host mirrors for step_host
+        self._host_async = None   # side stream + validated action buffers of step_host_async
         self._dev_index = self.device.index
         self._numel_cache = {}
         self._act_shape = (E, N) if variant == "uwd" else (E, N, 2)
@@ -316,6 +317,50 @@ class VecEnv:
             if rc:
                 check(rc)
         return hb["ret"]
+
+    def step_host_async(self, actions_cpu: torch.Tensor, dt: float = 0.1, noise_cpu: Optional[torch.Tensor] = None) -> None:
+        """`step_host` without the wait: pinned host actions in, results into the pinned host mirrors by
+        one packed copy, all on this env's own side stream; returns at once. `wait_host()` blocks until
+        the results have landed and returns them. Two VecEnvs driven alternately overlap one batch's
+        result copy with the other's action copy and step (bench.py `e2e`). Do not mix with `step()` on
+        the same env without a synchronisation in between. The per-call Python work is two ctypes calls."""
+        hs = self._host_async
+        if hs is None:
+            E, N = self.num_envs, self.num_particles
+            if self._host is None:
+                slab, (o, r, ad, ed) = self._alloc_outputs(None, pin=True)
+                self._host = dict(slab=slab, obs=o, reward=r, agent_done=ad, env_done=ed,
+                                  ptrs=(o.data_ptr(), r.data_ptr(), ad.data_ptr(), ed.data_ptr()),
+                                  ret=(o if self.obs_hist > 1 else o[:, :, 0, :], r, (ad, ed), {}))
+            stream = torch.cuda.Stream(device=self.device)
+            stream.wait_stream(torch.cuda.current_stream(self.device))   # after reset() etc.
+            hs = self._host_async = dict(stream=stream, raw=stream.cuda_stream, ok=set(),
+                                         want=E * N * (1 if self.variant == "uwd" else 2))
+        key = (actions_cpu.data_ptr(), actions_cpu.numel())
+        if key not in hs["ok"]:          # validated once per buffer: is_pinned() alone costs more than the launch
+            if (actions_cpu.device.type != "cpu" or actions_cpu.dtype != torch.float32 or not actions_cpu.is_contiguous()
+                    or not actions_cpu.is_pinned()):
+                raise ValueError("step_host_async wants a pinned contiguous float32 CPU tensor")
+            if actions_cpu.numel() != hs["want"]:
+                raise ValueError(f"actions has {actions_cpu.numel()} elements, expected {hs['want']}")
+            hs["ok"].add(key)
+        if torch.cuda.current_device() != self._dev_index:
+            with self._dev_guard():
+                rc = self.lib.flock_step_host_async(self._h, key[0], dt, None if noise_cpu is None else noise_cpu.data_ptr(),
+                                                    *self._host["ptrs"], hs["raw"])
+        else:
+            rc = self.lib.flock_step_host_async(self._h, key[0], dt, None if noise_cpu is None else noise_cpu.data_ptr(),
+                                                *self._host["ptrs"], hs["raw"])
+        if rc:
+            check(rc)
+
+    def wait_host(self):
+        """Block until the last `step_host_async` has delivered; returns (obs, reward, (agent_done, env_done), {})
+        as pinned host tensors (reused by the next call)."""
+        rc = self.lib.flock_wait_host(self._h)
+        if rc:
+            check(rc)
+        return self._host["ret"]
 
     # ---- checkpoint / injection --------------------------------------------------------------
     def get_state(self) -> Dict[str, torch.Tensor]:

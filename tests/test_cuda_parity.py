@@ -692,3 +692,29 @@ def test_cuda_uw_is_bit_identical_to_the_reference(path):
         assert_same(f"obs {t}", env.observation[0], g["obs"][t])
         assert_same(f"reward {t}", env.reward[0], g["reward"][t])
         assert_same(f"done {t}", env.dones[0][0], g["agent_done"][t])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,E,N,k", [("v2", 96, 10, 4), ("uw", 40, 32, 3), ("uwd", 64, 16, 4), ("v2", 3, 200, 8)])
+def test_async_host_path_two_batches_in_flight_matches_the_oracle(variant, E, N, k):
+    """flock_step_host_async (VecEnv.step_host_async / wait_host): two env batches stepped alternately with
+    their copies in flight give bit for bit what the oracle gives for each batch."""
+    pairs = [make_pair(variant, E, N, k, 0.5, rs=(0, 100), sr=7.0, seed=31 + i) for i in range(2)]
+    for env, orc in pairs:
+        env.reset()
+        orc.reset()
+    torch.cuda.synchronize()
+    acts = [[torch.from_numpy(orc.random_actions(t)).pin_memory() for t in range(6)] for _, orc in pairs]
+    for t in range(6):
+        for i, (env, orc) in enumerate(pairs):
+            env.step_host_async(acts[i][t], 0.1)
+        for i, (env, orc) in enumerate(pairs):
+            orc.step(acts[i][t].numpy(), 0.1)
+            obs, reward, (agent_done, env_done), _ = env.wait_host()
+            assert obs.device.type == "cpu"
+            assert_same("obs", obs.reshape(orc.obs.shape), orc.obs)
+            assert_same("reward", reward[..., 0], orc.reward)
+            assert_same("agent_done", agent_done.to(torch.uint8), orc.agent_done)
+            assert_same("env_done", env_done.to(torch.uint8), orc.env_done)
+    for env, orc in pairs:
+        assert_same("x", env.x, orc.x)
