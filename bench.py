@@ -319,7 +319,19 @@ def run_gpu(args, w):
     use_dist = world > 1
     if use_dist:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout at communicator creation; stdout carries ONE JSON line, so the
+        # file descriptor points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
         def barrier():
             dist.barrier()
