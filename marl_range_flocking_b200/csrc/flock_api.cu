@@ -580,8 +580,11 @@ int flock_qnet_forward(const float* const* params, int recurrent, const float* o
     if (n_obs < 1 || n_obs > flock::qnet_max_obs()) return fail(FLOCK_E_INVALID, "n_obs %d not in [1, %d]", n_obs, flock::qnet_max_obs());
     if (n_actions < 1 || n_actions > flock::qnet_max_actions())
         return fail(FLOCK_E_INVALID, "n_actions %d not in [1, %d]", n_actions, flock::qnet_max_actions());
-    for (int i = 0; i < (recurrent ? 10 : 6); ++i)
+    for (int i = 0; i < (recurrent ? 10 : 6); ++i) {
         if (params[i] == nullptr) return fail(FLOCK_E_INVALID, "Q-network parameter %d is NULL", i);
+        if (reinterpret_cast<uintptr_t>(params[i]) & 15u)
+            return fail(FLOCK_E_INVALID, "Q-network parameter %d is not 16-byte aligned", i);
+    }
     if (recurrent && hidden_in == nullptr) return fail(FLOCK_E_INVALID, "recurrent Q-network needs hidden_in");
     if (recurrent && ((reinterpret_cast<uintptr_t>(hidden_in) & 15u) || (reinterpret_cast<uintptr_t>(hidden_out) & 15u)))
         return fail(FLOCK_E_INVALID, "hidden state buffers must be 16-byte aligned");

@@ -62,7 +62,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ W, const float* 
 }
 
 template <bool REC>
-__global__ void __launch_bounds__(kThreads) flock_qnet_kernel(const __grid_constant__ Args a) {
+__global__ void __launch_bounds__(kThreads, 2) flock_qnet_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(16) float sw[];
     const int agent = blockIdx.x;
     const int n_obs = a.n_obs, n_act = a.n_act;
@@ -78,24 +78,26 @@ __global__ void __launch_bounds__(kThreads) flock_qnet_kernel(const __grid_const
     float* sbih = sWih + kHx * 3 * kHx;
     float* sWhh = sbih + 3 * kHx;
     float* sbhh = sWhh + kHx * 3 * kHx;
-    for (int t = threadIdx.x; t < n_obs * kHid1; t += kThreads) sW1[t] = a.w1[(size_t)agent * n_obs * kHid1 + t];
-    for (int t = threadIdx.x; t < kHid1; t += kThreads) sb1[t] = a.b1[(size_t)agent * kHid1 + t];
-    for (int t = threadIdx.x; t < kHid1 * kHx; t += kThreads) sW2[t] = a.w2[(size_t)agent * kHid1 * kHx + t];
-    for (int t = threadIdx.x; t < kHx; t += kThreads) sb2[t] = a.b2[(size_t)agent * kHx + t];
+    // stage the agent's weights: 128-bit copies (every block is a 16-byte multiple; the API checks alignment)
+    auto copy4 = [&](float* dst, const float* src, int n) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int t = threadIdx.x; t < (n >> 2); t += kThreads) d4[t] = s4[t];
+    };
+    copy4(sW1, a.w1 + (size_t)agent * n_obs * kHid1, n_obs * kHid1);
+    copy4(sb1, a.b1 + (size_t)agent * kHid1, kHid1);
+    copy4(sW2, a.w2 + (size_t)agent * kHid1 * kHx, kHid1 * kHx);
+    copy4(sb2, a.b2 + (size_t)agent * kHx, kHx);
     for (int t = threadIdx.x; t < kHx * actp; t += kThreads) {
         const int i = t / actp, j = t % actp;
         sWq[t] = j < n_act ? a.wq[((size_t)agent * kHx + i) * n_act + j] : 0.0f;
     }
     for (int t = threadIdx.x; t < actp; t += kThreads) sbq[t] = t < n_act ? a.bq[(size_t)agent * n_act + t] : 0.0f;
     if (REC) {
-        for (int t = threadIdx.x; t < kHx * 3 * kHx; t += kThreads) {
-            sWih[t] = a.w_ih[(size_t)agent * kHx * 3 * kHx + t];
-            sWhh[t] = a.w_hh[(size_t)agent * kHx * 3 * kHx + t];
-        }
-        for (int t = threadIdx.x; t < 3 * kHx; t += kThreads) {
-            sbih[t] = a.b_ih[(size_t)agent * 3 * kHx + t];
-            sbhh[t] = a.b_hh[(size_t)agent * 3 * kHx + t];
-        }
+        copy4(sWih, a.w_ih + (size_t)agent * kHx * 3 * kHx, kHx * 3 * kHx);
+        copy4(sWhh, a.w_hh + (size_t)agent * kHx * 3 * kHx, kHx * 3 * kHx);
+        copy4(sbih, a.b_ih + (size_t)agent * 3 * kHx, 3 * kHx);
+        copy4(sbhh, a.b_hh + (size_t)agent * 3 * kHx, 3 * kHx);
     }
     __syncthreads();
 

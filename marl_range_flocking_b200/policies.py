@@ -190,9 +190,14 @@ class BatchedQNet(torch.nn.Module):
         A = self.wq.shape[2]
         x = obs if (obs.dtype == torch.float32 and obs.is_contiguous()) else obs.float().contiguous()
         names = ["w1", "b1", "w2", "b2", "wq", "bq"] + (["w_ih", "b_ih", "w_hh", "b_hh"] if self.recurrent else [])
-        srcs = [getattr(self, n).detach() for n in names]
-        srcs = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in srcs]
-        ptrs = (ctypes.c_void_p * 10)(*([t.data_ptr() for t in srcs] + [None] * (10 - len(srcs))))
+        key = tuple(getattr(self, n).data_ptr() for n in names)
+        cache = getattr(self, "_fused_ptrs", None)
+        if cache is None or cache[0] != key:     # the pointer table is rebuilt only when a parameter moved
+            srcs = [getattr(self, n).detach() for n in names]
+            srcs = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in srcs]
+            ptrs = (ctypes.c_void_p * 10)(*([t.data_ptr() for t in srcs] + [None] * (10 - len(srcs))))
+            cache = self._fused_ptrs = (key, ptrs, srcs)
+        ptrs = cache[1]
         dev = x.device
         q = torch.empty(E, N, A, dtype=torch.float32, device=dev) if want_q else None
         act = torch.empty(E, N, dtype=torch.float32, device=dev) if want_actions else None
