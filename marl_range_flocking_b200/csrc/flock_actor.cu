@@ -5,15 +5,13 @@
 // evaluated for all envs in ONE launch, straight from the env's observation buffer into the action
 // buffer flock_step consumes. This IS GEMM-shaped work (250 kFLOP per agent-step, 40x the env step),
 // so it runs on the 5th-generation tensor cores:
-//   * CTA = 128 envs x one agent; both matrix layers are tcgen05.mma (kind::f16, bf16 operands, fp32
+//   * persistent kernel, one CTA per SM; work item = 128 envs x one agent, dealt out in contiguous runs so a
+//     CTA mostly stays on one agent; both matrix layers are tcgen05.mma (kind::f16, bf16 operands, fp32
 //     accumulators in TMEM, M = 128), issued by one thread; operands sit in shared memory in the
 //     no-swizzle K-major canonical layout (8-row x 16-byte core matrices);
 //   * the per-agent weights are pre-packed once (flock_actor_pack) into exactly the shared-memory
 //     image the MMA wants, so they stream from L2 with plain 1-D TMA bulk copies (cp.async.bulk +
 //     mbarrier complete_tx) through a 4-slot ring of two-K-step chunks -- no tensor maps;
-//   * optional (FLOCK_ACTOR_CLUSTER=2): CTAs run as clusters of two (same agent, neighbouring env tiles),
-//     each CTA fetches half of every W2 chunk and multicasts it to both, tcgen05.commit multicasts the
-//     "slot free" arrival -- halves the L2 -> SM weight traffic, but the layer is not L2-bound (see below);
 //   * one warp issues the TMA copies and one the MMAs, both warp-uniformly with a single elected lane
 //     (descriptors stay in uniform registers); biases ride in the MMAs as two extra K slots (hi + lo
 //     bf16 parts against constant-1 inputs);
@@ -63,7 +61,7 @@ constexpr int kOffW1 = kOffA1 + kA1Bytes;
 constexpr int kOffPar = kOffW1 + kW1Bytes;
 constexpr int kOffRing = (kOffPar + kParamBytes + 127) & ~127;
 constexpr int kOffBar = kOffRing + kStages * kChunkBytes;
-constexpr int kNumBars = 2 * kStages + 5;
+constexpr int kNumBars = 2 * kStages + 6;
 constexpr int kOffRed = kOffBar + kNumBars * 8 + 16;       // + tmem pointer; then row-statistic / head partials
 constexpr int kColGroups = 4;
 constexpr int kRedBytes = 2 * kColGroups * kRows * 8;       // two float2 [4][128] buffers
@@ -105,21 +103,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
 }
 __device__ __forceinline__ bool elect_one() {   // one lane of the (fully active) warp
     uint32_t pred;
@@ -163,11 +146,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {   // same, on `bar` of every CTA in mask
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when all MMAs issued so far are done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -191,24 +169,16 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                  :
                  : "memory");
 }
-// for (c0 = cb; c0 < ce; c0 += 16) f(c0, the 16 columns at c0), with the load of the next unit overlapped
+// for (c0 = cb; c0 < ce; c0 += 16) f(c0, the 16 columns at c0). (Keeping the next unit's load in flight in a
+// second register buffer was measured: no gain, and the 16 extra registers spill in the persistent kernel.)
 template <typename F>
 __device__ __forceinline__ void for_each_unit(uint32_t trow, int cb, int ce, F&& f) {
-    uint32_t r0[16], r1[16];
-    if (cb >= ce) return;
-    tmem_ld16_issue(trow + cb, r0);
-    int c0 = cb;
-    while (true) {
-        tmem_ld16_wait(r0);
-        if (c0 + 16 < ce) tmem_ld16_issue(trow + c0 + 16, r1);
-        f(c0, r0);
-        c0 += 16;
-        if (c0 >= ce) break;
-        tmem_ld16_wait(r1);
-        if (c0 + 16 < ce) tmem_ld16_issue(trow + c0 + 16, r0);
-        f(c0, r1);
-        c0 += 16;
-        if (c0 >= ce) break;
+#pragma unroll 1
+    for (int c0 = cb; c0 < ce; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_issue(trow + c0, r);
+        tmem_ld16_wait(r);
+        f(c0, r);
     }
 }
 
@@ -224,62 +194,38 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // column units (16 accumulator columns each) owned by column group g: layer 1 has 25 units, layer 2 has 19
 __device__ __forceinline__ int unit_begin(int units, int g) { return (units * g + kColGroups - 1) / kColGroups; }
 
-// grid = (agents, env tiles rounded up to a multiple of CL), cluster = (1, CL, 1);
+// Persistent kernel: grid = min(#SMs, work items) CTAs, one per SM; work item = (agent, tile of 128 envs),
+// items are dealt out in contiguous runs so that a CTA mostly stays on one agent (W1 and the fp32 parameters
+// are reloaded only when the agent changes; TMEM, the barriers and the W2 ring live across items).
 // obs [E][N][in_dims] fp32, out [E][N][2] fp32
-template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ obs, float* __restrict__ out, int E, int N,
-                   int in_dims, long long* __restrict__ dbg, int dbg_mode) {
+                   int in_dims, int tiles, int items_per_cta, long long* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
-    // phase timestamps (FLOCK_ACTOR_TIMING=1, see launch_actor_forward): 16 clock64 slots per CTA
-    long long* const dbg_cta = dbg != nullptr ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+    // phase timestamps of the CTA's FIRST item (FLOCK_ACTOR_TIMING=1, see launch_actor_forward): 16 clock64 slots
+    long long* dbg_cta = dbg != nullptr ? dbg + (size_t)blockIdx.x * 16 : nullptr;
     auto stamp = [&](int slot) {
         if (dbg_cta != nullptr) dbg_cta[slot] = clock64();
     };
     if (threadIdx.x == 0) stamp(0);
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 127u) & ~127u;     // the same offset in every CTA of the cluster
+    const uint32_t base = (raw + 127u) & ~127u;
     uint8_t* sm = smem_raw + (base - raw);
-    const int agent = blockIdx.x, tile = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t* blob = blobs + (size_t)agent * kBlobBytes;
-    const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
-    constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
+    const int total_items = N * tiles;
+    const int item0 = blockIdx.x * items_per_cta;
+    const int item1 = min(item0 + items_per_cta, total_items);
 
     const uint32_t sA2 = base + kOffA2, sA1 = base + kOffA1, sW1 = base + kOffW1, sPar = base + kOffPar;
     const uint32_t sRing = base + kOffRing, sBar = base + kOffBar;
     auto bar_full = [&](int s) { return sBar + 8u * s; };
     auto bar_empty = [&](int s) { return sBar + 8u * (kStages + s); };
     const uint32_t bar_w1 = sBar + 8u * (2 * kStages), bar_a1 = bar_w1 + 8u, bar_mma1 = bar_w1 + 16u, bar_a2 = bar_w1 + 24u,
-                   bar_mma2 = bar_w1 + 32u;
+                   bar_mma2 = bar_w1 + 32u, bar_done = bar_w1 + 40u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + kNumBars * 8);
     const float* par = reinterpret_cast<const float*>(sm + kOffPar);
     float2* red_stat = reinterpret_cast<float2*>(sm + kOffRed);               // [4][128] (sum, sum of squares)
     float2* red_head = red_stat + kColGroups * kRows;                          // [4][128] (o0, o1)
-
-    // epilogue-thread coordinates; the observation loads are issued before the set-up so that their
-    // DRAM latency overlaps the TMEM allocation and the barrier initialisation
-    const int q = warp & 3, cg = warp >> 2;
-    const int row = q * 32 + lane;                     // TMEM lane
-    const int env = tile * kRows + row;
-    const bool valid = env < E;
-    float xin[kInPad];
-#pragma unroll
-    for (int i = 0; i < kInPad; ++i) xin[i] = 0.0f;
-    if (warp < 4 && valid) {
-        const float* src = obs + ((size_t)env * N + agent) * in_dims;
-        if (in_dims == 12) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            const float4 a = s4[0], b = s4[1], c = s4[2];
-            xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w;
-            xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
-            xin[8] = c.x; xin[9] = c.y; xin[10] = c.z; xin[11] = c.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < kMaxIn; ++i)
-                if (i < in_dims) xin[i] = src[i];
-        }
-    }
 
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -289,18 +235,18 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
     } else if (warp == kTmaWarp && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), CL);          // one tcgen05.commit arrival per CTA of the cluster
+            mbar_init(bar_empty(s), 1);
         }
         mbar_init(bar_w1, 1);
         mbar_init(bar_a1, kRows);
         mbar_init(bar_mma1, 1);
         mbar_init(bar_a2, kEpiThreads);
         mbar_init(bar_mma2, 1);
+        mbar_init(bar_done, kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any multicast copy / arrival targets them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (threadIdx.x == 0) stamp(1);
@@ -310,103 +256,102 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
     // predicated on one elected lane. Under `if (lane == 0)` every descriptor went through a
     // per-thread -> uniform register waterfall and the issue loop, not the tensor core, set the pace
     // (316 cycles per K step instead of 152).
+    // Per-item barriers (a1, mma1, a2, mma2, done) complete once per item: parity = local item index & 1.
+    // bar_w1 completes once per agent change: every role counts the changes the same way.
     if (warp == kTmaWarp) {
-        // ---- TMA producer: W1 + parameters, then the W2 chunks through the ring ----
+        // ---- TMA producer: W1 + parameters on an agent change, the W2 chunks through the ring ----
         const bool leader = elect_one();
-        if (leader) {
-            mbar_expect_tx(bar_w1, kW1Bytes + kParamBytes);
-            bulk_g2s(sW1, blob, kW1Bytes, bar_w1);
-            bulk_g2s(sPar, blob + kW1Bytes, kParamBytes, bar_w1);
-        }
-        const uint8_t* w2 = blob + kW1Bytes + kParamBytes;
-        // chunk c -> ring slot c % kStages of EVERY CTA of the cluster: this CTA fetches its 1/CL share
-        constexpr uint32_t kShare = kChunkBytes / CL;
-        static_assert(kShare % 16 == 0, "share must be a 16-byte multiple");
-        const int nchunks = (dbg_mode & 1) ? kStages : kChunks;     // (timing experiment 1: no weight streaming)
-#pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
-            const int slot = c % kStages;
-            if (c >= kStages) mbar_wait(bar_empty(slot), (uint32_t)(c / kStages - 1) & 1u);   // MMAs of the chunk that used the slot are done
-            if (leader) {
-                mbar_expect_tx(bar_full(slot), kChunkBytes);
-                const uint32_t dst = sRing + slot * kChunkBytes + crank * kShare;
-                const uint8_t* src = w2 + (size_t)c * kChunkBytes + crank * kShare;
-                if (CL > 1) bulk_g2s_mc(dst, src, kShare, bar_full(slot), kAllCtas);
-                else bulk_g2s(dst, src, kShare, bar_full(slot));
+        int prev_agent = -1;
+        uint32_t g = 0;                                  // chunks issued so far (ring position)
+        for (int item = item0, it = 0; item < item1; ++item, ++it) {
+            const int agent = item / tiles;
+            const uint8_t* blob = blobs + (size_t)agent * kBlobBytes;
+            if (agent != prev_agent) {
+                // the previous item's epilogues still read the old parameters: wait until they are done
+                if (it > 0) mbar_wait(bar_done, (uint32_t)(it - 1) & 1u);
+                if (leader) {
+                    mbar_expect_tx(bar_w1, kW1Bytes + kParamBytes);
+                    bulk_g2s(sW1, blob, kW1Bytes, bar_w1);
+                    bulk_g2s(sPar, blob + kW1Bytes, kParamBytes, bar_w1);
+                }
+                prev_agent = agent;
             }
-            __syncwarp();
+            const uint8_t* w2 = blob + kW1Bytes + kParamBytes;
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c, ++g) {
+                const uint32_t slot = g % kStages;
+                if (g >= kStages) mbar_wait(bar_empty(slot), (g / kStages - 1u) & 1u);   // MMAs of the chunk that used the slot are done
+                if (leader) {
+                    mbar_expect_tx(bar_full(slot), kChunkBytes);
+                    bulk_g2s(sRing + slot * kChunkBytes, w2 + (size_t)c * kChunkBytes, kChunkBytes, bar_full(slot));
+                }
+                __syncwarp();
+            }
         }
     } else if (warp == kMmaWarp) {
         // ---- MMA issuer ----
         const bool leader = elect_one();
-        // layer 1: [128 x 16] x [16 x 400] -> TMEM columns [0, 400)
-        mbar_wait(bar_a1, 0);
-        if (lane == 0) stamp(8);
-        mbar_wait(bar_w1, 0);
-        if (lane == 0) stamp(9);
-        tc_fence_after();
-        if (leader) {
-            const uint64_t da = umma_desc(sA1, kRows * 16, 128);
-            umma_bf16(tmem + 0, da, umma_desc(sW1, kFc1 * 16, 128), umma_idesc(kRows, 256), 0u);
-            umma_bf16(tmem + 256, da, umma_desc(sW1 + 256 * 16, kFc1 * 16, 128), umma_idesc(kRows, 144), 0u);
-            umma_commit(bar_mma1);
-        }
-        __syncwarp();
-        // layer 2: [128 x 416] x [416 x 304] -> TMEM columns [0, 304) (layer-1 accumulators are dead by then)
-        mbar_wait(bar_a2, 0);
-        if (lane == 0) stamp(10);
-        tc_fence_after();
+        int prev_agent = -1;
+        uint32_t w1_loads = 0, g = 0;
+        const uint64_t da1 = umma_desc(sA1, kRows * 16, 128);
         const uint64_t da0 = umma_desc(sA2, kRows * 16, 128);
         const uint64_t db0 = umma_desc(sRing, kFc2Pad * 16, 128);
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-            constexpr int kAStep = (2 * kRows * 16) >> 4, kBSlot = kChunkBytes >> 4,
-                          kBStep = kStepBytes >> 4;   // 16-byte units of the descriptor start-address field
-            const int st = c % kStages;
-            if (!(dbg_mode & 1) || c < kStages) mbar_wait(bar_full(st), (uint32_t)(c / kStages) & 1u);
+        for (int item = item0, it = 0; item < item1; ++item, ++it) {
+            const int agent = item / tiles;
+            const uint32_t ph = (uint32_t)it & 1u;
+            // layer 1: [128 x 16] x [16 x 400] -> TMEM columns [0, 400). The previous item's epilogue 2 still reads
+            // columns [0, 304): wait until every epilogue thread has left it.
+            if (it > 0) mbar_wait(bar_done, (uint32_t)(it - 1) & 1u);
+            mbar_wait(bar_a1, ph);
+            if (lane == 0 && it == 0) stamp(8);
+            if (agent != prev_agent) {
+                mbar_wait(bar_w1, w1_loads & 1u);
+                ++w1_loads;
+                prev_agent = agent;
+            }
+            if (lane == 0 && it == 0) stamp(9);
             tc_fence_after();
             if (leader) {
+                umma_bf16(tmem + 0, da1, umma_desc(sW1, kFc1 * 16, 128), umma_idesc(kRows, 256), 0u);
+                umma_bf16(tmem + 256, da1, umma_desc(sW1 + 256 * 16, kFc1 * 16, 128), umma_idesc(kRows, 144), 0u);
+                umma_commit(bar_mma1);
+            }
+            __syncwarp();
+            // layer 2: [128 x 416] x [416 x 304] -> TMEM columns [0, 304) (layer-1 accumulators are dead by then)
+            mbar_wait(bar_a2, ph);
+            if (lane == 0 && it == 0) stamp(10);
+            tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < kStepsPerChunk; ++j) {
-                    const int s = c * kStepsPerChunk + j;
-                    const uint64_t da = da0 + (uint64_t)(s * kAStep);          // no carry out of the 14-bit field
-                    const uint64_t db = db0 + (uint64_t)(st * kBSlot + j * kBStep);
-                    const uint32_t acc = s > 0 ? 1u : 0u;
-                    if (!(dbg_mode & 2)) {   // N = 256 + 48 (measured faster than 160 + 144: 171 vs 194 cycles per K step)
+            for (int c = 0; c < kChunks; ++c, ++g) {
+                constexpr int kAStep = (2 * kRows * 16) >> 4, kBSlot = kChunkBytes >> 4,
+                              kBStep = kStepBytes >> 4;   // 16-byte units of the descriptor start-address field
+                const uint32_t st = g % kStages;
+                mbar_wait(bar_full(st), (g / kStages) & 1u);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int j = 0; j < kStepsPerChunk; ++j) {
+                        const int s = c * kStepsPerChunk + j;
+                        const uint64_t da = da0 + (uint64_t)(s * kAStep);          // no carry out of the 14-bit field
+                        const uint64_t db = db0 + (uint64_t)(st * kBSlot + j * kBStep);
+                        const uint32_t acc = s > 0 ? 1u : 0u;
+                        // N = 256 + 48 (measured faster than 160 + 144: 171 vs 194 cycles per K step)
                         umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 256), acc);
                         umma_bf16(tmem + 256, da, db + (256 * 16 >> 4), umma_idesc(kRows, kFc2Pad - 256), acc);
                     }
+                    umma_commit(bar_empty(st));
                 }
-                if (CL > 1) umma_commit_mc(bar_empty(st), kAllCtas);   // slot st is free once EVERY CTA has said so
-                else umma_commit(bar_empty(st));
+                __syncwarp();
             }
+            if (leader) umma_commit(bar_mma2);
             __syncwarp();
+            if (lane == 0 && it == 0) stamp(11);
         }
-        if (leader) umma_commit(bar_mma2);
-        __syncwarp();
-        if (lane == 0) stamp(11);
     } else {
         // ---- epilogue warps: thread = (env row, column group) ----
-        if (cg == 0) {
-            // this row's observation = the layer-1 A operand; the two slots after the inputs are the
-            // constant 1 that multiplies the bias rows of the packed W1
-#pragma unroll
-            for (int i = 0; i < kInPad; ++i)
-                if (i == in_dims || i == in_dims + 1) xin[i] = 1.0f;
-            sts128(sA1 + row * 16, pack_bf16(xin[0], xin[1]), pack_bf16(xin[2], xin[3]), pack_bf16(xin[4], xin[5]),
-                   pack_bf16(xin[6], xin[7]));
-            sts128(sA1 + kRows * 16 + row * 16, pack_bf16(xin[8], xin[9]), pack_bf16(xin[10], xin[11]),
-                   pack_bf16(xin[12], xin[13]), pack_bf16(xin[14], xin[15]));
-            fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(bar_a1);
-            if (threadIdx.x == 0) stamp(2);
-        } else if (cg == 1) {
-            // the bias K step of layer 2: A2[:, 400] = A2[:, 401] = 1, A2[:, 402..415] = 0
-            sts128(sA2 + (kFc1 / 8) * (kRows * 16) + row * 16, pack_bf16(1.0f, 1.0f), 0u, 0u, 0u);
-            sts128(sA2 + (kFc1 / 8 + 1) * (kRows * 16) + row * 16, 0u, 0u, 0u, 0u);
-        }
-
-        mbar_wait(bar_w1, 0);           // fp32 parameters have landed
+        const int q = warp & 3, cg = warp >> 2;
+        const int row = q * 32 + lane;                     // TMEM lane
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         const float* g1 = par;
         const float* be1 = par + kFc1;
         const float* g2 = par + 2 * kFc1;
@@ -414,105 +359,163 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         const float* w3a = g2 + 2 * kFc2Pad;
         const float* w3b = g2 + 3 * kFc2Pad;
         const float* b3 = g2 + 4 * kFc2Pad;
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-
-        // ---- epilogue 1: LayerNorm(400) + ReLU -> bf16 A operand of layer 2 (the bias came with the MMA) ----
         const int c1b = unit_begin(kFc1 / 16, cg) * 16, c1e = unit_begin(kFc1 / 16, cg + 1) * 16;
-        mbar_wait(bar_mma1, 0);
-        tc_fence_after();
-        if (threadIdx.x == 0) stamp(3);
-        float sum = 0.0f, sq = 0.0f;
-        auto stats = [&](int, const uint32_t (&r)[16]) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float v = __uint_as_float(r[i]);
-                sum += v;
-                sq = fmaf(v, v, sq);
-            }
-        };
-        for_each_unit(trow, c1b, c1e, stats);
-        red_stat[cg * kRows + row] = make_float2(sum, sq);
-        epi_sync();
-        if (threadIdx.x == 0) stamp(4);
-        sum = 0.0f;
-        sq = 0.0f;
-#pragma unroll
-        for (int g = 0; g < kColGroups; ++g) {
-            const float2 pr = red_stat[g * kRows + row];
-            sum += pr.x;
-            sq += pr.y;
-        }
-        float mean = sum * (1.0f / kFc1);
-        float rstd = rsqrtf(fmaxf(sq * (1.0f / kFc1) - mean * mean, 0.0f) + 1.0e-5f);
-        float nmr = -mean * rstd;
-        for_each_unit(trow, c1b, c1e, [&](int c0, const uint32_t (&r)[16]) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                v[i] = fmaxf(fmaf(fmaf(__uint_as_float(r[i]), rstd, nmr), g1[c0 + i], be1[c0 + i]), 0.0f);
-            const uint32_t dst = sA2 + (c0 >> 3) * (kRows * 16) + row * 16;
-            sts128(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            sts128(dst + kRows * 16, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                   pack_bf16(v[14], v[15]));
-        });
-        fence_proxy_async();
-        tc_fence_before();              // our tcgen05.ld of columns [0,400) precede the layer-2 MMAs that overwrite them
-        mbar_arrive(bar_a2);
-        if (threadIdx.x == 0) stamp(5);
-
-        // ---- epilogue 2: LayerNorm(300) + ReLU, mu head (300 -> 2), tanh ----
-        // (the four padded columns 300..303 are exactly 0: zero weights, zero bias)
         const int c2b = unit_begin(kFc2Pad / 16, cg) * 16, c2e = unit_begin(kFc2Pad / 16, cg + 1) * 16;
-        mbar_wait(bar_mma2, 0);
-        tc_fence_after();
-        if (threadIdx.x == 0) stamp(6);
-        sum = 0.0f;
-        sq = 0.0f;
-        for_each_unit(trow, c2b, c2e, stats);
-        red_stat[cg * kRows + row] = make_float2(sum, sq);   // (all epilogue-1 reads happened before bar_a2 completed)
-        epi_sync();
-        sum = 0.0f;
-        sq = 0.0f;
-#pragma unroll
-        for (int g = 0; g < kColGroups; ++g) {
-            const float2 pr = red_stat[g * kRows + row];
-            sum += pr.x;
-            sq += pr.y;
+        int prev_agent = -1;
+        uint32_t w1_loads = 0;
+        if (cg == 1) {
+            // the bias K step of layer 2 never changes: A2[:, 400] = A2[:, 401] = 1, A2[:, 402..415] = 0
+            sts128(sA2 + (kFc1 / 8) * (kRows * 16) + row * 16, pack_bf16(1.0f, 1.0f), 0u, 0u, 0u);
+            sts128(sA2 + (kFc1 / 8 + 1) * (kRows * 16) + row * 16, 0u, 0u, 0u, 0u);
         }
-        mean = sum * (1.0f / kFc2);
-        rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean * mean, 0.0f) + 1.0e-5f);
-        nmr = -mean * rstd;
-        float o0 = 0.0f, o1 = 0.0f;
-        for_each_unit(trow, c2b, c2e, [&](int c0, const uint32_t (&r)[16]) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                // padded columns: g2 = be2 = w3 = 0
-                const float yv = fmaxf(fmaf(fmaf(__uint_as_float(r[i]), rstd, nmr), g2[c0 + i], be2[c0 + i]), 0.0f);
-                o0 = fmaf(yv, w3a[c0 + i], o0);
-                o1 = fmaf(yv, w3b[c0 + i], o1);
+        for (int item = item0, it = 0; item < item1; ++item, ++it) {
+            const int agent = item / tiles, tile = item - agent * tiles;
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int env = tile * kRows + row;
+            const bool valid = env < E;
+            const bool first = it == 0 && threadIdx.x == 0;
+            if (cg == 0 && item + 1 < item1) {   // pull the next item's observation row towards L2 while this item computes
+                const int nagent = (item + 1) / tiles, ntile = (item + 1) - nagent * tiles;
+                const int nenv = ntile * kRows + row;
+                if (nenv < E)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(obs + ((size_t)nenv * N + nagent) * in_dims) : "memory");
             }
-        });
-        red_head[cg * kRows + row] = make_float2(o0, o1);
-        epi_sync();
-        if (cg == 0 && valid) {
-            o0 = 0.0f;
-            o1 = 0.0f;
+            if (cg == 0) {
+                // this row's observation = the layer-1 A operand; the two slots after the inputs are the
+                // constant 1 that multiplies the bias rows of the packed W1. (MMA1 of the previous item is long
+                // complete: its accumulators were consumed before this thread got here.)
+                float xin[kInPad];
+#pragma unroll
+                for (int i = 0; i < kInPad; ++i) xin[i] = 0.0f;
+                if (valid) {
+                    const float* src = obs + ((size_t)env * N + agent) * in_dims;
+                    if (in_dims == 12) {
+                        const float4* s4 = reinterpret_cast<const float4*>(src);
+                        const float4 a = s4[0], b = s4[1], c = s4[2];
+                        xin[0] = a.x; xin[1] = a.y; xin[2] = a.z; xin[3] = a.w;
+                        xin[4] = b.x; xin[5] = b.y; xin[6] = b.z; xin[7] = b.w;
+                        xin[8] = c.x; xin[9] = c.y; xin[10] = c.z; xin[11] = c.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kMaxIn; ++i)
+                            if (i < in_dims) xin[i] = src[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kInPad; ++i)
+                    if (i == in_dims || i == in_dims + 1) xin[i] = 1.0f;
+                sts128(sA1 + row * 16, pack_bf16(xin[0], xin[1]), pack_bf16(xin[2], xin[3]), pack_bf16(xin[4], xin[5]),
+                       pack_bf16(xin[6], xin[7]));
+                sts128(sA1 + kRows * 16 + row * 16, pack_bf16(xin[8], xin[9]), pack_bf16(xin[10], xin[11]),
+                       pack_bf16(xin[12], xin[13]), pack_bf16(xin[14], xin[15]));
+                fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(bar_a1);
+                if (first) stamp(2);
+            }
+            if (agent != prev_agent) {
+                mbar_wait(bar_w1, w1_loads & 1u);           // this agent's fp32 parameters have landed
+                ++w1_loads;
+                prev_agent = agent;
+            }
+
+            // ---- epilogue 1: LayerNorm(400) + ReLU -> bf16 A operand of layer 2 (the bias came with the MMA) ----
+            mbar_wait(bar_mma1, ph);
+            tc_fence_after();
+            if (first) stamp(3);
+            float sum = 0.0f, sq = 0.0f;
+            auto stats = [&](int, const uint32_t (&r)[16]) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float v = __uint_as_float(r[i]);
+                    sum += v;
+                    sq = fmaf(v, v, sq);
+                }
+            };
+            for_each_unit(trow, c1b, c1e, stats);
+            red_stat[cg * kRows + row] = make_float2(sum, sq);
+            epi_sync();
+            if (first) stamp(4);
+            sum = 0.0f;
+            sq = 0.0f;
 #pragma unroll
             for (int g = 0; g < kColGroups; ++g) {
-                const float2 pr = red_head[g * kRows + row];
-                o0 += pr.x;
-                o1 += pr.y;
+                const float2 pr = red_stat[g * kRows + row];
+                sum += pr.x;
+                sq += pr.y;
             }
-            float2 a;
-            a.x = tanhf(o0 + b3[0]);
-            a.y = tanhf(o1 + b3[1]);
-            reinterpret_cast<float2*>(out)[(size_t)env * N + agent] = a;
+            float mean = sum * (1.0f / kFc1);
+            float rstd = rsqrtf(fmaxf(sq * (1.0f / kFc1) - mean * mean, 0.0f) + 1.0e-5f);
+            float nmr = -mean * rstd;
+            for_each_unit(trow, c1b, c1e, [&](int c0, const uint32_t (&r)[16]) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    v[i] = fmaxf(fmaf(fmaf(__uint_as_float(r[i]), rstd, nmr), g1[c0 + i], be1[c0 + i]), 0.0f);
+                const uint32_t dst = sA2 + (c0 >> 3) * (kRows * 16) + row * 16;
+                sts128(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                sts128(dst + kRows * 16, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                       pack_bf16(v[14], v[15]));
+            });
+            fence_proxy_async();
+            tc_fence_before();              // our tcgen05.ld of columns [0,400) precede the layer-2 MMAs that overwrite them
+            mbar_arrive(bar_a2);
+            if (first) stamp(5);
+
+            // ---- epilogue 2: LayerNorm(300) + ReLU, mu head (300 -> 2), tanh ----
+            // (the four padded columns 300..303 are exactly 0: zero weights, zero bias)
+            mbar_wait(bar_mma2, ph);
+            tc_fence_after();
+            if (first) stamp(6);
+            sum = 0.0f;
+            sq = 0.0f;
+            for_each_unit(trow, c2b, c2e, stats);
+            red_stat[cg * kRows + row] = make_float2(sum, sq);   // (all epilogue-1 reads happened before bar_a2 completed)
+            epi_sync();
+            sum = 0.0f;
+            sq = 0.0f;
+#pragma unroll
+            for (int g = 0; g < kColGroups; ++g) {
+                const float2 pr = red_stat[g * kRows + row];
+                sum += pr.x;
+                sq += pr.y;
+            }
+            mean = sum * (1.0f / kFc2);
+            rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean * mean, 0.0f) + 1.0e-5f);
+            nmr = -mean * rstd;
+            float o0 = 0.0f, o1 = 0.0f;
+            for_each_unit(trow, c2b, c2e, [&](int c0, const uint32_t (&r)[16]) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    // padded columns: g2 = be2 = w3 = 0
+                    const float yv = fmaxf(fmaf(fmaf(__uint_as_float(r[i]), rstd, nmr), g2[c0 + i], be2[c0 + i]), 0.0f);
+                    o0 = fmaf(yv, w3a[c0 + i], o0);
+                    o1 = fmaf(yv, w3b[c0 + i], o1);
+                }
+            });
+            red_head[cg * kRows + row] = make_float2(o0, o1);
+            epi_sync();
+            if (cg == 0 && valid) {
+                o0 = 0.0f;
+                o1 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < kColGroups; ++g) {
+                    const float2 pr = red_head[g * kRows + row];
+                    o0 += pr.x;
+                    o1 += pr.y;
+                }
+                float2 a;
+                a.x = tanhf(o0 + b3[0]);
+                a.y = tanhf(o1 + b3[1]);
+                reinterpret_cast<float2*>(out)[(size_t)env * N + agent] = a;
+            }
+            // this item's TMEM reads and parameter reads are over: the next layer-1 MMAs / parameter loads may go
+            tc_fence_before();
+            mbar_arrive(bar_done);
+            if (first) stamp(7);
         }
     }
-    if (threadIdx.x == 0) stamp(7);
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into this CTA
     if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
@@ -607,74 +610,58 @@ cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs,
     return cudaGetLastError();
 }
 
-template <int CL>
-static cudaError_t launch_actor_forward_cl(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
-                                           cudaStream_t s) {
-    static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel<CL>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, actor::kSmemBytes);
+cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
+                                 cudaStream_t s) {
+    static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         actor::kSmemBytes);
     if (configured != cudaSuccess) return configured;
+    static const int sm_count = [] {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
     const int tiles = (E + actor::kRows - 1) / actor::kRows;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)N, (unsigned)((tiles + CL - 1) / CL * CL));   // surplus tiles are fully masked
-    cfg.blockDim = dim3(actor::kThreads);
-    cfg.dynamicSmemBytes = actor::kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = CL;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // FLOCK_ACTOR_TIMING=1 (developer knob): the first launch records clock64 at the phase boundaries of
-    // every CTA, synchronises and prints the mean phase lengths to stderr
+    const int total = tiles * N;
+    const int per_cta = (total + sm_count - 1) / sm_count;          // contiguous run of items per CTA
+    const int grid = (total + per_cta - 1) / per_cta;
+    const uint8_t* bl = static_cast<const uint8_t*>(blobs);
+    // FLOCK_ACTOR_TIMING=1 (developer knob): the first launch records clock64 at the phase boundaries of the first
+    // item of every CTA, synchronises and prints the mean phase lengths to stderr.
     static bool timing = getenv("FLOCK_ACTOR_TIMING") != nullptr;
-    // FLOCK_ACTOR_EXPERIMENT (developer knob, RESULTS INVALID when set): 1 = no weight streaming after the
-    // first ring fill (pure MMA rate), 2 = weight streaming without the MMAs
-    static const int dbg_mode = getenv("FLOCK_ACTOR_EXPERIMENT") ? atoi(getenv("FLOCK_ACTOR_EXPERIMENT")) & 3 : 0;
-    long long* dbg = nullptr;
     if (timing) {
         timing = false;
-        const size_t ctas = (size_t)cfg.gridDim.x * cfg.gridDim.y;
-        if (cudaMalloc(&dbg, ctas * 16 * sizeof(long long)) == cudaSuccess) {
-            cudaMemsetAsync(dbg, 0, ctas * 16 * sizeof(long long), s);
-            cudaError_t e = cudaLaunchKernelEx(&cfg, actor::flock_actor_kernel<CL>, static_cast<const uint8_t*>(blobs), obs,
-                                               actions, E, N, in_dims, dbg, dbg_mode);
+        long long* dbg = nullptr;
+        if (cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)) == cudaSuccess) {
+            cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), s);
+            actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(bl, obs, actions, E, N, in_dims, tiles,
+                                                                                   per_cta, dbg);
+            cudaError_t e = cudaGetLastError();
             cudaStreamSynchronize(s);
-            long long* h = static_cast<long long*>(malloc(ctas * 16 * sizeof(long long)));
-            cudaMemcpy(h, dbg, ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+            long long* h = static_cast<long long*>(malloc((size_t)grid * 16 * sizeof(long long)));
+            cudaMemcpy(h, dbg, (size_t)grid * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
             static const char* names[12] = {"setup (alloc, barrier init, sync)", "obs -> A1", "wait MMA1", "epilogue-1 pass 1 + sync",
-                                            "epilogue-1 pass 2 -> A2", "wait MMA2", "epilogue 2", "teardown sync + dealloc",
-                                            "[mma thread] start -> A1 ready", "[mma thread] W1 ready", "[mma thread] -> A2 ready",
-                                            "[mma thread] layer-2 issue loop"};
+                                            "epilogue-1 pass 2 -> A2", "wait MMA2", "epilogue 2", "items 2.. + teardown",
+                                            "[mma warp] start -> A1 ready", "[mma warp] W1 ready", "[mma warp] -> A2 ready",
+                                            "[mma warp] layer-2 issue loop"};
             static const int from[12] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 8, 9, 10}, to[12] = {1, 2, 3, 4, 5, 6, 7, 12, 8, 9, 10, 11};
-            fprintf(stderr, "flock_actor_kernel<%d> phase means over %zu CTAs (SM clocks):\n", CL, ctas);
+            fprintf(stderr, "flock_actor_kernel: %d CTAs x %d items, phase means of the first item (SM clocks):\n", grid, per_cta);
             for (int ph = 0; ph < 12; ++ph) {
                 double acc = 0;
-                for (size_t c = 0; c < ctas; ++c) acc += (double)(h[c * 16 + to[ph]] - h[c * 16 + from[ph]]);
-                fprintf(stderr, "  %-38s %9.0f\n", names[ph], acc / ctas);
+                for (int c = 0; c < grid; ++c) acc += (double)(h[c * 16 + to[ph]] - h[c * 16 + from[ph]]);
+                fprintf(stderr, "  %-38s %9.0f\n", names[ph], acc / grid);
             }
             double tot = 0;
-            for (size_t c = 0; c < ctas; ++c) tot += (double)(h[c * 16 + 12] - h[c * 16 + 0]);
-            fprintf(stderr, "  %-38s %9.0f\n", "CTA total", tot / ctas);
+            for (int c = 0; c < grid; ++c) tot += (double)(h[c * 16 + 12] - h[c * 16 + 0]);
+            fprintf(stderr, "  %-38s %9.0f\n", "CTA total (all items)", tot / grid);
             free(h);
             cudaFree(dbg);
             return e;
         }
     }
-    return cudaLaunchKernelEx(&cfg, actor::flock_actor_kernel<CL>, static_cast<const uint8_t*>(blobs), obs, actions, E, N,
-                              in_dims, dbg, dbg_mode);
-}
-
-cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
-                                 cudaStream_t s) {
-    // FLOCK_ACTOR_CLUSTER=2 runs CTAs as clusters of two that share every W2 chunk by TMA multicast (half the
-    // L2 -> SM weight reads). Correct and tested, but measured slower on B200 at 4096 x 32 (84.6 vs 74.6 us): the
-    // layer-2 phase is bound by shared-memory bandwidth (operand reads + TMA writes), not by L2, and the
-    // cluster barriers add ~2.5k cycles per CTA. Default: no clusters.
-    const char* v = getenv("FLOCK_ACTOR_CLUSTER");
-    if (v != nullptr && v[0] == '2' && E > actor::kRows) return launch_actor_forward_cl<2>(blobs, obs, actions, E, N, in_dims, s);
-    return launch_actor_forward_cl<1>(blobs, obs, actions, E, N, in_dims, s);
+    actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(bl, obs, actions, E, N, in_dims, tiles, per_cta,
+                                                                           nullptr);
+    return cudaGetLastError();
 }
 
 }  // namespace flock

@@ -90,22 +90,6 @@ def test_fused_actor_drives_the_env_and_repacks_after_an_update():
     assert torch.allclose(after, -before, atol=1e-6)             # tanh is odd: the new parameters are in use
 
 
-def test_fused_actor_cluster_multicast_variant_gives_the_same_result(monkeypatch):
-    """FLOCK_ACTOR_CLUSTER=2: clusters of two CTAs share the W2 chunks by TMA multicast (odd tile count:
-    one surplus, fully masked CTA). Same arithmetic in the same order -> identical bits."""
-    dev = torch.device("cuda:0")
-    E, N = 128 * 5 + 17, 6
-    a = _actors(N, 12, 21, dev)
-    torch.manual_seed(1)
-    obs = torch.rand(E, N, 12, device=dev) * 7.0
-    monkeypatch.delenv("FLOCK_ACTOR_CLUSTER", raising=False)
-    plain = a.forward_fused(obs).clone()
-    monkeypatch.setenv("FLOCK_ACTOR_CLUSTER", "2")
-    clustered = a.forward_fused(obs).clone()
-    torch.cuda.synchronize()
-    assert torch.equal(plain, clustered)
-
-
 def test_fused_actor_rejects_unsupported_shapes():
     from marl_range_flocking_b200 import _lib
     from marl_range_flocking_b200.policies import BatchedActors
