@@ -46,8 +46,10 @@ constexpr int kChunks = kSteps2 / kStepsPerChunk;
 constexpr int kChunkBytes = kStepsPerChunk * kStepBytes;
 constexpr int kStages = 4;                   // W2 ring depth (chunks)
 static_assert(kSteps2 % kStepsPerChunk == 0, "whole chunks");
-// fp32 parameters: g1 be1 [400] | g2 be2 [304] | w3[:,0] w3[:,1] [304] | b3[2] + 2 pad
-constexpr int kParamFloats = 2 * kFc1 + 4 * kFc2Pad + 4;
+// fp32 parameters: g1 be1 [400] | g2 be2 [304] | w3[:,0] w3[:,1] [304] | b3[2] + 2 pad | Gram matrix of W1 [16][16] | row sums [16]
+constexpr int kGramOff = 2 * kFc1 + 4 * kFc2Pad + 4;
+constexpr int kSumOff = kGramOff + kInPad * kInPad;          // + row sums of the packed W1 over the outputs [16]
+constexpr int kParamFloats = kSumOff + kInPad;
 constexpr int kParamBytes = kParamFloats * 4;
 constexpr int kBlobBytes = kW1Bytes + kParamBytes + kSteps2 * kStepBytes;
 static_assert(kParamBytes % 16 == 0 && kBlobBytes % 16 == 0, "bulk copies move 16-byte units");
@@ -64,7 +66,7 @@ constexpr int kOffBar = kOffRing + kStages * kChunkBytes;
 constexpr int kNumBars = 2 * kStages + 6;
 constexpr int kOffRed = kOffBar + kNumBars * 8 + 16;       // + tmem pointer; then row-statistic / head partials
 constexpr int kColGroups = 4;
-constexpr int kRedBytes = 2 * kColGroups * kRows * 8;       // two float2 [4][128] buffers
+constexpr int kRedBytes = 2 * kColGroups * kRows * 8 + kRows * 8;   // two float2 [4][128] buffers + (rstd, -mean rstd) of layer 1 [128]
 constexpr int kSmemBytes = kOffRed + kRedBytes + 128;       // + alignment slack
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -226,6 +228,7 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
     const float* par = reinterpret_cast<const float*>(sm + kOffPar);
     float2* red_stat = reinterpret_cast<float2*>(sm + kOffRed);               // [4][128] (sum, sum of squares)
     float2* red_head = red_stat + kColGroups * kRows;                          // [4][128] (o0, o1)
+    float2* row_stat = red_head + kColGroups * kRows;                          // [128] layer-1 (1/sigma, -mean/sigma), from the Gram matrix
 
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -411,9 +414,37 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                 fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
                 mbar_arrive(bar_a1);
                 if (first) stamp(2);
+                if (agent != prev_agent) mbar_wait(bar_w1, w1_loads & 1u);   // this agent's fp32 parameters have landed
+                // Layer-1 LayerNorm statistics without touching the accumulators: the packed weights are centred
+                // (row mean == 0) and sum_n h_n^2 = x^T G x with G the Gram matrix of the packed weights and x the
+                // bf16-rounded inputs the MMA sees. Runs while the MMA is in flight.
+                const float* G = par + kGramOff;
+                float xr[kInPad];
+#pragma unroll
+                for (int i = 0; i < kInPad; ++i) xr[i] = __bfloat162float(__float2bfloat16_rn(xin[i]));
+                float ss = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kInPad; ++i) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int jb = (i >> 2) << 2; jb < kInPad; jb += 4) {     // upper triangle, off-diagonals pre-doubled
+                        const float4 gq = *reinterpret_cast<const float4*>(G + i * kInPad + jb);
+                        if (jb + 0 >= i) acc = fmaf(gq.x, xr[jb + 0], acc);
+                        if (jb + 1 >= i) acc = fmaf(gq.y, xr[jb + 1], acc);
+                        if (jb + 2 >= i) acc = fmaf(gq.z, xr[jb + 2], acc);
+                        if (jb + 3 >= i) acc = fmaf(gq.w, xr[jb + 3], acc);
+                    }
+                    ss = fmaf(xr[i], acc, ss);
+                }
+                float rsum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kInPad; ++i) rsum = fmaf(xr[i], par[kSumOff + i], rsum);
+                const float mean1 = rsum * (1.0f / kFc1);      // residue of the centring after bf16 rounding (tiny)
+                const float rstd1 = rsqrtf(fmaxf(ss * (1.0f / kFc1) - mean1 * mean1, 0.0f) + 1.0e-5f);
+                row_stat[row] = make_float2(rstd1, -mean1 * rstd1);
             }
             if (agent != prev_agent) {
-                mbar_wait(bar_w1, w1_loads & 1u);           // this agent's fp32 parameters have landed
+                if (cg != 0) mbar_wait(bar_w1, w1_loads & 1u);       // this agent's fp32 parameters have landed
                 ++w1_loads;
                 prev_agent = agent;
             }
@@ -422,30 +453,9 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             mbar_wait(bar_mma1, ph);
             tc_fence_after();
             if (first) stamp(3);
-            float sum = 0.0f, sq = 0.0f;
-            auto stats = [&](int, const uint32_t (&r)[16]) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float v = __uint_as_float(r[i]);
-                    sum += v;
-                    sq = fmaf(v, v, sq);
-                }
-            };
-            for_each_unit(trow, c1b, c1e, stats);
-            red_stat[cg * kRows + row] = make_float2(sum, sq);
-            epi_sync();
+            epi_sync();                     // row_rstd of every row is written (and the previous item's reads are over)
             if (first) stamp(4);
-            sum = 0.0f;
-            sq = 0.0f;
-#pragma unroll
-            for (int g = 0; g < kColGroups; ++g) {
-                const float2 pr = red_stat[g * kRows + row];
-                sum += pr.x;
-                sq += pr.y;
-            }
-            float mean = sum * (1.0f / kFc1);
-            float rstd = rsqrtf(fmaxf(sq * (1.0f / kFc1) - mean * mean, 0.0f) + 1.0e-5f);
-            float nmr = -mean * rstd;
+            float rstd = row_stat[row].x, nmr = row_stat[row].y;
             for_each_unit(trow, c1b, c1e, [&](int c0, const uint32_t (&r)[16]) {
                 float v[16];
 #pragma unroll
@@ -466,22 +476,28 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             mbar_wait(bar_mma2, ph);
             tc_fence_after();
             if (first) stamp(6);
-            sum = 0.0f;
-            sq = 0.0f;
-            for_each_unit(trow, c2b, c2e, stats);
-            red_stat[cg * kRows + row] = make_float2(sum, sq);   // (all epilogue-1 reads happened before bar_a2 completed)
+            // centred W2 and bias: the row mean is only the rounding residue, and the MMA delivers its 300-fold in the
+            // padding column 300 (see flock_actor_pack_kernel) -- one pass for the sum of squares is all that is left
+            float sq = 0.0f, s300 = 0.0f;
+            for_each_unit(trow, c2b, c2e, [&](int, const uint32_t (&r)[16]) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sq = fmaf(__uint_as_float(r[i]), __uint_as_float(r[i]), sq);
+            });
+            if (cg == kColGroups - 1) {     // this group's last unit holds column 300: take it out of the squares
+                uint32_t r[16];
+                tmem_ld16_issue(trow + (kFc2Pad - 16), r);
+                tmem_ld16_wait(r);
+                s300 = __uint_as_float(r[kFc2 - (kFc2Pad - 16)]);
+                sq = fmaf(-s300, s300, sq);
+            }
+            red_stat[cg * kRows + row] = make_float2(sq, s300);   // (all epilogue-1 reads happened before bar_a2 completed)
             epi_sync();
-            sum = 0.0f;
             sq = 0.0f;
 #pragma unroll
-            for (int g = 0; g < kColGroups; ++g) {
-                const float2 pr = red_stat[g * kRows + row];
-                sum += pr.x;
-                sq += pr.y;
-            }
-            mean = sum * (1.0f / kFc2);
-            rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean * mean, 0.0f) + 1.0e-5f);
-            nmr = -mean * rstd;
+            for (int g = 0; g < kColGroups; ++g) sq += red_stat[g * kRows + row].x;
+            const float mean2 = red_stat[(kColGroups - 1) * kRows + row].y * (1.0f / kFc2);
+            rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean2 * mean2, 0.0f) + 1.0e-5f);
+            nmr = -mean2 * rstd;
             float o0 = 0.0f, o1 = 0.0f;
             for_each_unit(trow, c2b, c2e, [&](int c0, const uint32_t (&r)[16]) {
 #pragma unroll
@@ -528,9 +544,61 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
 struct PackArgs {
     const float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *w3, *b3;
     int agents, in_dims;
+    const float* means;      // per agent: column means of W1 [16] | mean(b1) | column means of W2 [400] | mean(b2), see prep
 };
+constexpr int kMeanFloats = kInPad + 1 + kFc1 + 1;
 
 __device__ __forceinline__ float bf16_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// LayerNorm subtracts the row mean of h = x W + b; that mean is x (W 1/n) + mean(b), linear in the weights, so it
+// is removed ONCE at pack time by centring every weight row (and the bias) over the output features: the MMAs
+// then deliver mean-free pre-activations and the epilogues only need the sum of squares.
+// Pack step 1: the means. One CTA per agent, thread t owns input row t.
+__global__ void __launch_bounds__(512) flock_actor_prep_kernel(PackArgs a, float* __restrict__ means) {
+    const int ag = blockIdx.x, t = threadIdx.x;
+    float* m = means + (size_t)ag * kMeanFloats;
+    if (t < kInPad) {
+        float acc = 0.0f;
+        if (t < a.in_dims)
+            for (int n = 0; n < kFc1; ++n) acc += a.w1[((size_t)ag * a.in_dims + t) * kFc1 + n];
+        m[t] = acc * (1.0f / kFc1);
+    } else if (t == kInPad) {
+        float acc = 0.0f;
+        for (int n = 0; n < kFc1; ++n) acc += a.b1[(size_t)ag * kFc1 + n];
+        m[kInPad] = acc * (1.0f / kFc1);
+    } else if (t >= 32 && t < 32 + kFc1) {
+        const int k = t - 32;
+        float acc = 0.0f;
+        for (int n = 0; n < kFc2; ++n) acc += a.w2[((size_t)ag * kFc1 + k) * kFc2 + n];
+        m[kInPad + 1 + k] = acc * (1.0f / kFc2);
+    } else if (t == 32 + kFc1) {
+        float acc = 0.0f;
+        for (int n = 0; n < kFc2; ++n) acc += a.b2[(size_t)ag * kFc2 + n];
+        m[kInPad + 1 + kFc1] = acc * (1.0f / kFc2);
+    }
+}
+
+// Pack step 3 (after the images exist): Gram matrix of the packed, bf16-rounded, centred layer-1 weights over the
+// 400 outputs, G[i][j] = sum_n W[i][n] W[j][n]. With it the layer-1 row variance is the quadratic form x^T G x / 400
+// of the 16 (bf16-rounded) inputs -- known before the accumulators are read, so epilogue 1 needs no statistics
+// pass. Stored upper-triangular with doubled off-diagonal entries. One CTA per agent, thread = (i, j).
+__global__ void __launch_bounds__(kInPad * kInPad) flock_actor_gram_kernel(uint8_t* __restrict__ blobs) {
+    const int ag = blockIdx.x, i = threadIdx.x / kInPad, j = threadIdx.x % kInPad;
+    uint8_t* blob = blobs + (size_t)ag * kBlobBytes;
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(blob);       // W1 image: [k-group][n][8]
+    float acc = 0.0f;
+    if (j >= i)
+        for (int n = 0; n < kFc1; ++n)
+            acc = fmaf(__bfloat162float(w[((i >> 3) * kFc1 + n) * 8 + (i & 7)]),
+                       __bfloat162float(w[((j >> 3) * kFc1 + n) * 8 + (j & 7)]), acc);
+    float* par = reinterpret_cast<float*>(blob + kW1Bytes);
+    par[kGramOff + i * kInPad + j] = j > i ? 2.0f * acc : (j == i ? acc : 0.0f);
+    if (j == 0) {   // what is left of the row mean after rounding the centred weights to bf16: x . rowsum / 400
+        float rs = 0.0f;
+        for (int n = 0; n < kFc1; ++n) rs += __bfloat162float(w[((i >> 3) * kFc1 + n) * 8 + (i & 7)]);
+        par[kSumOff + i] = rs;
+    }
+}
 
 __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs) {
     const int units = kBlobBytes / 16;
@@ -542,10 +610,11 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
     if (u < kW1Bytes / 16) {                       // W1 image: [k-group][n] x 8 bf16; K slots in_dims, in_dims+1 = bias hi, lo
         const int kg = u / kFc1, n = u % kFc1;
         float v[8];
+        const float* mm = a.means + (size_t)ag * kMeanFloats;
         for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            const float bias = a.b1[(size_t)ag * kFc1 + n];
-            v[j] = k < a.in_dims ? a.w1[((size_t)ag * a.in_dims + k) * kFc1 + n]
+            const float bias = a.b1[(size_t)ag * kFc1 + n] - mm[kInPad];
+            v[j] = k < a.in_dims ? a.w1[((size_t)ag * a.in_dims + k) * kFc1 + n] - mm[k]
                  : (k == a.in_dims ? bias : (k == a.in_dims + 1 ? bias - bf16_hi(bias) : 0.0f));
         }
         o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -555,7 +624,9 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
         for (int j = 0; j < 4; ++j) {
             int f = f0 + j;
             float x = 0.0f;
-            if (f < 2 * kFc1) {
+            if (f >= kGramOff) {
+                x = 0.0f;                                   // Gram matrix, row sums: written by flock_actor_gram_kernel
+            } else if (f < 2 * kFc1) {
                 const float* src = f < kFc1 ? a.g1 : a.be1;
                 x = src[(size_t)ag * kFc1 + f % kFc1];
             } else {
@@ -581,10 +652,20 @@ __global__ void flock_actor_pack_kernel(PackArgs a, uint8_t* __restrict__ blobs)
         for (int j = 0; j < 8; ++j) {
             const int k = s * 16 + kg * 8 + j;
             float x = 0.0f;
+            const float* mm = a.means + (size_t)ag * kMeanFloats + kInPad + 1;
+            auto entry = [&](int kk, int nn) {     // centred layer-2 weight / bias-hi / bias-lo entry (kk, nn), nn < 300
+                const float bias = a.b2[(size_t)ag * kFc2 + nn] - mm[kFc1];
+                if (kk < kFc1) return a.w2[((size_t)ag * kFc1 + kk) * kFc2 + nn] - mm[kk];
+                if (kk == kFc1) return bias;
+                if (kk == kFc1 + 1) return bias - bf16_hi(bias);
+                return 0.0f;
+            };
             if (n < kFc2) {
-                if (k < kFc1) x = a.w2[((size_t)ag * kFc1 + k) * kFc2 + n];
-                else if (k == kFc1) x = a.b2[(size_t)ag * kFc2 + n];
-                else if (k == kFc1 + 1) x = a.b2[(size_t)ag * kFc2 + n] - bf16_hi(a.b2[(size_t)ag * kFc2 + n]);
+                x = entry(k, n);
+            } else if (n == kFc2 && k <= kFc1 + 1) {
+                // output column 300 (padding) = row sum of the ROUNDED entries: the MMA then delivers the exact sum of
+                // the 300 real pre-activations of each row, i.e. what is left of the row mean after rounding
+                for (int nn = 0; nn < kFc2; ++nn) x += bf16_hi(entry(k, nn));
             }
             v[j] = x;
         }
@@ -604,10 +685,17 @@ void actor_dims(int* fc1, int* fc2, int* n_actions) {
 }
 
 cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s) {
-    actor::PackArgs a{ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6], ptrs[7], ptrs[8], ptrs[9], agents, in_dims};
+    float* means = nullptr;      // stream-ordered scratch for the centring means
+    cudaError_t err = cudaMallocAsync(&means, (size_t)agents * actor::kMeanFloats * sizeof(float), s);
+    if (err != cudaSuccess) return err;
+    actor::PackArgs a{ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6], ptrs[7], ptrs[8], ptrs[9], agents, in_dims, means};
+    actor::flock_actor_prep_kernel<<<agents, 512, 0, s>>>(a, means);
     const size_t total = (size_t)(actor::kBlobBytes / 16) * agents;
     actor::flock_actor_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, static_cast<uint8_t*>(blobs));
-    return cudaGetLastError();
+    actor::flock_actor_gram_kernel<<<agents, actor::kInPad * actor::kInPad, 0, s>>>(static_cast<uint8_t*>(blobs));
+    err = cudaGetLastError();
+    cudaFreeAsync(means, s);
+    return err;
 }
 
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,

@@ -32,12 +32,15 @@ def _actors(N, in_dims, seed, device):
 
 
 def _emulate_bf16_operands(a, obs):
+    """The kernel's arithmetic in fp32: weights and biases centred over the output features at pack time (LayerNorm
+    removes that mean anyway), matrix operands rounded to bf16, everything else fp32."""
     r = lambda t: t.bfloat16().float()
+    c = lambda t: t - t.mean(dim=2, keepdim=True)
     E, N = obs.shape[:2]
     x = r(obs.reshape(E, N, -1).transpose(0, 1))
-    x = torch.baddbmm(a.b1, x, r(a.w1))
+    x = torch.baddbmm(c(a.b1), x, r(c(a.w1)))
     x = F.relu(F.layer_norm(x, x.shape[-1:]) * a.g1 + a.be1)
-    x = torch.baddbmm(a.b2, r(x), r(a.w2))
+    x = torch.baddbmm(c(a.b2), r(x), r(c(a.w2)))
     x = F.relu(F.layer_norm(x, x.shape[-1:]) * a.g2 + a.be2)
     return torch.tanh(torch.baddbmm(a.b3, x, a.w3)).transpose(0, 1).contiguous()
 
