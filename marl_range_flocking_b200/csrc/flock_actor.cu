@@ -63,7 +63,7 @@ constexpr int kOffW1 = kOffA1 + kA1Bytes;
 constexpr int kOffPar = kOffW1 + kW1Bytes;
 constexpr int kOffRing = (kOffPar + kParamBytes + 127) & ~127;
 constexpr int kOffBar = kOffRing + kStages * kChunkBytes;
-constexpr int kNumBars = 2 * kStages + 6;
+constexpr int kNumBars = 2 * kStages + 7;
 constexpr int kOffRed = kOffBar + kNumBars * 8 + 16;       // + tmem pointer; then row-statistic / head partials
 constexpr int kColGroups = 4;
 constexpr int kRedBytes = 2 * kColGroups * kRows * 8 + kRows * 8;   // two float2 [4][128] buffers + (rstd, -mean rstd) of layer 1 [128]
@@ -76,6 +76,13 @@ constexpr int kMmaWarp = kEpiWarps;           // warp 16: TMEM allocation + MMA 
 constexpr int kTmaWarp = kEpiWarps + 1;       // warp 17: TMA producer (one thread)
 constexpr int kThreads = kEpiThreads + 64;
 constexpr int kTmemCols = 512;
+// Layer-1 accumulators live in TMEM columns [0, 400), layer-2 accumulators in [208, 512). Epilogue 1 first consumes
+// the layer-1 columns [192, 400) (phase A), which frees everything the layer-2 accumulators overlap, so the layer-2
+// MMAs over K steps 12..25 run while phase B turns columns [0, 192) into K steps 0..11.
+constexpr int kL2Col = 208;
+constexpr int kPhaseAUnit = 12;                       // first layer-1 column unit (16 columns) of phase A
+constexpr int kFirstChunk = kPhaseAUnit / kStepsPerChunk;   // W2 chunks are streamed / multiplied in the order 6..12, 0..5
+static_assert(kPhaseAUnit % kStepsPerChunk == 0 && kPhaseAUnit * 16 <= kL2Col && kL2Col + kFc2Pad <= kTmemCols, "phase split");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -223,7 +230,7 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
     auto bar_full = [&](int s) { return sBar + 8u * s; };
     auto bar_empty = [&](int s) { return sBar + 8u * (kStages + s); };
     const uint32_t bar_w1 = sBar + 8u * (2 * kStages), bar_a1 = bar_w1 + 8u, bar_mma1 = bar_w1 + 16u, bar_a2 = bar_w1 + 24u,
-                   bar_mma2 = bar_w1 + 32u, bar_done = bar_w1 + 40u;
+                   bar_mma2 = bar_w1 + 32u, bar_done = bar_w1 + 40u, bar_a2b = bar_w1 + 48u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + kNumBars * 8);
     const float* par = reinterpret_cast<const float*>(sm + kOffPar);
     float2* red_stat = reinterpret_cast<float2*>(sm + kOffRed);               // [4][128] (sum, sum of squares)
@@ -246,6 +253,7 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         mbar_init(bar_a2, kEpiThreads);
         mbar_init(bar_mma2, 1);
         mbar_init(bar_done, kEpiThreads);
+        mbar_init(bar_a2b, kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -281,7 +289,8 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             }
             const uint8_t* w2 = blob + kW1Bytes + kParamBytes;
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c, ++g) {
+            for (int idx = 0; idx < kChunks; ++idx, ++g) {
+                const int c = (idx + kFirstChunk) % kChunks;     // the order the MMA warp consumes them in
                 const uint32_t slot = g % kStages;
                 if (g >= kStages) mbar_wait(bar_empty(slot), (g / kStages - 1u) & 1u);   // MMAs of the chunk that used the slot are done
                 if (leader) {
@@ -320,14 +329,21 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                 umma_commit(bar_mma1);
             }
             __syncwarp();
-            // layer 2: [128 x 416] x [416 x 304] -> TMEM columns [0, 304) (layer-1 accumulators are dead by then)
+            // layer 2: [128 x 416] x [416 x 304] -> TMEM columns [208, 512). K steps 12..25 first: their A operand
+            // (phase A of epilogue 1) is ready early and the accumulators only overlap layer-1 columns that phase A
+            // has consumed; K steps 0..11 follow when phase B is done.
             mbar_wait(bar_a2, ph);
             if (lane == 0 && it == 0) stamp(10);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < kChunks; ++c, ++g) {
+            for (int idx = 0; idx < kChunks; ++idx, ++g) {
                 constexpr int kAStep = (2 * kRows * 16) >> 4, kBSlot = kChunkBytes >> 4,
                               kBStep = kStepBytes >> 4;   // 16-byte units of the descriptor start-address field
+                const int c = (idx + kFirstChunk) % kChunks;
+                if (c == 0) {                              // first chunk of phase B
+                    mbar_wait(bar_a2b, ph);
+                    tc_fence_after();
+                }
                 const uint32_t st = g % kStages;
                 mbar_wait(bar_full(st), (g / kStages) & 1u);
                 tc_fence_after();
@@ -337,10 +353,10 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                         const int s = c * kStepsPerChunk + j;
                         const uint64_t da = da0 + (uint64_t)(s * kAStep);          // no carry out of the 14-bit field
                         const uint64_t db = db0 + (uint64_t)(st * kBSlot + j * kBStep);
-                        const uint32_t acc = s > 0 ? 1u : 0u;
+                        const uint32_t acc = (idx > 0 || j > 0) ? 1u : 0u;
                         // N = 256 + 48 (measured faster than 160 + 144: 171 vs 194 cycles per K step)
-                        umma_bf16(tmem + 0, da, db, umma_idesc(kRows, 256), acc);
-                        umma_bf16(tmem + 256, da, db + (256 * 16 >> 4), umma_idesc(kRows, kFc2Pad - 256), acc);
+                        umma_bf16(tmem + kL2Col, da, db, umma_idesc(kRows, 256), acc);
+                        umma_bf16(tmem + kL2Col + 256, da, db + (256 * 16 >> 4), umma_idesc(kRows, kFc2Pad - 256), acc);
                     }
                     umma_commit(bar_empty(st));
                 }
@@ -362,8 +378,12 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         const float* w3a = g2 + 2 * kFc2Pad;
         const float* w3b = g2 + 3 * kFc2Pad;
         const float* b3 = g2 + 4 * kFc2Pad;
-        const int c1b = unit_begin(kFc1 / 16, cg) * 16, c1e = unit_begin(kFc1 / 16, cg + 1) * 16;
+        // layer-1 columns of this column group: phase A = units [12, 25), phase B = units [0, 12)
+        const int cab = (kPhaseAUnit + unit_begin(kFc1 / 16 - kPhaseAUnit, cg)) * 16,
+                  cae = (kPhaseAUnit + unit_begin(kFc1 / 16 - kPhaseAUnit, cg + 1)) * 16;
+        const int cbb = unit_begin(kPhaseAUnit, cg) * 16, cbe = unit_begin(kPhaseAUnit, cg + 1) * 16;
         const int c2b = unit_begin(kFc2Pad / 16, cg) * 16, c2e = unit_begin(kFc2Pad / 16, cg + 1) * 16;
+        const uint32_t trow2 = trow + kL2Col;                  // layer-2 accumulators
         int prev_agent = -1;
         uint32_t w1_loads = 0;
         if (cg == 1) {
@@ -456,7 +476,7 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             epi_sync();                     // row_rstd of every row is written (and the previous item's reads are over)
             if (first) stamp(4);
             float rstd = row_stat[row].x, nmr = row_stat[row].y;
-            for_each_unit(trow, c1b, c1e, [&](int c0, const uint32_t (&r)[16]) {
+            auto norm_unit = [&](int c0, const uint32_t (&r)[16]) {
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -465,10 +485,15 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                 sts128(dst, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 sts128(dst + kRows * 16, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
                        pack_bf16(v[14], v[15]));
-            });
+            };
+            for_each_unit(trow, cab, cae, norm_unit);       // phase A: columns [192, 400) -> K steps 12..24
             fence_proxy_async();
-            tc_fence_before();              // our tcgen05.ld of columns [0,400) precede the layer-2 MMAs that overwrite them
+            tc_fence_before();              // our tcgen05.ld of columns [192,400) precede the layer-2 MMAs that overwrite them
             mbar_arrive(bar_a2);
+            for_each_unit(trow, cbb, cbe, norm_unit);       // phase B: columns [0, 192) -> K steps 0..11, under the first MMAs
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_a2b);
             if (first) stamp(5);
 
             // ---- epilogue 2: LayerNorm(300) + ReLU, mu head (300 -> 2), tanh ----
@@ -479,13 +504,13 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             // centred W2 and bias: the row mean is only the rounding residue, and the MMA delivers its 300-fold in the
             // padding column 300 (see flock_actor_pack_kernel) -- one pass for the sum of squares is all that is left
             float sq = 0.0f, s300 = 0.0f;
-            for_each_unit(trow, c2b, c2e, [&](int, const uint32_t (&r)[16]) {
+            for_each_unit(trow2, c2b, c2e, [&](int, const uint32_t (&r)[16]) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) sq = fmaf(__uint_as_float(r[i]), __uint_as_float(r[i]), sq);
             });
             if (cg == kColGroups - 1) {     // this group's last unit holds column 300: take it out of the squares
                 uint32_t r[16];
-                tmem_ld16_issue(trow + (kFc2Pad - 16), r);
+                tmem_ld16_issue(trow2 + (kFc2Pad - 16), r);
                 tmem_ld16_wait(r);
                 s300 = __uint_as_float(r[kFc2 - (kFc2Pad - 16)]);
                 sq = fmaf(-s300, s300, sq);
@@ -499,7 +524,7 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             rstd = rsqrtf(fmaxf(sq * (1.0f / kFc2) - mean2 * mean2, 0.0f) + 1.0e-5f);
             nmr = -mean2 * rstd;
             float o0 = 0.0f, o1 = 0.0f;
-            for_each_unit(trow, c2b, c2e, [&](int c0, const uint32_t (&r)[16]) {
+            for_each_unit(trow2, c2b, c2e, [&](int c0, const uint32_t (&r)[16]) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     // padded columns: g2 = be2 = w3 = 0
