@@ -170,9 +170,9 @@ FLOCK_API int flock_step_host(flock_env_t *env, const float *h_actions, float dt
                     float *h_obs, float *h_reward, uint8_t *h_agent_done, uint8_t *h_env_done,
                     void *stream);
 
-/* flock_step_host without the final synchronisation (same transfer policy: zero-copy kernel for small
- * result sets, otherwise one staged H2D copy and one packed D2H copy): everything is enqueued on
- * `stream` and the call returns at once. The host buffers must be pinned and must stay untouched until
+/* flock_step_host without the final synchronisation: one staged H2D copy of the actions, the fused step,
+ * one packed D2H copy of the results (copy engines on both sides: with several steps in flight they beat
+ * the zero-copy kernel of flock_step_host); everything is enqueued on `stream` and the call returns at once. The host buffers must be pinned and must stay untouched until
  * the caller has synchronised `stream` (or an event recorded on it). Two handles driven on two streams
  * overlap one env batch's result copy with the other's action copy and step: the pipelined `e2e` leg of
  * bench.py. Same results as flock_step_host. */

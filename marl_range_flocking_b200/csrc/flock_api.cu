@@ -440,8 +440,16 @@ static int step_host_impl(flock_env_t* e, const float* h_actions, float dt, cons
             return v == nullptr ? 2 : (v[0] == '0' ? 0 : 1);
         }();
         const size_t out_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float) + EN * 5 + (size_t)e->cfg.num_envs;
-        const bool zc_inputs = e->zc_ok && e->path == 0 && zc_mode != 0;
-        const bool zc_outputs = zc_inputs && e->cfg.range_noise_std == 0.0f && !e->auto_reset &&   // post-step launches
+        // async (pipelined) callers keep several steps in flight, which hides the fixed cost of the copy engines:
+        // there both directions go by DMA (measured, cfg2, four batches in flight: 1.87-1.97e9 agent-steps/s,
+        // against 1.78e9 with the zero-copy kernel and 1.65e9 with zero-copy inputs + DMA results);
+        // FLOCK_ASYNC_ZC_INPUTS=1 lets the kernel read the actions from host memory itself
+        static const bool async_zc_inputs = [] {
+            const char* v = getenv("FLOCK_ASYNC_ZC_INPUTS");
+            return v != nullptr && v[0] == '1';
+        }();
+        const bool zc_inputs = e->zc_ok && e->path == 0 && zc_mode != 0 && (sync || async_zc_inputs);
+        const bool zc_outputs = sync && zc_inputs && e->cfg.range_noise_std == 0.0f && !e->auto_reset &&   // post-step launches
                                 (zc_mode == 1 || out_bytes <= (size_t)3 << 20);
         if (zc_outputs) {
             HostMirrors mir;
