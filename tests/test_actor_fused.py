@@ -45,7 +45,7 @@ def _emulate_bf16_operands(a, obs):
     return torch.tanh(torch.baddbmm(a.b3, x, a.w3)).transpose(0, 1).contiguous()
 
 
-@pytest.mark.parametrize("E,N,in_dims", [(128, 1, 12), (300, 5, 12), (4096, 32, 12), (77, 3, 14), (200, 4, 9), (1, 2, 12)])
+@pytest.mark.parametrize("E,N,in_dims", [(128, 1, 12), (64, 10, 4), (300, 5, 12), (4096, 32, 12), (77, 3, 14), (200, 4, 9), (1, 2, 12)])
 def test_fused_actor_matches_pytorch(E, N, in_dims):
     dev = torch.device("cuda:0")
     a = _actors(N, in_dims, 11 + E, dev)
