@@ -105,3 +105,31 @@ def test_device_replay_ring_never_straddles_the_write_head():
     for _ in range(20):
         s = rb.get_minibatch(16, generator=g)[0][..., 0, 0]                     # (B, C) step ids
         assert bool((s[:, 1:] - s[:, :-1] == 1).all()) and float(s.min()) >= 13 and float(s.max()) <= 20
+
+
+def test_fused_policy_paths_have_no_cpu_fallback():
+    """The fused kernels (flock_actor_forward, flock_qnet_forward) are CUDA only: with CPU parameters the fused
+    entry points raise instead of silently running the PyTorch path."""
+    import pytest
+    from marl_range_flocking_b200.policies import BatchedActors, BatchedQNet
+    a = BatchedActors(2, 12, 400, 300, 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        a.forward_fused(torch.zeros(4, 2, 12))
+    q = BatchedQNet(2, 4, 4, recurrent=True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        q.sample_action_fused(torch.zeros(4, 2, 4), q_hidden := torch.zeros(4, 2, 32), 0.1)
+
+
+def test_actor_and_qnet_entry_points_validate_arguments_without_a_gpu():
+    """Argument validation of the new C entry points happens before any CUDA call."""
+    import ctypes
+    from marl_range_flocking_b200 import _lib
+    lib = _lib.load_library()
+    assert lib.flock_actor_packed_bytes(3) == 3 * lib.flock_actor_packed_bytes(1) > 0
+    null10 = (ctypes.c_void_p * 10)()
+    assert lib.flock_actor_pack(2, 12, 256, 128, 2, null10, None, None) == -1          # FLOCK_E_INVALID: dims
+    assert b"400-300-2" in lib.flock_last_error()
+    assert lib.flock_actor_pack(2, 15, 400, 300, 2, null10, None, None) == -1          # input width
+    assert lib.flock_actor_forward(None, None, None, 128, 2, 12, None) == -1
+    assert lib.flock_qnet_forward(null10, 1, None, None, None, None, None, 8, 2, 4, 4, 0.1, 0, 0, 0, None) == -1
+    assert lib.flock_wait_host(None) == -1
