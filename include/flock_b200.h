@@ -227,6 +227,15 @@ FLOCK_API int flock_actor_pack(int num_agents, int input_dims, int fc1_dims, int
                      const float *const *params, void *packed, void *stream);
 FLOCK_API int flock_actor_forward(const void *packed, const float *obs, float *actions, int num_envs, int num_agents,
                         int input_dims, void *stream);
+/* The same with the exploration noise of the learner fused into the output stage: one Ornstein-Uhlenbeck process per
+ * (env, agent, action) -- OUActionNoiseGPU, learners/maddpg_shared_critic/utils.py:6-21 (defaults theta 0.2, mu 0,
+ * sigma 0.15, dt 1e-2), applied as mu' = mu + noise() (agent_simple_shared_critic.py:104):
+ *     x <- x + theta (mu - x) dt + sigma sqrt(dt) N(0, 1),   actions = tanh(...) + x.
+ * ou_state [E][A][2] float32 is read and updated in place (zero it to reset(), utils.py:20-21). The normals are
+ * Philox4x32-10 with counter (env_offset + env, agent, step, tag) and key = seed: pass the rollout step as `step`. */
+FLOCK_API int flock_actor_forward_ou(const void *packed, const float *obs, float *actions, int num_envs, int num_agents,
+                           int input_dims, float *ou_state, float theta, float mu, float sigma, float dt,
+                           uint64_t seed, uint32_t step, int env_offset, void *stream);
 
 /* Fused VDN action selection ("VDN action selection", BASELINE configs[3]): QNet.forward + QNet.sample_action of
  * learners/vdn/net.py:11-58 for all envs and agents in one fp32 launch, replacing the per-agent Python loop

@@ -25,9 +25,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
+#include "flock_device.cuh"
 #include "flock_launch.h"
 
 namespace flock {
@@ -203,13 +205,26 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // column units (16 accumulator columns each) owned by column group g: layer 1 has 25 units, layer 2 has 19
 __device__ __forceinline__ int unit_begin(int units, int g) { return (units * g + kColGroups - 1) / kColGroups; }
 
+// Optional exploration noise fused into the output stage: the Ornstein-Uhlenbeck process of the shared-critic
+// learner (OUActionNoiseGPU, learners/maddpg_shared_critic/utils.py:6-21; mu' = mu + noise(),
+// agent_simple_shared_critic.py:104), one independent process per (env, agent, action):
+//     x <- x + theta (mu - x) dt + sigma sqrt(dt) N(0, 1),   action = tanh(...) + x
+// with the normals from Philox4x32-10, counter (env_offset + env, agent, step, tag 6), key = seed.
+struct OuArgs {
+    float2* state;            // [E][A] (x0, x1), updated in place; nullptr = no noise
+    float theta_dt, mu, sigma_sqrt_dt;
+    uint32_t seed_lo, seed_hi, step;
+    int env_offset;
+};
+constexpr uint32_t kTagOu = 6u;
+
 // Persistent kernel: grid = min(#SMs, work items) CTAs, one per SM; work item = (agent, tile of 128 envs),
 // items are dealt out in contiguous runs so that a CTA mostly stays on one agent (W1 and the fp32 parameters
 // are reloaded only when the agent changes; TMEM, the barriers and the W2 ring live across items).
 // obs [E][N][in_dims] fp32, out [E][N][2] fp32
 __global__ void __launch_bounds__(kThreads, 1)
 flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ obs, float* __restrict__ out, int E, int N,
-                   int in_dims, int tiles, int items_per_cta, long long* __restrict__ dbg) {
+                   int in_dims, int tiles, int items_per_cta, OuArgs ou, long long* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     // phase timestamps of the CTA's FIRST item (FLOCK_ACTOR_TIMING=1, see launch_actor_forward): 16 clock64 slots
     long long* dbg_cta = dbg != nullptr ? dbg + (size_t)blockIdx.x * 16 : nullptr;
@@ -547,6 +562,18 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                 float2 a;
                 a.x = tanhf(o0 + b3[0]);
                 a.y = tanhf(o1 + b3[1]);
+                if (ou.state != nullptr) {
+                    float2 x = ou.state[(size_t)env * N + agent];
+                    const uint4 rnd = philox4x32_10((uint32_t)(ou.env_offset + env), (uint32_t)agent, ou.step, kTagOu, ou.seed_lo,
+                                                    ou.seed_hi);
+                    float z0, z1;
+                    normal2(rnd.x, rnd.y, z0, z1);
+                    x.x = x.x + ou.theta_dt * (ou.mu - x.x) + ou.sigma_sqrt_dt * z0;
+                    x.y = x.y + ou.theta_dt * (ou.mu - x.y) + ou.sigma_sqrt_dt * z1;
+                    ou.state[(size_t)env * N + agent] = x;
+                    a.x += x.x;
+                    a.y += x.y;
+                }
                 reinterpret_cast<float2*>(out)[(size_t)env * N + agent] = a;
             }
             // this item's TMEM reads and parameter reads are over: the next layer-1 MMAs / parameter loads may go
@@ -724,7 +751,17 @@ cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs,
 }
 
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
-                                 cudaStream_t s) {
+                                 float* ou_state, float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed,
+                                 uint32_t step, int env_offset, cudaStream_t s) {
+    actor::OuArgs ou;
+    ou.state = reinterpret_cast<float2*>(ou_state);
+    ou.theta_dt = ou_theta * ou_dt;
+    ou.mu = ou_mu;
+    ou.sigma_sqrt_dt = ou_sigma * sqrtf(ou_dt);
+    ou.seed_lo = (uint32_t)seed;
+    ou.seed_hi = (uint32_t)(seed >> 32);
+    ou.step = step;
+    ou.env_offset = env_offset;
     static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          actor::kSmemBytes);
     if (configured != cudaSuccess) return configured;
@@ -748,7 +785,7 @@ cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* act
         if (cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)) == cudaSuccess) {
             cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(long long), s);
             actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(bl, obs, actions, E, N, in_dims, tiles,
-                                                                                   per_cta, dbg);
+                                                                                   per_cta, ou, dbg);
             cudaError_t e = cudaGetLastError();
             cudaStreamSynchronize(s);
             long long* h = static_cast<long long*>(malloc((size_t)grid * 16 * sizeof(long long)));
@@ -773,7 +810,7 @@ cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* act
         }
     }
     actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(bl, obs, actions, E, N, in_dims, tiles, per_cta,
-                                                                           nullptr);
+                                                                           ou, nullptr);
     return cudaGetLastError();
 }
 

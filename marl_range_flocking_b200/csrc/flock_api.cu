@@ -566,18 +566,33 @@ int flock_actor_pack(int num_agents, int in_dims, int fc1_dims, int fc2_dims, in
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor pack kernel launch");
 }
 
-int flock_actor_forward(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
-                        void* stream) {
+static int actor_forward_impl(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
+                              float* ou_state, float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step,
+                              int env_offset, void* stream) {
     int rc = actor_check_dims(num_agents, in_dims, 400, 300, 2);
     if (rc != FLOCK_OK) return rc;
     if (packed == nullptr || obs == nullptr || actions == nullptr) return fail(FLOCK_E_INVALID, "null argument");
     if (num_envs < 1 || (num_envs + 127) / 128 > 65535) return fail(FLOCK_E_INVALID, "num_envs %d out of range", num_envs);
     if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(obs) & 15u) ||
-        (reinterpret_cast<uintptr_t>(actions) & 7u))
+        (reinterpret_cast<uintptr_t>(actions) & 7u) || (reinterpret_cast<uintptr_t>(ou_state) & 7u))
         return fail(FLOCK_E_INVALID, "actor buffers must be 16-byte aligned");
-    cudaError_t err = flock::launch_actor_forward(packed, obs, actions, num_envs, num_agents, in_dims,
-                                                  static_cast<cudaStream_t>(stream));
+    cudaError_t err = flock::launch_actor_forward(packed, obs, actions, num_envs, num_agents, in_dims, ou_state, theta, mu, sigma,
+                                                  dt, seed, step, env_offset, static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor forward kernel launch");
+}
+
+int flock_actor_forward(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
+                        void* stream) {
+    return actor_forward_impl(packed, obs, actions, num_envs, num_agents, in_dims, nullptr, 0.f, 0.f, 0.f, 0.f, 0ULL, 0u, 0, stream);
+}
+
+int flock_actor_forward_ou(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
+                           float* ou_state, float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step,
+                           int env_offset, void* stream) {
+    if (ou_state == nullptr) return fail(FLOCK_E_INVALID, "ou_state is NULL");
+    if (!(dt >= 0.0f) || !(sigma >= 0.0f)) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
+    return actor_forward_impl(packed, obs, actions, num_envs, num_agents, in_dims, ou_state, theta, mu, sigma, dt, seed, step,
+                              env_offset, stream);
 }
 
 int flock_qnet_forward(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,

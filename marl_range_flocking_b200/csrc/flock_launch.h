@@ -33,7 +33,8 @@ int actor_max_in_dims();
 void actor_dims(int* fc1, int* fc2, int* n_actions);
 cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s);
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
-                                 cudaStream_t s);
+                                 float* ou_state, float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed,
+                                 uint32_t step, int env_offset, cudaStream_t s);
 
 // flock_qnet.cu (fused VDN Q-network forward + epsilon-greedy action selection, fp32)
 int qnet_max_obs();

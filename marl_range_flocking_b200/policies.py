@@ -83,9 +83,16 @@ class BatchedActors(torch.nn.Module):
         return packed
 
     @torch.no_grad()
-    def forward_fused(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_fused(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None, ou_state: Optional[torch.Tensor] = None,
+                      ou_theta: float = 0.2, ou_mu: float = 0.0, ou_sigma: float = 0.15, ou_dt: float = 1e-2, seed: int = 0,
+                      step: int = 0, env_offset: int = 0) -> torch.Tensor:
         """Same function as `forward` in ONE kernel launch on the tensor cores (bf16 operands, fp32
-        accumulation / LayerNorm): `(E, N, ...)` float32 CUDA observations -> `(E, N, 2)` actions."""
+        accumulation / LayerNorm): `(E, N, ...)` float32 CUDA observations -> `(E, N, 2)` actions.
+
+        With `ou_state` (an `(E, N, 2)` float32 CUDA tensor, zeros after a reset) the learner's exploration noise is
+        fused into the same launch: one Ornstein-Uhlenbeck process per (env, agent, action) as in
+        `OUActionNoiseGPU` (learners/maddpg_shared_critic/utils.py:6-21), `actions = mu + x` with
+        `x <- x + theta (mu_ou - x) dt + sigma sqrt(dt) N(0,1)` updated in place; normals from Philox(seed; env, agent, step)."""
         from . import _lib
         lib = _lib.load_library()
         if getattr(self, "_packed", None) is None:
@@ -97,8 +104,15 @@ class BatchedActors(torch.nn.Module):
         if out is None:
             out = torch.empty(E, N, 2, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.check(lib.flock_actor_forward(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2],
-                                               torch.cuda.current_stream().cuda_stream))
+            stream = torch.cuda.current_stream().cuda_stream
+            if ou_state is None:
+                _lib.check(lib.flock_actor_forward(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2], stream))
+            else:
+                if ou_state.shape != (E, N, 2) or ou_state.dtype != torch.float32 or not ou_state.is_contiguous():
+                    raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
+                _lib.check(lib.flock_actor_forward_ou(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2],
+                                                      ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
+                                                      float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset), stream))
         return out
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:

@@ -101,3 +101,45 @@ def test_fused_actor_rejects_unsupported_shapes():
         BatchedActors(2, 12, 256, 128, 2, device=dev).pack_fused()
     with pytest.raises(_lib.FlockError):
         BatchedActors(2, 15, 400, 300, 2, device=dev).pack_fused()
+
+
+def test_fused_ou_exploration_noise():
+    """flock_actor_forward_ou: the Ornstein-Uhlenbeck exploration noise of the shared-critic learner
+    (OUActionNoiseGPU, learners/maddpg_shared_critic/utils.py:6-21) fused into the actor launch.
+    sigma = 0: the state follows the deterministic recurrence exactly (fp32, 1e-6); sigma > 0: increments have the
+    right mean / variance (2.6e5 samples), draws are reproducible per (seed, step) and invariant under env sharding;
+    actions = mu + x."""
+    dev = torch.device("cuda:0")
+    E, N = 4096, 32
+    a = _actors(N, 12, 5, dev)
+    torch.manual_seed(2)
+    obs = torch.rand(E, N, 12, device=dev) * 7.0
+    mu_act = a.forward_fused(obs).clone()
+    theta, mu, sigma, dt = 0.2, 0.3, 0.15, 1e-2
+    # deterministic part
+    x = torch.full((E, N, 2), -1.0, device=dev)
+    ref = x.clone()
+    for t in range(3):
+        out = a.forward_fused(obs, ou_state=x, ou_theta=theta, ou_mu=mu, ou_sigma=0.0, ou_dt=dt, seed=9, step=t)
+        ref = ref + theta * dt * (mu - ref)
+        assert torch.allclose(x, ref, atol=1e-6) and torch.allclose(out, mu_act + x, atol=1e-6)
+    # stochastic part
+    x0 = torch.zeros(E, N, 2, device=dev)
+    x1 = x0.clone()
+    out1 = a.forward_fused(obs, ou_state=x1, ou_theta=theta, ou_mu=mu, ou_sigma=sigma, ou_dt=dt, seed=9, step=4).clone()
+    x2 = x0.clone()
+    a.forward_fused(obs, ou_state=x2, ou_theta=theta, ou_mu=mu, ou_sigma=sigma, ou_dt=dt, seed=9, step=4)
+    x3 = x0.clone()
+    a.forward_fused(obs, ou_state=x3, ou_theta=theta, ou_mu=mu, ou_sigma=sigma, ou_dt=dt, seed=9, step=5)
+    torch.cuda.synchronize()
+    assert torch.equal(x1, x2) and not torch.equal(x1, x3)
+    assert torch.allclose(out1, mu_act + x1, atol=1e-6)
+    z = (x1 - theta * dt * mu) / (sigma * dt ** 0.5)               # the standard normals that were drawn
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs((z[..., 0] * z[..., 1]).mean().item()) < 0.01        # the two action dims are independent
+    half = E // 2
+    xs = x0[half:].clone()
+    a.forward_fused(obs[half:].contiguous(), ou_state=xs, ou_theta=theta, ou_mu=mu, ou_sigma=sigma, ou_dt=dt, seed=9,
+                    step=4, env_offset=half)
+    torch.cuda.synchronize()
+    assert torch.equal(xs, x1[half:])
