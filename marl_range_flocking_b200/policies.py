@@ -126,6 +126,73 @@ class BatchedActors(torch.nn.Module):
         return mu.transpose(0, 1).float().contiguous()                           # (E, N, n_actions)
 
 
+class BatchedRnnActors(torch.nn.Module):
+    """N per-agent recurrent MADDPG actors (`Actor`, learners/maddpg_official_rnn/net.py:14-72 -- the policy of the
+    reference's default `main.py` loop): fce(in -> 32) -> GRUCell(32, 32) -> fc1(32 -> 400) -> ReLU -> fc2(400 -> 300)
+    -> ReLU -> [linear_speed -> (tanh + 1) / 2 | angular_speed -> 1.5 tanh], evaluated for all envs and agents at once
+    (one `baddbmm` per layer over the agent dimension; plain PyTorch -- the fused tensor-core kernel covers the
+    shared-critic actor, this one is the batched reference path for the recurrent learner).
+    `forward(obs (E, N, in), hidden (E, N, 32)) -> (actions (E, N, 2), next_hidden (E, N, 32))`."""
+
+    def __init__(self, num_agents: int, input_dims: int, hidden1: int = 400, hidden2: int = 300, hidden_rnn: int = 32,
+                 init_w: float = 3e-3, device=None, dtype=torch.float32):
+        super().__init__()
+        kw = dict(device=device, dtype=dtype)
+        n = num_agents
+
+        def lin(i, o, bound=None):
+            b = (i ** -0.5) if bound is None else bound
+            return (torch.nn.Parameter(torch.empty(n, i, o, **kw).uniform_(-b, b)),
+                    torch.nn.Parameter(torch.empty(n, 1, o, **kw).uniform_(-(i ** -0.5), i ** -0.5)))
+
+        self.we, self.be = lin(input_dims, hidden_rnn)
+        self.w_ih, self.b_ih = lin(hidden_rnn, 3 * hidden_rnn)
+        self.w_hh, self.b_hh = lin(hidden_rnn, 3 * hidden_rnn)
+        self.w1, self.b1 = lin(hidden_rnn, hidden1)
+        self.w2, self.b2 = lin(hidden1, hidden2)
+        self.wl, self.bl = lin(hidden2, 1, init_w)         # linear_speed, net.py:47
+        self.wa, self.ba = lin(hidden2, 1, init_w)         # angular_speed, net.py:48
+        self.num_agents, self.input_dims, self.hidden_rnn = n, input_dims, hidden_rnn
+
+    @classmethod
+    def from_state_dicts(cls, sds: Sequence[Dict[str, torch.Tensor]], device=None, dtype=torch.float32):
+        """Build from N reference `Actor.state_dict()`s (keys fce / gru / fc1 / fc2 / linear_speed / angular_speed)."""
+        self = cls(len(sds), sds[0]["fce.weight"].shape[1], sds[0]["fc1.weight"].shape[0], sds[0]["fc2.weight"].shape[0],
+                   sds[0]["fce.weight"].shape[0], device=device, dtype=dtype)
+        pairs = ((self.we, self.be, "fce.weight", "fce.bias"), (self.w_ih, self.b_ih, "gru.weight_ih", "gru.bias_ih"),
+                 (self.w_hh, self.b_hh, "gru.weight_hh", "gru.bias_hh"), (self.w1, self.b1, "fc1.weight", "fc1.bias"),
+                 (self.w2, self.b2, "fc2.weight", "fc2.bias"), (self.wl, self.bl, "linear_speed.weight", "linear_speed.bias"),
+                 (self.wa, self.ba, "angular_speed.weight", "angular_speed.bias"))
+        with torch.no_grad():
+            for wt, b, kw_, kb_ in pairs:
+                wt.copy_(_stack(sds, kw_).transpose(1, 2))
+                b.copy_(_stack(sds, kb_).unsqueeze(1))
+        return self
+
+    def init_hidden(self, batch_size: int = 1) -> torch.Tensor:
+        return torch.zeros(batch_size, self.num_agents, self.hidden_rnn, device=self.we.device)
+
+    def forward(self, obs: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        E, N = obs.shape[0], obs.shape[1]
+        x = obs.reshape(E, N, -1).transpose(0, 1).to(self.we.dtype)               # (N, E, in)
+        h = hidden.transpose(0, 1).to(x.dtype)
+        x = torch.baddbmm(self.be, x, self.we)                                     # fce: no activation (net.py:57)
+        gi = torch.baddbmm(self.b_ih, x, self.w_ih)
+        gh = torch.baddbmm(self.b_hh, h, self.w_hh)
+        i_r, i_z, i_n = gi.chunk(3, dim=-1)
+        h_r, h_z, h_n = gh.chunk(3, dim=-1)
+        r = torch.sigmoid(i_r + h_r)
+        z = torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        x = (1 - z) * n + z * h                                                    # torch.nn.GRUCell
+        next_hidden = x.transpose(0, 1).float().contiguous()
+        x = F.relu(torch.baddbmm(self.b1, x, self.w1))
+        x = F.relu(torch.baddbmm(self.b2, x, self.w2))
+        linear = (torch.tanh(torch.baddbmm(self.bl, x, self.wl)) + 1) / 2          # net.py:66-67
+        angular = torch.tanh(torch.baddbmm(self.ba, x, self.wa)) * 1.5             # net.py:70-71
+        return torch.cat([linear, angular], dim=-1).transpose(0, 1).float().contiguous(), next_hidden
+
+
 class BatchedQNet(torch.nn.Module):
     """The VDN per-agent Q networks (`QNet`, learners/vdn/net.py:11-37): Linear(n_obs,64)-ReLU-
     Linear(64,32)-ReLU [-GRUCell(32,32)] -Linear(32,n_actions) per agent, batched over agents.

@@ -133,3 +133,35 @@ def test_actor_and_qnet_entry_points_validate_arguments_without_a_gpu():
     assert lib.flock_actor_forward(None, None, None, 128, 2, 12, None) == -1
     assert lib.flock_qnet_forward(null10, 1, None, None, None, None, None, 8, 2, 4, 4, 0.1, 0, 0, 0, None) == -1
     assert lib.flock_wait_host(None) == -1
+
+
+class _RnnActor(nn.Module):                                # layer names = the reference's state_dict keys (net.py:32-38)
+    def __init__(self, i, a=2, h1=40, h2=30, hr=32):
+        super().__init__()
+        self.fce, self.gru = nn.Linear(i, hr), nn.GRUCell(hr, hr)
+        self.fc1, self.fc2 = nn.Linear(hr, h1), nn.Linear(h1, h2)
+        self.linear_speed, self.angular_speed = nn.Linear(h2, a // 2), nn.Linear(h2, a // 2)
+
+    def forward(self, x, hidden):                          # net.py:53-72
+        out = self.gru(self.fce(x), hidden)
+        nxt = out.clone()
+        out = torch.relu(self.fc2(torch.relu(self.fc1(out))))
+        lin = (torch.tanh(self.linear_speed(out)) + 1) / 2
+        ang = torch.tanh(self.angular_speed(out)) * 1.5
+        return torch.cat([lin, ang], dim=1), nxt
+
+
+def test_batched_rnn_actors_match_per_agent_modules():
+    from marl_range_flocking_b200.policies import BatchedRnnActors
+    torch.manual_seed(3)
+    N, E, k = 4, 6, 4
+    actors = [_RnnActor(k) for _ in range(N)]
+    batched = BatchedRnnActors.from_state_dicts([a.state_dict() for a in actors])
+    obs, hid = torch.rand(E, N, k) * 14, torch.randn(E, N, 32) * 0.5
+    want_a = torch.stack([actors[i](obs[:, i], hid[:, i])[0] for i in range(N)], dim=1)
+    want_h = torch.stack([actors[i](obs[:, i], hid[:, i])[1] for i in range(N)], dim=1)
+    got_a, got_h = batched(obs, hid)
+    assert got_a.shape == (E, N, 2) and got_h.shape == (E, N, 32)
+    assert torch.allclose(got_a, want_a, atol=1e-5, rtol=1e-5) and torch.allclose(got_h, want_h, atol=1e-5, rtol=1e-5)
+    assert bool(((got_a[..., 0] >= 0) & (got_a[..., 0] <= 1)).all()) and bool((got_a[..., 1].abs() <= 1.5).all())
+    assert batched.init_hidden(E).shape == (E, N, 32)
