@@ -237,6 +237,24 @@ FLOCK_API int flock_actor_forward_ou(const void *packed, const float *obs, float
                            int input_dims, float *ou_state, float theta, float mu, float sigma, float dt,
                            uint64_t seed, uint32_t step, int env_offset, void *stream);
 
+/* Fused recurrent MADDPG actor -- the policy of the reference's default main.py loop: `Actor` of
+ * learners/maddpg_official_rnn/net.py:14-72 (fce(in,32) - GRUCell(32,32) - fc1(32,400) - ReLU - fc2(400,300) - ReLU -
+ * [linear_speed: (tanh+1)/2 | angular_speed: 1.5 tanh]), one weight set per agent, replacing the per-agent Python loop
+ * of MADDPG.get_actions (learners/maddpg_official_rnn/MADDPG.py:24-33). Two launches: fce + GRU in fp32, then the MLP
+ * on the tensor cores (bf16 operands, fp32 accumulation).
+ *   flock_rnn_actor_pack: `params` = 8 DEVICE pointers {w1 [A][32][400], b1 [A][400], w2 [A][400][300], b2 [A][300],
+ *     w_linear [A][300], b_linear [A], w_angular [A][300], b_angular [A]}, float32, weights input-major; writes
+ *     `packed` (flock_rnn_actor_packed_bytes(A) bytes, 16-byte aligned). Call again after a parameter update.
+ *   flock_rnn_actor_forward: `front_params` = 6 DEVICE pointers {w_e [A][n_obs][32], b_e [A][32], w_ih [A][32][96],
+ *     b_ih [A][96], w_hh [A][32][96], b_hh [A][96]} (used as they are, gate order r|z|n); obs [E][A][n_obs],
+ *     hidden_in / hidden_out [E][A][32] (may alias) -> actions [E][A][2] = (linear, angular). n_obs <= 16. */
+FLOCK_API size_t flock_rnn_actor_packed_bytes(int num_agents);
+FLOCK_API int flock_rnn_actor_pack(int num_agents, int hidden_rnn, int hidden1, int hidden2, int n_actions,
+                         const float *const *params, void *packed, void *stream);
+FLOCK_API int flock_rnn_actor_forward(const void *packed, const float *const *front_params, const float *obs,
+                            const float *hidden_in, float *hidden_out, float *actions, int num_envs, int num_agents,
+                            int n_obs, void *stream);
+
 /* Fused VDN action selection ("VDN action selection", BASELINE configs[3]): QNet.forward + QNet.sample_action of
  * learners/vdn/net.py:11-58 for all envs and agents in one fp32 launch, replacing the per-agent Python loop
  * (net.py:30-35). Per agent: Linear(n_obs,64)-ReLU-Linear(64,32)-ReLU-[GRUCell(32,32)]-Linear(32,n_actions).

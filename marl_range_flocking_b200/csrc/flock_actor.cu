@@ -31,6 +31,7 @@
 
 #include "flock_device.cuh"
 #include "flock_launch.h"
+#include "flock_tc.cuh"
 
 namespace flock {
 namespace actor {
@@ -86,121 +87,9 @@ constexpr int kPhaseAUnit = 12;                       // first layer-1 column un
 constexpr int kFirstChunk = kPhaseAUnit / kStepsPerChunk;   // W2 chunks are streamed / multiplied in the order 6..12, 0..5
 static_assert(kPhaseAUnit % kStepsPerChunk == 0 && kPhaseAUnit * 16 <= kL2Col && kL2Col + kFc2Pad <= kTmemCols, "phase split");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tc;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ bool elect_one() {   // one lane of the (fully active) warp
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred P;\n"
-        "elect.sync _|P, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, P;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0u;
-}
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B contiguous;
-// SBO = byte distance between consecutive 8-row groups, LBO = between the two 8-element K halves of
-// one K = 16 step (cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30), SBO [32,46) in 16-byte
-// units, version [46,48) = 1 on sm_100, layout type [61,64) = 0).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= 1ull << 46;
-    return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = BF16 [7,10) / [10,13) = 1,
-// both K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when all MMAs issued so far are done
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 16 consecutive fp32 accumulator columns of this thread's TMEM lane (warp-collective), split into
-// issue and wait so that the next load is in flight while the current columns are processed
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-// waits for ALL outstanding tcgen05.ld of the thread; takes the registers as in/out operands so that
-// no use can be scheduled above it
-__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
-// for (c0 = cb; c0 < ce; c0 += 16) f(c0, the 16 columns at c0). (Keeping the next unit's load in flight in a
-// second register buffer was measured: no gain, and the 16 extra registers spill in the persistent kernel.)
-template <typename F>
-__device__ __forceinline__ void for_each_unit(uint32_t trow, int cb, int ce, F&& f) {
-#pragma unroll 1
-    for (int c0 = cb; c0 < ce; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16_issue(trow + c0, r);
-        tmem_ld16_wait(r);
-        f(c0, r);
-    }
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);   // .x = lo (low half), .y = hi
-    return *reinterpret_cast<const uint32_t*>(&b);
-}
-
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
 // column units (16 accumulator columns each) owned by column group g: layer 1 has 25 units, layer 2 has 19
 __device__ __forceinline__ int unit_begin(int units, int g) { return (units * g + kColGroups - 1) / kColGroups; }

@@ -595,6 +595,44 @@ int flock_actor_forward_ou(const void* packed, const float* obs, float* actions,
                               env_offset, stream);
 }
 
+size_t flock_rnn_actor_packed_bytes(int num_agents) {
+    return num_agents > 0 ? (size_t)num_agents * flock::rnn_actor_blob_bytes() : 0;
+}
+
+int flock_rnn_actor_pack(int num_agents, int hidden_rnn, int hidden1, int hidden2, int n_actions, const float* const* params,
+                         void* packed, void* stream) {
+    if (num_agents < 1 || num_agents > 65535) return fail(FLOCK_E_INVALID, "num_agents %d not in [1, 65535]", num_agents);
+    if (hidden_rnn != 32 || hidden1 != 400 || hidden2 != 300 || n_actions != 2)
+        return fail(FLOCK_E_INVALID, "fused recurrent actor is built for 32-400-300-2 (got %d-%d-%d-%d)", hidden_rnn, hidden1,
+                    hidden2, n_actions);
+    if (params == nullptr || packed == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    for (int i = 0; i < 8; ++i)
+        if (params[i] == nullptr) return fail(FLOCK_E_INVALID, "recurrent actor parameter %d is NULL", i);
+    cudaError_t err = flock::launch_rnn_actor_pack(num_agents, params, packed, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor pack kernel launch");
+}
+
+int flock_rnn_actor_forward(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
+                            float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, void* stream) {
+    if (packed == nullptr || front_params == nullptr || obs == nullptr || hidden_in == nullptr || hidden_out == nullptr ||
+        actions == nullptr)
+        return fail(FLOCK_E_INVALID, "null argument");
+    if (num_agents < 1 || num_agents > 65535 || num_envs < 1) return fail(FLOCK_E_INVALID, "bad num_envs / num_agents");
+    if (n_obs < 1 || n_obs > flock::rnn_actor_max_obs())
+        return fail(FLOCK_E_INVALID, "n_obs %d not in [1, %d]", n_obs, flock::rnn_actor_max_obs());
+    for (int i = 0; i < 6; ++i) {
+        if (front_params[i] == nullptr) return fail(FLOCK_E_INVALID, "front-end parameter %d is NULL", i);
+        if (reinterpret_cast<uintptr_t>(front_params[i]) & 15u)
+            return fail(FLOCK_E_INVALID, "front-end parameter %d is not 16-byte aligned", i);
+    }
+    if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(hidden_in) & 15u) ||
+        (reinterpret_cast<uintptr_t>(hidden_out) & 15u) || (reinterpret_cast<uintptr_t>(actions) & 7u))
+        return fail(FLOCK_E_INVALID, "recurrent actor buffers must be 16-byte aligned");
+    cudaError_t err = flock::launch_rnn_actor_forward(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs,
+                                                      num_agents, n_obs, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor kernel launch");
+}
+
 int flock_qnet_forward(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
                        float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, int n_actions,
                        float epsilon, uint64_t seed, uint32_t step, int env_offset, void* stream) {

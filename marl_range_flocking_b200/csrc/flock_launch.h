@@ -42,4 +42,11 @@ int qnet_max_actions();
 cudaError_t launch_qnet(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
                         float* hidden_out, float* actions, int E, int A, int n_obs, int n_act, float epsilon, uint64_t seed,
                         uint32_t step, int env_offset, cudaStream_t s);
+
+// flock_rnn_actor.cu (fused recurrent MADDPG actor: fp32 GRU front end + tensor-core MLP)
+size_t rnn_actor_blob_bytes();
+int rnn_actor_max_obs();
+cudaError_t launch_rnn_actor_pack(int agents, const float* const* ptrs, void* blobs, cudaStream_t s);
+cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* front, const float* obs, const float* hidden_in,
+                                     float* hidden_out, float* actions, int E, int N, int n_obs, cudaStream_t s);
 }  // namespace flock

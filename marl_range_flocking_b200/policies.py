@@ -153,6 +153,7 @@ class BatchedRnnActors(torch.nn.Module):
         self.wl, self.bl = lin(hidden2, 1, init_w)         # linear_speed, net.py:47
         self.wa, self.ba = lin(hidden2, 1, init_w)         # angular_speed, net.py:48
         self.num_agents, self.input_dims, self.hidden_rnn = n, input_dims, hidden_rnn
+        self._packed = None
 
     @classmethod
     def from_state_dicts(cls, sds: Sequence[Dict[str, torch.Tensor]], device=None, dtype=torch.float32):
@@ -171,6 +172,49 @@ class BatchedRnnActors(torch.nn.Module):
 
     def init_hidden(self, batch_size: int = 1) -> torch.Tensor:
         return torch.zeros(batch_size, self.num_agents, self.hidden_rnn, device=self.we.device)
+
+    # ---- fused path (csrc/flock_rnn_actor.cu through the C ABI): fp32 GRU front end + tensor-core MLP ----
+    def pack_fused(self) -> torch.Tensor:
+        """(Re)build the packed MLP parameter image (call after every optimiser step). No fallback."""
+        import ctypes
+
+        from . import _lib
+        lib = _lib.load_library()
+        if self.we.device.type != "cuda":
+            raise RuntimeError("the fused recurrent actor kernel needs CUDA parameters (there is no CPU path)")
+        srcs = [t.detach().float().contiguous() for t in (self.w1, self.b1, self.w2, self.b2, self.wl, self.bl, self.wa, self.ba)]
+        ptrs = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in srcs])
+        packed = torch.empty(lib.flock_rnn_actor_packed_bytes(self.num_agents), dtype=torch.uint8, device=self.we.device)
+        with torch.cuda.device(self.we.device):
+            _lib.check(lib.flock_rnn_actor_pack(self.num_agents, self.hidden_rnn, self.w1.shape[2], self.w2.shape[2], 2, ptrs,
+                                                packed.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        front = [t.detach().float().contiguous() for t in (self.we, self.be, self.w_ih, self.b_ih, self.w_hh, self.b_hh)]
+        self._packed, self._packed_srcs = packed, srcs
+        self._front, self._front_ptrs = front, (ctypes.c_void_p * 6)(*[t.data_ptr() for t in front])
+        return packed
+
+    @torch.no_grad()
+    def forward_fused(self, obs: torch.Tensor, hidden: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      hidden_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`forward` in two kernel launches: fce + GRUCell in fp32 (the recurrent state stays exact), then the
+        32-400-300-2 MLP on the tensor cores (bf16 operands, fp32 accumulation). `hidden_out` may be `hidden`."""
+        from . import _lib
+        lib = _lib.load_library()
+        if getattr(self, "_packed", None) is None:
+            self.pack_fused()
+        E, N = obs.shape[0], obs.shape[1]
+        x = obs.reshape(E, N, -1)
+        x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        h = hidden if (hidden.dtype == torch.float32 and hidden.is_contiguous()) else hidden.float().contiguous()
+        if out is None:
+            out = torch.empty(E, N, 2, dtype=torch.float32, device=x.device)
+        if hidden_out is None:
+            hidden_out = torch.empty(E, N, self.hidden_rnn, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.flock_rnn_actor_forward(self._packed.data_ptr(), self._front_ptrs, x.data_ptr(), h.data_ptr(),
+                                                   hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2],
+                                                   torch.cuda.current_stream().cuda_stream))
+        return out, hidden_out
 
     def forward(self, obs: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         E, N = obs.shape[0], obs.shape[1]
