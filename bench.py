@@ -502,6 +502,65 @@ def run_gpu(args, w):
                               "one launch for all envs and agents"}
         torch.cuda.current_stream(device).wait_stream(side)
 
+    # the reference's default main.py loop: v2 env + recurrent MADDPG actors (learners/maddpg_official_rnn/net.py);
+    # closed loop policy + env step with the fused kernels (fp32 GRU front end + tcgen05 MLP) under CUDA-graph replay,
+    # next to the same networks as PyTorch baddbmm's
+    if rank == 0 and args.policy == "actor" and w["variant"] == "v2":
+        from marl_range_flocking_b200.policies import BatchedRnnActors
+        env = envs[0]
+        k_obs = env.observation.shape[-1]
+        extra["rnn_actor_rollout"] = {}
+        for dtype, name in ((torch.float32, "pytorch_fp32"), (torch.bfloat16, "pytorch_bf16")):
+            net = BatchedRnnActors(N, k_obs, device=device, dtype=dtype)
+            hidden = net.init_hidden(E)
+            obs = env.observation
+            with torch.no_grad():
+                for _ in range(5):
+                    act, hidden = net(obs, hidden)
+                    obs, *_ = env.step(act, DT)
+                torch.cuda.synchronize(device)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 100
+                ev0.record()
+                for _ in range(reps):
+                    act, hidden = net(obs, hidden)
+                    obs, *_ = env.step(act, DT)
+                ev1.record()
+                torch.cuda.synchronize(device)
+            t = ev0.elapsed_time(ev1) * 1e-3 / reps
+            extra["rnn_actor_rollout"][name] = {"ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t}
+        net = BatchedRnnActors(N, k_obs, device=device)
+        net.pack_fused()
+        hidden = net.init_hidden(E)
+        acts = torch.empty(E, N, 2, device=device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                net.forward_fused(env.observation, hidden, out=acts, hidden_out=hidden)
+                env.step(acts, DT)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            reps, inner = 20, 50
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(inner):
+                    net.forward_fused(env.observation, hidden, out=acts, hidden_out=hidden)
+                    env.step(acts, DT)
+            g.replay()
+            side.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(side)
+            for _ in range(reps):
+                g.replay()
+            ev1.record(side)
+            side.synchronize()
+        torch.cuda.current_stream(device).wait_stream(side)
+        t = ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
+        extra["rnn_actor_rollout"]["fused_closed_loop"] = {
+            "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
+            "policy": f"{N} per-agent recurrent actors {k_obs}-32-GRU32-400-300-2: flock_rnn_actor_forward (fp32 GRU front kernel + "
+                      "tcgen05 MLP kernel) + one env launch per step, CUDA-graph replay"}
+
     # VDN action selection next to the discrete env (BASELINE configs[3]): the per-agent Q networks of
     # learners/vdn/net.py (recurrent, as the reference trains them) + per-env epsilon-greedy, closed loop with the
     # env step; fused fp32 kernel (flock_qnet_forward) vs the same networks as PyTorch baddbmm's
