@@ -143,3 +143,25 @@ def test_fused_ou_exploration_noise():
                     step=4, env_offset=half)
     torch.cuda.synchronize()
     assert torch.equal(xs, x1[half:])
+
+
+def test_graphed_rollout_with_the_fused_actor_matches_the_python_loop():
+    """policy = fused actor kernel inside rollout.GraphedRollout (everything captured in one CUDA graph) against
+    rollout.collect with the same policy: the kernels are deterministic, so the final states are identical."""
+    from marl_range_flocking_b200 import VecEnv
+    from marl_range_flocking_b200.rollout import GraphedRollout, collect
+    dev = torch.device("cuda:0")
+    E, N, k = 256, 8, 3
+    mk = lambda: VecEnv("uw", E, N, k, 0.5, range_start=(0, 60), sensor_range=7.0, seed=8, device="cuda:0")
+    a, b = mk(), mk()
+    actors = _actors(N, 4 * k, 13, dev)
+    buf_a, buf_b = torch.empty(E, N, 2, device=dev), torch.empty(E, N, 2, device=dev)
+    stats_a = collect(a, lambda obs: actors.forward_fused(obs, out=buf_a), 2 + 3 * 8, max_episode_steps=11)
+    b.reset()
+    gr = GraphedRollout(b, lambda obs: actors.forward_fused(obs, out=buf_b), steps_per_replay=8, max_episode_steps=11,
+                        warmup_steps=2)
+    stats_b = gr.run(3)
+    torch.cuda.synchronize()
+    for name in ("x", "y", "_obs", "_reward", "_env_done", "_ep_len", "_ep_return_fx"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(buf_a, buf_b) and stats_a == stats_b
