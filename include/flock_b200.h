@@ -254,6 +254,13 @@ FLOCK_API int flock_rnn_actor_pack(int num_agents, int hidden_rnn, int hidden1, 
 FLOCK_API int flock_rnn_actor_forward(const void *packed, const float *const *front_params, const float *obs,
                             const float *hidden_in, float *hidden_out, float *actions, int num_envs, int num_agents,
                             int n_obs, void *stream);
+/* The same with the learner's exploration noise (mu' = mu + noise.sample(), learners/maddpg_official_rnn/agent.py:61;
+ * OrnsteinUhlenbeckProcess.sample, utils.py:43-47) fused into the output stage, one process per (env, agent, action):
+ * ou_state [E][A][2] float32 read and updated in place; see flock_actor_forward_ou for the recurrence and the draws. */
+FLOCK_API int flock_rnn_actor_forward_ou(const void *packed, const float *const *front_params, const float *obs,
+                               const float *hidden_in, float *hidden_out, float *actions, int num_envs,
+                               int num_agents, int n_obs, float *ou_state, float theta, float mu, float sigma,
+                               float dt, uint64_t seed, uint32_t step, int env_offset, void *stream);
 
 /* Fused VDN action selection ("VDN action selection", BASELINE configs[3]): QNet.forward + QNet.sample_action of
  * learners/vdn/net.py:11-58 for all envs and agents in one fp32 launch, replacing the per-agent Python loop

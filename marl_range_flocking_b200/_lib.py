@@ -91,6 +91,8 @@ def load_library() -> ctypes.CDLL:
         "flock_rnn_actor_packed_bytes": (ctypes.c_size_t, [i32]),
         "flock_rnn_actor_pack": (i32, [i32, i32, i32, i32, i32, ctypes.POINTER(vp), vp, vp]),
         "flock_rnn_actor_forward": (i32, [vp, ctypes.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, vp]),
+        "flock_rnn_actor_forward_ou": (i32, [vp, ctypes.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32,
+                                           u64, u32, i32, vp]),
         "flock_qnet_forward": (i32, [ctypes.POINTER(vp), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u32, i32, vp]),
         "flock_last_error": (ctypes.c_char_p, []),
         "flock_abi_version": (i32, []),

@@ -612,8 +612,10 @@ int flock_rnn_actor_pack(int num_agents, int hidden_rnn, int hidden1, int hidden
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor pack kernel launch");
 }
 
-int flock_rnn_actor_forward(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
-                            float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, void* stream) {
+static int rnn_actor_forward_impl(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
+                                  float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, float* ou_state,
+                                  float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step, int env_offset,
+                                  void* stream) {
     if (packed == nullptr || front_params == nullptr || obs == nullptr || hidden_in == nullptr || hidden_out == nullptr ||
         actions == nullptr)
         return fail(FLOCK_E_INVALID, "null argument");
@@ -626,11 +628,29 @@ int flock_rnn_actor_forward(const void* packed, const float* const* front_params
             return fail(FLOCK_E_INVALID, "front-end parameter %d is not 16-byte aligned", i);
     }
     if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(hidden_in) & 15u) ||
-        (reinterpret_cast<uintptr_t>(hidden_out) & 15u) || (reinterpret_cast<uintptr_t>(actions) & 7u))
+        (reinterpret_cast<uintptr_t>(hidden_out) & 15u) || (reinterpret_cast<uintptr_t>(actions) & 7u) ||
+        (reinterpret_cast<uintptr_t>(ou_state) & 7u))
         return fail(FLOCK_E_INVALID, "recurrent actor buffers must be 16-byte aligned");
     cudaError_t err = flock::launch_rnn_actor_forward(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs,
-                                                      num_agents, n_obs, static_cast<cudaStream_t>(stream));
+                                                      num_agents, n_obs, ou_state, theta, mu, sigma, dt, seed, step, env_offset,
+                                                      static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor kernel launch");
+}
+
+int flock_rnn_actor_forward(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
+                            float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, void* stream) {
+    return rnn_actor_forward_impl(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs, num_agents, n_obs, nullptr,
+                                  0.f, 0.f, 0.f, 0.f, 0ULL, 0u, 0, stream);
+}
+
+int flock_rnn_actor_forward_ou(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
+                               float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, float* ou_state,
+                               float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step, int env_offset,
+                               void* stream) {
+    if (ou_state == nullptr) return fail(FLOCK_E_INVALID, "ou_state is NULL");
+    if (!(dt >= 0.0f) || !(sigma >= 0.0f)) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
+    return rnn_actor_forward_impl(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs, num_agents, n_obs, ou_state,
+                                  theta, mu, sigma, dt, seed, step, env_offset, stream);
 }
 
 int flock_qnet_forward(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,

@@ -48,5 +48,7 @@ size_t rnn_actor_blob_bytes();
 int rnn_actor_max_obs();
 cudaError_t launch_rnn_actor_pack(int agents, const float* const* ptrs, void* blobs, cudaStream_t s);
 cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* front, const float* obs, const float* hidden_in,
-                                     float* hidden_out, float* actions, int E, int N, int n_obs, cudaStream_t s);
+                                     float* hidden_out, float* actions, int E, int N, int n_obs, float* ou_state,
+                                     float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed, uint32_t step,
+                                     int env_offset, cudaStream_t s);
 }  // namespace flock

@@ -10,6 +10,7 @@
 //      streamed by 1-D TMA bulk copies, accumulators in TMEM, two-phase epilogue 1 under the first layer-2 MMAs).
 //      No LayerNorm here, so the epilogues are one pass each: bias + ReLU -> bf16 (layer 1; the layer-2 bias rides
 //      in the MMA as hi + lo bf16 rows), ReLU + the two heads (layer 2).
+#include <cmath>
 #include <cstdlib>
 
 #include "flock_device.cuh"
@@ -68,10 +69,23 @@ constexpr int kFirstChunk = kPhaseAUnit / kStepsPerChunk;
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 __device__ __forceinline__ int unit_begin(int units, int g) { return (units * g + kColGroups - 1) / kColGroups; }
 
+// Optional exploration noise fused into the output stage (mu' = mu + noise.sample(), agent.py:61): one
+// Ornstein-Uhlenbeck process per (env, agent, action) -- OrnsteinUhlenbeckProcess.sample,
+// learners/maddpg_official_rnn/utils.py:43-47 -- x <- x + theta (mu - x) dt + sigma sqrt(dt) N(0, 1), with Philox
+// normals (counter = env_offset + env, agent, step, tag 7; key = seed). The reference shares ONE process object
+// between all agents of its single env; the batched form keeps them independent.
+struct OuArgs {
+    float2* state;            // [E][A] (x0, x1), updated in place; nullptr = no noise
+    float theta_dt, mu, sigma_sqrt_dt;
+    uint32_t seed_lo, seed_hi, step;
+    int env_offset;
+};
+constexpr uint32_t kTagOu = 7u;
+
 // hin [E][N][32] fp32 (the GRU state the front kernel just wrote), out [E][N][2] fp32
 __global__ void __launch_bounds__(kThreads, 1)
 flock_rnn_mlp_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ hin, float* __restrict__ out, int E, int N,
-                     int tiles, int items_per_cta) {
+                     int tiles, int items_per_cta, OuArgs ou) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;
@@ -298,6 +312,18 @@ flock_rnn_mlp_kernel(const uint8_t* __restrict__ blobs, const float* __restrict_
                 float2 a;
                 a.x = (tanhf(o0 + bh[0]) + 1.0f) * 0.5f;      // net.py:66-67
                 a.y = tanhf(o1 + bh[1]) * 1.5f;              // net.py:70-71
+                if (ou.state != nullptr) {
+                    float2 x = ou.state[(size_t)env * N + agent];
+                    const uint4 rnd = philox4x32_10((uint32_t)(ou.env_offset + env), (uint32_t)agent, ou.step, kTagOu, ou.seed_lo,
+                                                    ou.seed_hi);
+                    float z0, z1;
+                    normal2(rnd.x, rnd.y, z0, z1);
+                    x.x = x.x + ou.theta_dt * (ou.mu - x.x) + ou.sigma_sqrt_dt * z0;
+                    x.y = x.y + ou.theta_dt * (ou.mu - x.y) + ou.sigma_sqrt_dt * z1;
+                    ou.state[(size_t)env * N + agent] = x;
+                    a.x += x.x;
+                    a.y += x.y;
+                }
                 reinterpret_cast<float2*>(out)[(size_t)env * N + agent] = a;
             }
             tc_fence_before();
@@ -487,7 +513,18 @@ cudaError_t launch_rnn_actor_pack(int agents, const float* const* ptrs, void* bl
 }
 
 cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* front, const float* obs, const float* hidden_in,
-                                     float* hidden_out, float* actions, int E, int N, int n_obs, cudaStream_t s) {
+                                     float* hidden_out, float* actions, int E, int N, int n_obs, float* ou_state,
+                                     float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed, uint32_t step,
+                                     int env_offset, cudaStream_t s) {
+    rnn::OuArgs ou;
+    ou.state = reinterpret_cast<float2*>(ou_state);
+    ou.theta_dt = ou_theta * ou_dt;
+    ou.mu = ou_mu;
+    ou.sigma_sqrt_dt = ou_sigma * sqrtf(ou_dt);
+    ou.seed_lo = (uint32_t)seed;
+    ou.seed_hi = (uint32_t)(seed >> 32);
+    ou.step = step;
+    ou.env_offset = env_offset;
     static cudaError_t configured = cudaFuncSetAttribute(rnn::flock_rnn_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          rnn::kSmemBytes);
     if (configured != cudaSuccess) return configured;
@@ -511,7 +548,7 @@ cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* fron
     const int per_cta = (total + sm_count - 1) / sm_count;
     const int grid = (total + per_cta - 1) / per_cta;
     rnn::flock_rnn_mlp_kernel<<<grid, rnn::kThreads, rnn::kSmemBytes, s>>>(static_cast<const uint8_t*>(blobs), hidden_out,
-                                                                         actions, E, N, tiles, per_cta);
+                                                                         actions, E, N, tiles, per_cta, ou);
     return cudaGetLastError();
 }
 

@@ -195,9 +195,13 @@ class BatchedRnnActors(torch.nn.Module):
 
     @torch.no_grad()
     def forward_fused(self, obs: torch.Tensor, hidden: torch.Tensor, out: Optional[torch.Tensor] = None,
-                      hidden_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                      hidden_out: Optional[torch.Tensor] = None, ou_state: Optional[torch.Tensor] = None,
+                      ou_theta: float = 0.15, ou_mu: float = 0.0, ou_sigma: float = 0.2, ou_dt: float = 1e-2, seed: int = 0,
+                      step: int = 0, env_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """`forward` in two kernel launches: fce + GRUCell in fp32 (the recurrent state stays exact), then the
-        32-400-300-2 MLP on the tensor cores (bf16 operands, fp32 accumulation). `hidden_out` may be `hidden`."""
+        32-400-300-2 MLP on the tensor cores (bf16 operands, fp32 accumulation). `hidden_out` may be `hidden`.
+        With `ou_state` ((E, N, 2) float32, zeros after a reset) the learner's Ornstein-Uhlenbeck exploration noise
+        (agent.py:61, utils.py:43-47) is added in the same launch, one process per (env, agent, action)."""
         from . import _lib
         lib = _lib.load_library()
         if getattr(self, "_packed", None) is None:
@@ -211,9 +215,18 @@ class BatchedRnnActors(torch.nn.Module):
         if hidden_out is None:
             hidden_out = torch.empty(E, N, self.hidden_rnn, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.check(lib.flock_rnn_actor_forward(self._packed.data_ptr(), self._front_ptrs, x.data_ptr(), h.data_ptr(),
-                                                   hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2],
-                                                   torch.cuda.current_stream().cuda_stream))
+            stream = torch.cuda.current_stream().cuda_stream
+            if ou_state is None:
+                _lib.check(lib.flock_rnn_actor_forward(self._packed.data_ptr(), self._front_ptrs, x.data_ptr(), h.data_ptr(),
+                                                       hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2], stream))
+            else:
+                if ou_state.shape != (E, N, 2) or ou_state.dtype != torch.float32 or not ou_state.is_contiguous():
+                    raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
+                _lib.check(lib.flock_rnn_actor_forward_ou(self._packed.data_ptr(), self._front_ptrs, x.data_ptr(), h.data_ptr(),
+                                                          hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2],
+                                                          ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
+                                                          float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
+                                                          stream))
         return out, hidden_out
 
     def forward(self, obs: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -82,3 +82,30 @@ def test_fused_rnn_actor_drives_the_env_with_the_state_updated_in_place():
         obs, reward, dones, _ = env.step(acts, 0.1)
     torch.cuda.synchronize()
     assert torch.isfinite(obs).all() and torch.isfinite(hidden).all()
+
+
+def test_fused_rnn_actor_ou_exploration_noise():
+    """flock_rnn_actor_forward_ou: sigma = 0 gives the deterministic recurrence exactly and actions = mu + x;
+    sigma > 0 gives unit-normal increments, reproducible per (seed, step)."""
+    dev = torch.device("cuda:0")
+    E, N = 2048, 10
+    a = _net(N, 4, 2, dev)
+    torch.manual_seed(4)
+    obs = torch.rand(E, N, 4, device=dev) * 14.0
+    hidden = torch.randn(E, N, 32, device=dev) * 0.3
+    mu_act, _ = a.forward_fused(obs, hidden)
+    mu_act = mu_act.clone()
+    theta, mu, sigma, dt = 0.15, 0.1, 0.2, 1e-2
+    x = torch.full((E, N, 2), 0.5, device=dev)
+    ref = x + theta * dt * (mu - x)
+    out, _ = a.forward_fused(obs, hidden, ou_state=x, ou_theta=theta, ou_mu=mu, ou_sigma=0.0, ou_dt=dt, seed=3, step=0)
+    assert torch.allclose(x, ref, atol=1e-6) and torch.allclose(out, mu_act + x, atol=1e-6)
+    x1, x2, x3 = (torch.zeros(E, N, 2, device=dev) for _ in range(3))
+    kw = dict(ou_theta=theta, ou_mu=mu, ou_sigma=sigma, ou_dt=dt, seed=3)
+    a.forward_fused(obs, hidden, ou_state=x1, step=1, **kw)
+    a.forward_fused(obs, hidden, ou_state=x2, step=1, **kw)
+    a.forward_fused(obs, hidden, ou_state=x3, step=2, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(x1, x2) and not torch.equal(x1, x3)
+    z = (x1 - theta * dt * mu) / (sigma * dt ** 0.5)
+    assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
