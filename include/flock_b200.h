@@ -33,7 +33,7 @@ extern "C" {
 #define FLOCK_API
 #endif
 
-#define FLOCK_ABI_VERSION 1
+#define FLOCK_ABI_VERSION 2
 #define FLOCK_MAX_K 8          /* neighbours per agent (reference uses 3, 4; BASELINE cfg 5 uses 8) */
 #define FLOCK_MAX_AGENTS 8192  /* per env; whole env is staged in shared memory */
 
@@ -73,12 +73,9 @@ typedef struct flock_cfg_t {
     uint64_t seed;              /* Philox4x32-10 key */
 } flock_cfg_t;
 
-/* Device pointers of the caller-owned buffers. `*_alt` are the second copy of the state used by
- * the tiled (N > 32) path, which ping-pongs between the two copies every step; they may be NULL
- * when N <= 32. Nullable outputs are skipped by the kernels. */
+/* Device pointers of the caller-owned buffers. Nullable outputs are skipped by the kernels. */
 typedef struct flock_buffers_t {
-    float *x, *y, *h;               /* [E][N] positions and headings, updated in place */
-    float *x_alt, *y_alt, *h_alt;   /* unused (kept for layout compatibility), may be NULL */
+    float *x, *y, *h;               /* [E][N] positions and headings, updated in place (both kernel paths) */
     float *prev_h;                  /* [E][N] `prev_headings` (uw reward term, gym_flock_uw.py:201) */
     float *vx, *vy;                 /* [E][N] last displacement = reference `velocities`; nullable */
     float *obs;                     /* [E][N][obs_hist][k] newest first (gym_flock_uw.py:120-123) */
@@ -183,9 +180,6 @@ FLOCK_API int flock_step_host_async(flock_env_t *env, const float *h_actions, fl
  * (an event recorded behind the result copy; other work on the stream is not waited for). */
 FLOCK_API int flock_wait_host(flock_env_t *env);
 
-/* Which state copy is current: always 0 (the state is updated in place; kept for ABI compatibility). */
-FLOCK_API int flock_state_slot(const flock_env_t *env);
-
 /* Host-side count of steps issued through this handle (informational). */
 FLOCK_API uint32_t flock_get_step_index(const flock_env_t *env);
 FLOCK_API int flock_set_step_index(flock_env_t *env, uint32_t step_index);
@@ -209,6 +203,18 @@ FLOCK_API int flock_set_tiled_mode(flock_env_t *env, int mode);
 
 FLOCK_API const char *flock_last_error(void);
 FLOCK_API int flock_abi_version(void);
+
+/* Device-side step counters for the exploration noise fused into the policy kernels below. The host scalar `step`
+ * of those calls is baked into a captured CUDA graph, so on replay every launch would redraw the same normals /
+ * uniforms; with counters the Philox counter words become
+ *     (env_offset + env, agent, step + env_step[env], tag + 16 * env_epoch[env])
+ * read on the DEVICE at launch time. Pass the env's own per-env counters -- ep_len (steps since the last reset) and
+ * reset_epoch (flock_buffers_t) -- and the draws are unique over the env's life, replay-safe and invariant under
+ * sharding, exactly like the env's own streams. NULL (or NULL members) = host `step` only: do not capture that. */
+typedef struct flock_noise_counters_t {
+    const int32_t *env_step;    /* [E] device, nullable */
+    const uint32_t *env_epoch;  /* [E] device, nullable */
+} flock_noise_counters_t;
 
 /* Fused per-agent actor MLP for the batched rollout ("MADDPG actor rollout", BASELINE configs[2]): the
  * N ActorNetworks of learners/maddpg_shared_critic/ddpg_network.py:85-141 (fc1 -> LayerNorm -> ReLU ->
@@ -235,7 +241,8 @@ FLOCK_API int flock_actor_forward(const void *packed, const float *obs, float *a
  * Philox4x32-10 with counter (env_offset + env, agent, step, tag) and key = seed: pass the rollout step as `step`. */
 FLOCK_API int flock_actor_forward_ou(const void *packed, const float *obs, float *actions, int num_envs, int num_agents,
                            int input_dims, float *ou_state, float theta, float mu, float sigma, float dt,
-                           uint64_t seed, uint32_t step, int env_offset, void *stream);
+                           uint64_t seed, uint32_t step, int env_offset, const flock_noise_counters_t *counters,
+                           void *stream);
 
 /* Fused recurrent MADDPG actor -- the policy of the reference's default main.py loop: `Actor` of
  * learners/maddpg_official_rnn/net.py:14-72 (fce(in,32) - GRUCell(32,32) - fc1(32,400) - ReLU - fc2(400,300) - ReLU -
@@ -260,7 +267,8 @@ FLOCK_API int flock_rnn_actor_forward(const void *packed, const float *const *fr
 FLOCK_API int flock_rnn_actor_forward_ou(const void *packed, const float *const *front_params, const float *obs,
                                const float *hidden_in, float *hidden_out, float *actions, int num_envs,
                                int num_agents, int n_obs, float *ou_state, float theta, float mu, float sigma,
-                               float dt, uint64_t seed, uint32_t step, int env_offset, void *stream);
+                               float dt, uint64_t seed, uint32_t step, int env_offset,
+                               const flock_noise_counters_t *counters, void *stream);
 
 /* Fused VDN action selection ("VDN action selection", BASELINE configs[3]): QNet.forward + QNet.sample_action of
  * learners/vdn/net.py:11-58 for all envs and agents in one fp32 launch, replacing the per-agent Python loop
@@ -275,7 +283,8 @@ FLOCK_API int flock_rnn_actor_forward_ou(const void *packed, const float *const 
  *   n_obs <= 16, n_actions <= 16. Asynchronous on `stream`. */
 FLOCK_API int flock_qnet_forward(const float *const *params, int recurrent, const float *obs, const float *hidden_in,
                        float *q_out, float *hidden_out, float *actions, int num_envs, int num_agents, int n_obs,
-                       int n_actions, float epsilon, uint64_t seed, uint32_t step, int env_offset, void *stream);
+                       int n_actions, float epsilon, uint64_t seed, uint32_t step, int env_offset,
+                       const flock_noise_counters_t *counters, void *stream);
 
 /* Debug / test hooks for the canonical arithmetic (device arrays, n elements). */
 FLOCK_API int flock_debug_sincos(const float *h, int n, float *sn, float *cs, void *stream);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FLOCK_LIBRARY_PATH lets a developer A/B an alternative build of the same ABI (still a CUDA library)
 LIB_PATH = os.environ.get("FLOCK_LIBRARY_PATH") or os.path.join(_HERE, "libflock_b200.so")
 
-FLOCK_ABI_VERSION = 1
+FLOCK_ABI_VERSION = 2
 FLOCK_MAX_K = 8
 FLOCK_MAX_AGENTS = 8192
 FLOCK_RESET_KEEP_OUTPUTS = 1
@@ -42,13 +42,27 @@ class FlockCfg(ctypes.Structure):
     ]
 
 
-BUFFER_FIELDS = ("x", "y", "h", "x_alt", "y_alt", "h_alt", "prev_h", "vx", "vy", "obs", "nn_idx", "reward",
+BUFFER_FIELDS = ("x", "y", "h", "prev_h", "vx", "vy", "obs", "nn_idx", "reward",
                  "agent_done", "env_done", "reset_epoch", "ep_return_fx", "ep_len", "stats")
 
 
 class FlockBuffers(ctypes.Structure):
     """flock_buffers_t"""
     _fields_ = [(n, ctypes.c_void_p) for n in BUFFER_FIELDS]
+
+
+class NoiseCounters(ctypes.Structure):
+    """flock_noise_counters_t"""
+    _fields_ = [("env_step", ctypes.c_void_p), ("env_epoch", ctypes.c_void_p)]
+
+
+def noise_counters(counters):
+    """ctypes argument for the `counters` parameter of the fused-noise entry points: None, or a pair of device
+    tensors (env_step int32 [E], env_epoch int32/uint32 [E]) such as `VecEnv.noise_counters`."""
+    if counters is None:
+        return None
+    step, epoch = counters
+    return ctypes.byref(NoiseCounters(None if step is None else step.data_ptr(), None if epoch is None else epoch.data_ptr()))
 
 
 _lib = None
@@ -76,7 +90,6 @@ def load_library() -> ctypes.CDLL:
         "flock_step_host": (i32, [vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "flock_step_host_async": (i32, [vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "flock_wait_host": (i32, [vp]),
-        "flock_state_slot": (i32, [vp]),
         "flock_get_step_index": (u32, [vp]),
         "flock_set_step_index": (i32, [vp, u32]),
         "flock_launch_count": (u64, [vp]),
@@ -87,13 +100,13 @@ def load_library() -> ctypes.CDLL:
         "flock_actor_packed_bytes": (ctypes.c_size_t, [i32]),
         "flock_actor_pack": (i32, [i32, i32, i32, i32, i32, ctypes.POINTER(vp), vp, vp]),
         "flock_actor_forward": (i32, [vp, vp, vp, i32, i32, i32, vp]),
-        "flock_actor_forward_ou": (i32, [vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32, u64, u32, i32, vp]),
+        "flock_actor_forward_ou": (i32, [vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32, u64, u32, i32, vp, vp]),
         "flock_rnn_actor_packed_bytes": (ctypes.c_size_t, [i32]),
         "flock_rnn_actor_pack": (i32, [i32, i32, i32, i32, i32, ctypes.POINTER(vp), vp, vp]),
         "flock_rnn_actor_forward": (i32, [vp, ctypes.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, vp]),
         "flock_rnn_actor_forward_ou": (i32, [vp, ctypes.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32,
-                                           u64, u32, i32, vp]),
-        "flock_qnet_forward": (i32, [ctypes.POINTER(vp), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u32, i32, vp]),
+                                           u64, u32, i32, vp, vp]),
+        "flock_qnet_forward": (i32, [ctypes.POINTER(vp), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u32, i32, vp, vp]),
         "flock_last_error": (ctypes.c_char_p, []),
         "flock_abi_version": (i32, []),
         "flock_debug_sincos": (i32, [vp, i32, vp, vp, vp]),

@@ -104,6 +104,8 @@ struct OuArgs {
     float theta_dt, mu, sigma_sqrt_dt;
     uint32_t seed_lo, seed_hi, step;
     int env_offset;
+    const int32_t* env_step;      // [E] device step counters added to `step` (nullable; replay-safe under CUDA graphs)
+    const uint32_t* env_epoch;    // [E] device epoch counters folded into the tag word (nullable)
 };
 constexpr uint32_t kTagOu = 6u;
 
@@ -453,7 +455,9 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
                 a.y = tanhf(o1 + b3[1]);
                 if (ou.state != nullptr) {
                     float2 x = ou.state[(size_t)env * N + agent];
-                    const uint4 rnd = philox4x32_10((uint32_t)(ou.env_offset + env), (uint32_t)agent, ou.step, kTagOu, ou.seed_lo,
+                    const uint32_t c2 = ou.step + (ou.env_step != nullptr ? (uint32_t)ou.env_step[env] : 0u);
+                    const uint32_t c3 = kTagOu + (ou.env_epoch != nullptr ? (ou.env_epoch[env] << 4) : 0u);
+                    const uint4 rnd = philox4x32_10((uint32_t)(ou.env_offset + env), (uint32_t)agent, c2, c3, ou.seed_lo,
                                                     ou.seed_hi);
                     float z0, z1;
                     normal2(rnd.x, rnd.y, z0, z1);
@@ -641,8 +645,10 @@ cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs,
 
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
                                  float* ou_state, float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed,
-                                 uint32_t step, int env_offset, cudaStream_t s) {
+                                 uint32_t step, int env_offset, NoiseCounters ctr, cudaStream_t s) {
     actor::OuArgs ou;
+    ou.env_step = ctr.env_step;
+    ou.env_epoch = ctr.env_epoch;
     ou.state = reinterpret_cast<float2*>(ou_state);
     ou.theta_dt = ou_theta * ou_dt;
     ou.mu = ou_mu;
@@ -651,15 +657,12 @@ cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* act
     ou.seed_hi = (uint32_t)(seed >> 32);
     ou.step = step;
     ou.env_offset = env_offset;
-    static cudaError_t configured = cudaFuncSetAttribute(actor::flock_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         actor::kSmemBytes);
+    static DeviceOnce once;
+    int sm_count = 148;
+    const cudaError_t configured = once.get(
+        [] { return cudaFuncSetAttribute(actor::flock_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, actor::kSmemBytes); },
+        &sm_count);
     if (configured != cudaSuccess) return configured;
-    static const int sm_count = [] {
-        int dev = 0, n = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n > 0 ? n : 148;
-    }();
     const int tiles = (E + actor::kRows - 1) / actor::kRows;
     const int total = tiles * N;
     const int per_cta = (total + sm_count - 1) / sm_count;          // contiguous run of items per CTA

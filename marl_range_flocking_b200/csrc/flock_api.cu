@@ -34,7 +34,6 @@ struct flock_env {
     int device;
     int sm_count;
     int path;            // 0 small, 1 tiled
-    int slot;            // current state copy on the tiled path
     int tiled_mode;      // 0 auto, 1 thread-per-row, 2 warp-per-row
     int auto_reset;      // flock_set_auto_reset: restart finished envs as part of flock_step
     int auto_reset_attempts;
@@ -309,7 +308,6 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         cudaFree(e->tile_perm);
         cudaFree(e->tile_inv);
         cudaFree(e->sorted_xy);
-    cudaFree(e->hint_slots);
         cudaFree(e->hint_slots);
         cudaFree(e->pair_counter);
         cudaFree(e->stage_actions);
@@ -342,7 +340,6 @@ int flock_bind(flock_env_t* e, const flock_buffers_t* b) {
         return fail(FLOCK_E_UNBOUND, "a required buffer pointer is NULL");
     e->b = *b;
     e->bound = true;
-    e->slot = 0;
     return FLOCK_OK;
 }
 
@@ -364,6 +361,9 @@ int flock_step(flock_env_t* e, const float* actions, float dt, const float* nois
     int rc = check_bound(e);
     if (rc != FLOCK_OK) return rc;
     if (actions == nullptr) return fail(FLOCK_E_INVALID, "actions is NULL");
+    // the kernels read (a0, a1) / (n_u, n_w) pairs as 8-byte vectors
+    if ((reinterpret_cast<uintptr_t>(actions) & (e->cfg.variant == FLOCK_UWD ? 3u : 7u)) || (reinterpret_cast<uintptr_t>(noise) & 7u))
+        return fail(FLOCK_E_INVALID, "actions / noise must be 8-byte aligned (4-byte for uw_discrete action ids)");
     return step_device(e, actions, dt, noise, static_cast<cudaStream_t>(stream));
 }
 
@@ -409,6 +409,8 @@ static int step_host_impl(flock_env_t* e, const float* h_actions, float dt, cons
     int rc = check_bound(e);
     if (rc != FLOCK_OK) return rc;
     if (h_actions == nullptr) return fail(FLOCK_E_INVALID, "h_actions is NULL");
+    if ((reinterpret_cast<uintptr_t>(h_actions) & (e->cfg.variant == FLOCK_UWD ? 3u : 7u)) || (reinterpret_cast<uintptr_t>(h_noise) & 7u))
+        return fail(FLOCK_E_INVALID, "h_actions / h_noise must be 8-byte aligned (4-byte for uw_discrete action ids)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t EN = (size_t)e->cfg.num_envs * e->cfg.num_agents;
     // Zero-copy fast path: when every host buffer is pinned (device-visible under UVA) the kernel
@@ -511,7 +513,6 @@ int flock_wait_host(flock_env_t* e) {
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "event synchronize");
 }
 
-int flock_state_slot(const flock_env_t* e) { return e ? e->slot : 0; }
 uint32_t flock_get_step_index(const flock_env_t* e) { return e ? e->step_index : 0u; }
 int flock_set_step_index(flock_env_t* e, uint32_t step_index) {
     if (e == nullptr) return fail(FLOCK_E_INVALID, "null handle");
@@ -566,9 +567,18 @@ int flock_actor_pack(int num_agents, int in_dims, int fc1_dims, int fc2_dims, in
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor pack kernel launch");
 }
 
+static flock::NoiseCounters noise_counters(const flock_noise_counters_t* c) {
+    flock::NoiseCounters n;
+    if (c != nullptr) {
+        n.env_step = c->env_step;
+        n.env_epoch = c->env_epoch;
+    }
+    return n;
+}
+
 static int actor_forward_impl(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
                               float* ou_state, float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step,
-                              int env_offset, void* stream) {
+                              int env_offset, const flock_noise_counters_t* counters, void* stream) {
     int rc = actor_check_dims(num_agents, in_dims, 400, 300, 2);
     if (rc != FLOCK_OK) return rc;
     if (packed == nullptr || obs == nullptr || actions == nullptr) return fail(FLOCK_E_INVALID, "null argument");
@@ -577,22 +587,24 @@ static int actor_forward_impl(const void* packed, const float* obs, float* actio
         (reinterpret_cast<uintptr_t>(actions) & 7u) || (reinterpret_cast<uintptr_t>(ou_state) & 7u))
         return fail(FLOCK_E_INVALID, "actor buffers must be 16-byte aligned");
     cudaError_t err = flock::launch_actor_forward(packed, obs, actions, num_envs, num_agents, in_dims, ou_state, theta, mu, sigma,
-                                                  dt, seed, step, env_offset, static_cast<cudaStream_t>(stream));
+                                                  dt, seed, step, env_offset, noise_counters(counters),
+                                                  static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor forward kernel launch");
 }
 
 int flock_actor_forward(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
                         void* stream) {
-    return actor_forward_impl(packed, obs, actions, num_envs, num_agents, in_dims, nullptr, 0.f, 0.f, 0.f, 0.f, 0ULL, 0u, 0, stream);
+    return actor_forward_impl(packed, obs, actions, num_envs, num_agents, in_dims, nullptr, 0.f, 0.f, 0.f, 0.f, 0ULL, 0u, 0, nullptr,
+                              stream);
 }
 
 int flock_actor_forward_ou(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
                            float* ou_state, float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step,
-                           int env_offset, void* stream) {
+                           int env_offset, const flock_noise_counters_t* counters, void* stream) {
     if (ou_state == nullptr) return fail(FLOCK_E_INVALID, "ou_state is NULL");
     if (!(dt >= 0.0f) || !(sigma >= 0.0f)) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
     return actor_forward_impl(packed, obs, actions, num_envs, num_agents, in_dims, ou_state, theta, mu, sigma, dt, seed, step,
-                              env_offset, stream);
+                              env_offset, counters, stream);
 }
 
 size_t flock_rnn_actor_packed_bytes(int num_agents) {
@@ -615,7 +627,7 @@ int flock_rnn_actor_pack(int num_agents, int hidden_rnn, int hidden1, int hidden
 static int rnn_actor_forward_impl(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
                                   float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, float* ou_state,
                                   float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step, int env_offset,
-                                  void* stream) {
+                                  const flock_noise_counters_t* counters, void* stream) {
     if (packed == nullptr || front_params == nullptr || obs == nullptr || hidden_in == nullptr || hidden_out == nullptr ||
         actions == nullptr)
         return fail(FLOCK_E_INVALID, "null argument");
@@ -633,29 +645,30 @@ static int rnn_actor_forward_impl(const void* packed, const float* const* front_
         return fail(FLOCK_E_INVALID, "recurrent actor buffers must be 16-byte aligned");
     cudaError_t err = flock::launch_rnn_actor_forward(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs,
                                                       num_agents, n_obs, ou_state, theta, mu, sigma, dt, seed, step, env_offset,
-                                                      static_cast<cudaStream_t>(stream));
+                                                      noise_counters(counters), static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor kernel launch");
 }
 
 int flock_rnn_actor_forward(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
                             float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, void* stream) {
     return rnn_actor_forward_impl(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs, num_agents, n_obs, nullptr,
-                                  0.f, 0.f, 0.f, 0.f, 0ULL, 0u, 0, stream);
+                                  0.f, 0.f, 0.f, 0.f, 0ULL, 0u, 0, nullptr, stream);
 }
 
 int flock_rnn_actor_forward_ou(const void* packed, const float* const* front_params, const float* obs, const float* hidden_in,
                                float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, float* ou_state,
                                float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step, int env_offset,
-                               void* stream) {
+                               const flock_noise_counters_t* counters, void* stream) {
     if (ou_state == nullptr) return fail(FLOCK_E_INVALID, "ou_state is NULL");
     if (!(dt >= 0.0f) || !(sigma >= 0.0f)) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
     return rnn_actor_forward_impl(packed, front_params, obs, hidden_in, hidden_out, actions, num_envs, num_agents, n_obs, ou_state,
-                                  theta, mu, sigma, dt, seed, step, env_offset, stream);
+                                  theta, mu, sigma, dt, seed, step, env_offset, counters, stream);
 }
 
 int flock_qnet_forward(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
                        float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, int n_actions,
-                       float epsilon, uint64_t seed, uint32_t step, int env_offset, void* stream) {
+                       float epsilon, uint64_t seed, uint32_t step, int env_offset, const flock_noise_counters_t* counters,
+                       void* stream) {
     if (params == nullptr || obs == nullptr) return fail(FLOCK_E_INVALID, "null argument");
     if (num_envs < 1 || num_agents < 1 || num_agents > 65535) return fail(FLOCK_E_INVALID, "bad num_envs / num_agents");
     if (n_obs < 1 || n_obs > flock::qnet_max_obs()) return fail(FLOCK_E_INVALID, "n_obs %d not in [1, %d]", n_obs, flock::qnet_max_obs());
@@ -671,7 +684,8 @@ int flock_qnet_forward(const float* const* params, int recurrent, const float* o
         return fail(FLOCK_E_INVALID, "hidden state buffers must be 16-byte aligned");
     if (!(epsilon >= 0.0f)) return fail(FLOCK_E_INVALID, "epsilon must be >= 0");
     cudaError_t err = flock::launch_qnet(params, recurrent, obs, hidden_in, q_out, hidden_out, actions, num_envs, num_agents,
-                                         n_obs, n_actions, epsilon, seed, step, env_offset, static_cast<cudaStream_t>(stream));
+                                         n_obs, n_actions, epsilon, seed, step, env_offset, noise_counters(counters),
+                                         static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "qnet kernel launch");
 }
 

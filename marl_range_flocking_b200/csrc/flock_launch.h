@@ -6,6 +6,39 @@
 namespace flock {
 struct Params;
 
+// Per-device one-time kernel configuration (dynamic shared memory opt-in, SM count): a process may drive
+// several GPUs (VecEnv / the policies take device=...), and a function attribute belongs to the device
+// that was current when it was set.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+    bool done[kMaxDevices] = {};
+    int sm_count[kMaxDevices] = {};
+    // returns the current device's SM count; runs `configure` the first time this device is seen
+    template <typename F>
+    cudaError_t get(F configure, int* sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kMaxDevices) dev = kMaxDevices - 1, done[dev] = false;
+        if (!done[dev]) {
+            e = configure();
+            if (e != cudaSuccess) return e;
+            int n = 0;
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            sm_count[dev] = n > 0 ? n : 148;
+            done[dev] = true;
+        }
+        *sms = sm_count[dev];
+        return cudaSuccess;
+    }
+};
+
+// device-side step counters of the fused exploration noise (flock_noise_counters_t)
+struct NoiseCounters {
+    const int32_t* env_step = nullptr;
+    const uint32_t* env_epoch = nullptr;
+};
+
 // flock_small.cu (N <= 32)
 cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool multi, int sm_count, cudaStream_t s);
 cudaError_t launch_reset_small(const Params& p, int sm_count, cudaStream_t s);
@@ -34,14 +67,14 @@ void actor_dims(int* fc1, int* fc2, int* n_actions);
 cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s);
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
                                  float* ou_state, float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed,
-                                 uint32_t step, int env_offset, cudaStream_t s);
+                                 uint32_t step, int env_offset, NoiseCounters ctr, cudaStream_t s);
 
 // flock_qnet.cu (fused VDN Q-network forward + epsilon-greedy action selection, fp32)
 int qnet_max_obs();
 int qnet_max_actions();
 cudaError_t launch_qnet(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
                         float* hidden_out, float* actions, int E, int A, int n_obs, int n_act, float epsilon, uint64_t seed,
-                        uint32_t step, int env_offset, cudaStream_t s);
+                        uint32_t step, int env_offset, NoiseCounters ctr, cudaStream_t s);
 
 // flock_rnn_actor.cu (fused recurrent MADDPG actor: fp32 GRU front end + tensor-core MLP)
 size_t rnn_actor_blob_bytes();
@@ -50,5 +83,5 @@ cudaError_t launch_rnn_actor_pack(int agents, const float* const* ptrs, void* bl
 cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* front, const float* obs, const float* hidden_in,
                                      float* hidden_out, float* actions, int E, int N, int n_obs, float* ou_state,
                                      float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed, uint32_t step,
-                                     int env_offset, cudaStream_t s);
+                                     int env_offset, NoiseCounters ctr, cudaStream_t s);
 }  // namespace flock

@@ -33,6 +33,8 @@ struct Args {
     int E, A, n_obs, n_act, env_offset;
     float epsilon;
     uint32_t seed_lo, seed_hi, step;
+    const int32_t* env_step;      // [E] device step counters added to `step` (nullable; replay-safe under CUDA graphs)
+    const uint32_t* env_epoch;    // [E] device epoch counters folded into the tag words (nullable)
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -199,9 +201,11 @@ __global__ void __launch_bounds__(kThreads, 2) flock_qnet_kernel(const __grid_co
                 best = j;
             }
         const uint32_t ge = (uint32_t)(a.env_offset + env);
-        const uint4 re = philox4x32_10(ge, 0xffffffffu, a.step, kTagExplore, a.seed_lo, a.seed_hi);
+        const uint32_t c2 = a.step + (a.env_step != nullptr ? (uint32_t)a.env_step[env] : 0u);
+        const uint32_t ep = a.env_epoch != nullptr ? (a.env_epoch[env] << 4) : 0u;
+        const uint4 re = philox4x32_10(ge, 0xffffffffu, c2, kTagExplore + ep, a.seed_lo, a.seed_hi);
         if (u24(re.x) <= a.epsilon && a.epsilon > 0.0f) {
-            const uint4 ra = philox4x32_10(ge, (uint32_t)agent, a.step, kTagRandAct, a.seed_lo, a.seed_hi);
+            const uint4 ra = philox4x32_10(ge, (uint32_t)agent, c2, kTagRandAct + ep, a.seed_lo, a.seed_hi);
             best = (int)(((unsigned long long)ra.x * (unsigned long long)n_act) >> 32);
         }
         a.actions[ea] = (float)best;
@@ -215,8 +219,10 @@ int qnet_max_actions() { return qnet::kMaxAct; }
 
 cudaError_t launch_qnet(const float* const* params, int recurrent, const float* obs, const float* hidden_in, float* q_out,
                         float* hidden_out, float* actions, int E, int A, int n_obs, int n_act, float epsilon, uint64_t seed,
-                        uint32_t step, int env_offset, cudaStream_t s) {
+                        uint32_t step, int env_offset, NoiseCounters ctr, cudaStream_t s) {
     qnet::Args a;
+    a.env_step = ctr.env_step;
+    a.env_epoch = ctr.env_epoch;
     a.w1 = params[0]; a.b1 = params[1]; a.w2 = params[2]; a.b2 = params[3]; a.wq = params[4]; a.bq = params[5];
     a.w_ih = recurrent ? params[6] : nullptr; a.b_ih = recurrent ? params[7] : nullptr;
     a.w_hh = recurrent ? params[8] : nullptr; a.b_hh = recurrent ? params[9] : nullptr;
@@ -229,7 +235,11 @@ cudaError_t launch_qnet(const float* const* params, int recurrent, const float* 
     const size_t bytes = floats * sizeof(float);
     const dim3 grid((unsigned)A, (unsigned)((E + qnet::kThreads - 1) / qnet::kThreads));
     if (recurrent) {
-        static cudaError_t cfg = cudaFuncSetAttribute(qnet::flock_qnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        static DeviceOnce once;
+        int sms = 0;
+        const cudaError_t cfg = once.get(
+            [] { return cudaFuncSetAttribute(qnet::flock_qnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); },
+            &sms);
         if (cfg != cudaSuccess) return cfg;
         qnet::flock_qnet_kernel<true><<<grid, qnet::kThreads, bytes, s>>>(a);
     } else {

@@ -79,6 +79,8 @@ struct OuArgs {
     float theta_dt, mu, sigma_sqrt_dt;
     uint32_t seed_lo, seed_hi, step;
     int env_offset;
+    const int32_t* env_step;      // [E] device step counters added to `step` (nullable; replay-safe under CUDA graphs)
+    const uint32_t* env_epoch;    // [E] device epoch counters folded into the tag word (nullable)
 };
 constexpr uint32_t kTagOu = 7u;
 
@@ -314,7 +316,9 @@ flock_rnn_mlp_kernel(const uint8_t* __restrict__ blobs, const float* __restrict_
                 a.y = tanhf(o1 + bh[1]) * 1.5f;              // net.py:70-71
                 if (ou.state != nullptr) {
                     float2 x = ou.state[(size_t)env * N + agent];
-                    const uint4 rnd = philox4x32_10((uint32_t)(ou.env_offset + env), (uint32_t)agent, ou.step, kTagOu, ou.seed_lo,
+                    const uint32_t c2 = ou.step + (ou.env_step != nullptr ? (uint32_t)ou.env_step[env] : 0u);
+                    const uint32_t c3 = kTagOu + (ou.env_epoch != nullptr ? (ou.env_epoch[env] << 4) : 0u);
+                    const uint4 rnd = philox4x32_10((uint32_t)(ou.env_offset + env), (uint32_t)agent, c2, c3, ou.seed_lo,
                                                     ou.seed_hi);
                     float z0, z1;
                     normal2(rnd.x, rnd.y, z0, z1);
@@ -515,8 +519,10 @@ cudaError_t launch_rnn_actor_pack(int agents, const float* const* ptrs, void* bl
 cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* front, const float* obs, const float* hidden_in,
                                      float* hidden_out, float* actions, int E, int N, int n_obs, float* ou_state,
                                      float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed, uint32_t step,
-                                     int env_offset, cudaStream_t s) {
+                                     int env_offset, NoiseCounters ctr, cudaStream_t s) {
     rnn::OuArgs ou;
+    ou.env_step = ctr.env_step;
+    ou.env_epoch = ctr.env_epoch;
     ou.state = reinterpret_cast<float2*>(ou_state);
     ou.theta_dt = ou_theta * ou_dt;
     ou.mu = ou_mu;
@@ -525,15 +531,12 @@ cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* fron
     ou.seed_hi = (uint32_t)(seed >> 32);
     ou.step = step;
     ou.env_offset = env_offset;
-    static cudaError_t configured = cudaFuncSetAttribute(rnn::flock_rnn_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         rnn::kSmemBytes);
+    static DeviceOnce once;
+    int sm_count = 148;
+    const cudaError_t configured = once.get(
+        [] { return cudaFuncSetAttribute(rnn::flock_rnn_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rnn::kSmemBytes); },
+        &sm_count);
     if (configured != cudaSuccess) return configured;
-    static const int sm_count = [] {
-        int dev = 0, n = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n > 0 ? n : 148;
-    }();
     // launch 1 of 2: fce + GRUCell (fp32); the hidden state may be updated in place (each thread reads its own
     // row before it writes it)
     rnn::FrontArgs fa{front[0], front[1], front[2], front[3], front[4], front[5], obs, hidden_in, hidden_out, E, N, n_obs};

@@ -1129,7 +1129,11 @@ static cudaError_t opt_in(Kern kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t tiled_configure(int num_agents) {
+// The opt-in is an attribute of the FUNCTION on the current device, not of an env handle, so it is always
+// raised to the worst case (FLOCK_MAX_AGENTS): a later, smaller env can then never lower the limit under an
+// earlier, larger one. Called by every flock_create after cudaSetDevice (idempotent per device).
+cudaError_t tiled_configure(int /*num_agents*/) {
+    const int num_agents = FLOCK_MAX_AGENTS;
     const size_t b = tiled_smem_bytes(num_agents, kMaxTileThreads, true);
     cudaError_t e = cudaSuccess;
     {

@@ -85,14 +85,18 @@ class BatchedActors(torch.nn.Module):
     @torch.no_grad()
     def forward_fused(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None, ou_state: Optional[torch.Tensor] = None,
                       ou_theta: float = 0.2, ou_mu: float = 0.0, ou_sigma: float = 0.15, ou_dt: float = 1e-2, seed: int = 0,
-                      step: int = 0, env_offset: int = 0) -> torch.Tensor:
+                      step: int = 0, env_offset: int = 0, counters=None) -> torch.Tensor:
         """Same function as `forward` in ONE kernel launch on the tensor cores (bf16 operands, fp32
         accumulation / LayerNorm): `(E, N, ...)` float32 CUDA observations -> `(E, N, 2)` actions.
 
         With `ou_state` (an `(E, N, 2)` float32 CUDA tensor, zeros after a reset) the learner's exploration noise is
         fused into the same launch: one Ornstein-Uhlenbeck process per (env, agent, action) as in
         `OUActionNoiseGPU` (learners/maddpg_shared_critic/utils.py:6-21), `actions = mu + x` with
-        `x <- x + theta (mu_ou - x) dt + sigma sqrt(dt) N(0,1)` updated in place; normals from Philox(seed; env, agent, step)."""
+        `x <- x + theta (mu_ou - x) dt + sigma sqrt(dt) N(0,1)` updated in place; normals from Philox(seed; env, agent, step).
+
+        `step` is a HOST scalar: captured in a CUDA graph (e.g. `rollout.GraphedRollout`) it would be frozen and every
+        replay would redraw the same normals. Pass `counters=env.noise_counters` (per-env device counters, added to
+        `step` inside the kernel) whenever the launch may be captured."""
         from . import _lib
         lib = _lib.load_library()
         if getattr(self, "_packed", None) is None:
@@ -112,7 +116,8 @@ class BatchedActors(torch.nn.Module):
                     raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
                 _lib.check(lib.flock_actor_forward_ou(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2],
                                                       ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
-                                                      float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset), stream))
+                                                      float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
+                                                      _lib.noise_counters(counters), stream))
         return out
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
@@ -197,11 +202,12 @@ class BatchedRnnActors(torch.nn.Module):
     def forward_fused(self, obs: torch.Tensor, hidden: torch.Tensor, out: Optional[torch.Tensor] = None,
                       hidden_out: Optional[torch.Tensor] = None, ou_state: Optional[torch.Tensor] = None,
                       ou_theta: float = 0.15, ou_mu: float = 0.0, ou_sigma: float = 0.2, ou_dt: float = 1e-2, seed: int = 0,
-                      step: int = 0, env_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                      step: int = 0, env_offset: int = 0, counters=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """`forward` in two kernel launches: fce + GRUCell in fp32 (the recurrent state stays exact), then the
         32-400-300-2 MLP on the tensor cores (bf16 operands, fp32 accumulation). `hidden_out` may be `hidden`.
         With `ou_state` ((E, N, 2) float32, zeros after a reset) the learner's Ornstein-Uhlenbeck exploration noise
-        (agent.py:61, utils.py:43-47) is added in the same launch, one process per (env, agent, action)."""
+        (agent.py:61, utils.py:43-47) is added in the same launch, one process per (env, agent, action). Pass
+        `counters=env.noise_counters` when the launch may be captured in a CUDA graph (see BatchedActors.forward_fused)."""
         from . import _lib
         lib = _lib.load_library()
         if getattr(self, "_packed", None) is None:
@@ -226,7 +232,7 @@ class BatchedRnnActors(torch.nn.Module):
                                                           hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2],
                                                           ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
                                                           float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
-                                                          stream))
+                                                          _lib.noise_counters(counters), stream))
         return out, hidden_out
 
     def forward(self, obs: torch.Tensor, hidden: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -317,7 +323,8 @@ class BatchedQNet(torch.nn.Module):
 
     # ---- fused path (csrc/flock_qnet.cu through the C ABI): one fp32 launch for all envs and agents ----
     @torch.no_grad()
-    def _fused(self, obs, hidden, want_q: bool, want_actions: bool, epsilon: float, step: int, seed: int, env_offset: int):
+    def _fused(self, obs, hidden, want_q: bool, want_actions: bool, epsilon: float, step: int, seed: int, env_offset: int,
+               out=None, hidden_out=None, counters=None):
         import ctypes
 
         from . import _lib
@@ -338,16 +345,16 @@ class BatchedQNet(torch.nn.Module):
         ptrs = cache[1]
         dev = x.device
         q = torch.empty(E, N, A, dtype=torch.float32, device=dev) if want_q else None
-        act = torch.empty(E, N, dtype=torch.float32, device=dev) if want_actions else None
+        act = (out if out is not None else torch.empty(E, N, dtype=torch.float32, device=dev)) if want_actions else None
         h_in = h_out = None
         if self.recurrent:
             h_in = hidden if (hidden.dtype == torch.float32 and hidden.is_contiguous()) else hidden.float().contiguous()
-            h_out = torch.empty(E, N, self.hx_size, dtype=torch.float32, device=dev)
+            h_out = hidden_out if hidden_out is not None else torch.empty(E, N, self.hx_size, dtype=torch.float32, device=dev)
         p = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(dev):
             _lib.check(lib.flock_qnet_forward(ptrs, int(self.recurrent), x.data_ptr(), p(h_in), p(q), p(h_out), p(act), E, N,
                                               n_obs, A, float(epsilon), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
-                                              torch.cuda.current_stream().cuda_stream))
+                                              _lib.noise_counters(counters), torch.cuda.current_stream().cuda_stream))
         if h_out is None:
             h_out = torch.empty(E, N, self.hx_size, device=dev)      # like `forward`: unused without the GRU
         return q, h_out, act
@@ -358,11 +365,15 @@ class BatchedQNet(torch.nn.Module):
         return q, h
 
     def sample_action_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor], epsilon: float, step: int = 0,
-                            seed: int = 0, env_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                            seed: int = 0, env_offset: int = 0, out: Optional[torch.Tensor] = None,
+                            hidden_out: Optional[torch.Tensor] = None, counters=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """`sample_action` (net.py:52-58) in one kernel launch: Q-values, argmax and the per-env epsilon-greedy
         decision never leave the SM. Exploration draws are Philox(seed; env_offset + env, agent, step), i.e.
-        reproducible and invariant under env sharding -- pass the rollout step as `step`."""
-        _, h, act = self._fused(obs, hidden, False, True, epsilon, step, seed, env_offset)
+        reproducible and invariant under env sharding -- pass the rollout step as `step`, or, when the launch may be
+        captured in a CUDA graph (a host `step` is frozen there), `counters=env.noise_counters`. `out` (E, N) and
+        `hidden_out` (E, N, 32; may be `hidden`) receive the results in place when given."""
+        _, h, act = self._fused(obs, hidden, False, True, epsilon, step, seed, env_offset, out=out, hidden_out=hidden_out,
+                                counters=counters)
         return act, h
 
     @torch.no_grad()

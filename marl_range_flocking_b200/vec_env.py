@@ -115,16 +115,14 @@ class VecEnv:
         self._stats = z(8, dtype=torch.int64)
         ptr = lambda t: None if t is None else t.data_ptr()
         bufs = FlockBuffers(
-            ptr(self._x), ptr(self._y), ptr(self._hd), None, None, None,    # x_alt / y_alt / h_alt: unused (ABI v1 slots)
-            ptr(self._prev_h), ptr(self._vx), ptr(self._vy), ptr(self._obs), ptr(self._nn), ptr(self._reward),
+            ptr(self._x), ptr(self._y), ptr(self._hd), ptr(self._prev_h), ptr(self._vx), ptr(self._vy), ptr(self._obs), ptr(self._nn), ptr(self._reward),
             ptr(self._agent_done), ptr(self._env_done), ptr(self._reset_epoch), ptr(self._ep_return_fx),
             ptr(self._ep_len), ptr(self._stats))
         check(self.lib.flock_bind(self._h, ctypes.byref(bufs)))
         self._host = None   # pinned host mirrors for step_host
         self._host_async = None   # side stream + validated action buffers of step_host_async
         self._dev_index = self.device.index
-        self._numel_cache = {}
-        self._act_shape = (E, N) if variant == "uwd" else (E, N, 2)
+        self._act_shape = torch.Size((E, N) if variant == "uwd" else (E, N, 2))
         self._obs_view = self._obs if self.obs_hist > 1 else self._obs[:, :, 0, :]
 
     # ------------------------------------------------------------------------------------------
@@ -163,17 +161,20 @@ class VecEnv:
         return torch.cuda.device(self.device)
 
     def _as_input(self, t, shape, name) -> torch.Tensor:
-        # fast path: already a contiguous float32 tensor of the right size on our device
+        # fast path: already a contiguous float32 tensor of the right shape on our device, 8-byte aligned (the
+        # kernels read action / noise pairs as float2; a view with an odd element offset would fault)
         if (type(t) is torch.Tensor and t.dtype is torch.float32 and t.device == self.device and t.is_contiguous()
-                and t.numel() == self._numel_cache.get(shape, -1)):
+                and t.shape == shape and not (t.data_ptr() & 7)):
             return t
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t)
         t = t.to(device=self.device, dtype=torch.float32)
         if t.numel() != math.prod(shape):
             raise ValueError(f"{name} has {t.numel()} elements, expected shape {tuple(shape)}")
-        self._numel_cache[shape] = math.prod(shape)
-        return t.reshape(shape).contiguous()
+        t = t.reshape(shape).contiguous()
+        if t.data_ptr() & 7:
+            t = t.clone()                 # a fresh allocation is at least 256-byte aligned
+        return t
 
     # ---- views of the device state (zero copy; overwritten by the next step) ------------------
     @property
@@ -247,6 +248,13 @@ class VecEnv:
         return int(self.lib.flock_pairs_evaluated(self._h, int(reset)))
 
     @property
+    def noise_counters(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(ep_len, reset_epoch): the per-env DEVICE counters to pass as `counters=` to the fused policy kernels
+        (`forward_fused(..., ou_state=...)`, `sample_action_fused`), so that their exploration draws advance with the
+        env even when the launch is replayed from a CUDA graph (flock_noise_counters_t)."""
+        return self._ep_len, self._reset_epoch
+
+    @property
     def launch_count(self) -> int:
         return int(self.lib.flock_launch_count(self._h))
 
@@ -261,7 +269,7 @@ class VecEnv:
             m = mask.to(device=self.device).reshape(self.num_envs)
             m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
             m = m.contiguous()
-        ini = None if init_state is None else self._as_input(init_state, (3, self.num_envs, self.num_particles), "init_state")
+        ini = None if init_state is None else self._as_input(init_state, torch.Size((3, self.num_envs, self.num_particles)), "init_state")
         with self._dev_guard():
             check(self.lib.flock_reset(self._h, None if m is None else m.data_ptr(),
                                        None if ini is None else ini.data_ptr(), self.max_reset_attempts,
@@ -274,7 +282,7 @@ class VecEnv:
         Returns `(obs, reward (E,N,1), (agent_done (E,N) bool, env_done (E,) bool), {})`; all are
         views of env-owned device tensors."""
         a = self._as_input(actions, self._act_shape, "actions")
-        nz = None if noise is None else self._as_input(noise, (self.num_envs, self.num_particles, 2), "noise")
+        nz = None if noise is None else self._as_input(noise, torch.Size((self.num_envs, self.num_particles, 2)), "noise")
         with self._dev_guard():
             rc = self.lib.flock_step(self._h, a.data_ptr(), dt, None if nz is None else nz.data_ptr(), self._stream())
             if rc:

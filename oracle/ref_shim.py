@@ -19,12 +19,16 @@ GPU exists in the build container, so the shim
     gym_flock_uw_discrete.py:333-334) by `mean + <noise we supply>` so the same
     noise can be fed to the oracle / the CUDA kernels.
 
-It cannot travel to the GPU box: nothing in `-m gpu` tests, `smoke()` or
-`bench.py` imports it.
+The reference TREE does not travel to the GPU box. What does travel is `oracle/_ref/`
+(git-ignored build output of `oracle/build_ref.py`: the three environment modules byte-compiled
+from where they lie under /root/reference). When /root/reference is absent the shim loads that
+bytecode with importlib's sourceless loader, so the CPU-baseline legs of `bench.py` can time the
+UNMODIFIED reference step on the box's host cores. `-m gpu` tests and `smoke()` never import it.
 """
 from __future__ import annotations
 
 import contextlib
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -40,8 +44,23 @@ _VARIANT_FILES = {
 }
 
 
+_REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
 def reference_available() -> bool:
+    """The reference source tree is present (build container)."""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "environments", _VARIANT_FILES["v2"]))
+
+
+def compiled_reference_available() -> bool:
+    """oracle/_ref/ holds the byte-compiled reference modules for THIS interpreter version."""
+    try:
+        with open(os.path.join(_REF_DIR, "PYTHON_VERSION")) as fh:
+            if fh.read().strip() != "%d.%d" % sys.version_info[:2]:
+                return False
+    except OSError:
+        return False
+    return all(os.path.isfile(os.path.join(_REF_DIR, f + "c")) for f in _VARIANT_FILES.values())
 
 
 def _install_stubs() -> None:
@@ -87,11 +106,16 @@ def load_reference(variant: str):
     """Return the reference module for `variant` in {"v2","uw","uwd"} (cached)."""
     if variant in _loaded:
         return _loaded[variant]
-    if not reference_available():
-        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+    name = f"_flock_reference_{variant}"
+    if reference_available():
+        path = os.path.join(REFERENCE_ROOT, "environments", _VARIANT_FILES[variant])
+        spec = importlib.util.spec_from_file_location(name, path)
+    elif compiled_reference_available():
+        path = os.path.join(_REF_DIR, _VARIANT_FILES[variant] + "c")
+        spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, path))
+    else:
+        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT} and no compiled copy in {_REF_DIR}")
     _install_stubs()
-    path = os.path.join(REFERENCE_ROOT, "environments", _VARIANT_FILES[variant])
-    spec = importlib.util.spec_from_file_location(f"_flock_reference_{variant}", path)
     mod = importlib.util.module_from_spec(spec)
     cwd = os.getcwd()
     scratch = tempfile.mkdtemp(prefix="flock_ref_")

@@ -187,5 +187,27 @@ def test_bench_reference_arm_prints_one_json_line():
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     j = json.loads(lines[0])
-    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] in ("reference", "port")
+    assert j["cpu_baseline"]["port"]["value"] > 0          # the C port is always timed next to the reference
+    if j["cpu_baseline"]["kind"] == "reference":           # oracle/_ref present: the unmodified reference step
+        assert "unmodified reference" in j["cpu_baseline"]["sample"] and j["value"] < j["cpu_baseline"]["port"]["value"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["unit"] == "agent-steps/s"
+    # the config object is the GPU arm's, key for key (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert j["config"] == bench.config_of("cfg2", bench.WORKLOADS["cfg2"])
+
+
+def test_compiled_reference_loads_without_the_source_tree():
+    """oracle/build_ref.py byte-compiles the reference env modules into oracle/_ref; the shim must be able to
+    load them when /root/reference is absent (what bench.py does on the GPU box)."""
+    from oracle import build_ref
+    if not build_ref.build_ref():
+        pytest.skip("no reference tree and no compiled copy on this machine")
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['FLOCK_REFERENCE_ROOT'] = '/nonexistent';"
+            "from oracle import ref_shim; assert not ref_shim.reference_available() and ref_shim.compiled_reference_available();"
+            "import torch; m = ref_shim.load_reference('uw'); e = m.MultiAgentEnv(agents=6, k=3, collision_distance=0.5, range_start=(0, 100));"
+            "o = e.reset(); o, r, d, _ = e.step(torch.rand(6, 2)); assert o.shape == (6, 4, 3) and r.shape == (6, 1)") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stderr[-2000:]

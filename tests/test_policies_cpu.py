@@ -131,7 +131,7 @@ def test_actor_and_qnet_entry_points_validate_arguments_without_a_gpu():
     assert b"400-300-2" in lib.flock_last_error()
     assert lib.flock_actor_pack(2, 15, 400, 300, 2, null10, None, None) == -1          # input width
     assert lib.flock_actor_forward(None, None, None, 128, 2, 12, None) == -1
-    assert lib.flock_qnet_forward(null10, 1, None, None, None, None, None, 8, 2, 4, 4, 0.1, 0, 0, 0, None) == -1
+    assert lib.flock_qnet_forward(null10, 1, None, None, None, None, None, 8, 2, 4, 4, 0.1, 0, 0, 0, None, None) == -1
     assert lib.flock_wait_host(None) == -1
 
 
