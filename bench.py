@@ -50,7 +50,6 @@ WORKLOADS = {
 }
 L2_BYTES = 126 * 1024 * 1024
 DT = 0.1
-SHORT_MAX_STEPS = 2048      # up to here K steps are one graph and the median of many repetitions is reported
 
 
 def config_of(name, w):
@@ -278,12 +277,16 @@ def ref_run(w, steps, warmup, budget_s, workers=None, torch_threads=1, m_max=Non
                         warmup=warmup, budget_s=budget_s, m_max=m_max, torch_threads=torch_threads, seed=i, index=i,
                         workers=P, sync_dir=sync_dir if P > 1 else None)
             procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", json.dumps(spec)],
-                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT, text=True))
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, cwd=ROOT, text=True))
         outs = []
         for p in procs:
-            out, _ = p.communicate(timeout=600)
+            out, err = p.communicate(timeout=600)
             lines = [l for l in out.splitlines() if l.startswith("{")]
             if p.returncode != 0 or not lines:
+                sys.stderr.write("reference worker failed:\n" + err[-1500:] + "\n")
+                for q in procs:
+                    if q.poll() is None:
+                        q.kill()
                 return None
             outs.append(json.loads(lines[-1]))
     envs = sum(o["m"] for o in outs)
@@ -397,78 +400,54 @@ def capture(envs, acts, n, start):
     return g, sum(e.launch_count for e in envs) - before       # kernel nodes in the graph
 
 
-def timed_graph_steps(envs, acts, steps, warmup, device, barrier, reduce_max, target_ms=40.0):
-    """Device time of exactly `steps` steps (max over ranks). Returns a dict with ms (per `steps` steps), the number
-    of repetitions the median was taken over, the kernel launches inside ALL timed repetitions, and the spread."""
+def timed_graph_steps(envs, acts, steps, warmup, device, barrier, reduce_max, target_steps=8192):
+    """Device time per step of the sustained step stream (max over ranks).
+
+    The unit of timing is one repetition = exactly `steps` steps. A short repetition cannot be timed alone: measured
+    on B200 (profiles/README.md, round 2), a 20-step graph bracketed by its own event pair reads 3.55 us per step
+    where the sustained stream runs at 3.02, because every isolated graph launch carries ~10 us of launch head. So
+    `repeats` = ceil(target_steps / steps) repetitions are enqueued back to back as ONE contiguous stream (CUDA
+    graphs of ~1000 steps continuing the ring where the previous one stopped, every graph exec replayed un-timed
+    first) and timed as one region; this is done three times and the median region is reported. `--steps 20`
+    therefore measures the same thing as `--steps 20480`. Returns ms per `steps` steps and the bookkeeping."""
     import torch
 
     R = len(envs)
-    if steps <= SHORT_MAX_STEPS:
-        # every repetition starts where the previous one ended on the ring, so it always meets batches that
-        # >= one ring (> L2) of other data has passed over; one graph exec per distinct start offset
-        offs, o = [], 0
-        while o not in offs:
-            offs.append(o)
-            o = (o + steps) % R
-        graphs = [capture(envs, acts, steps, o) for o in offs]
-        n_warm = max(len(offs), -(-warmup // steps))
-        for i in range(n_warm):                  # warm-up: EVERY timed graph exec is replayed un-timed first
-            graphs[i % len(offs)][0].replay()
-        torch.cuda.synchronize(device)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        graphs[n_warm % len(offs)][0].replay()
-        ev1.record()
-        torch.cuda.synchronize(device)
-        est = max(ev0.elapsed_time(ev1), 1e-3)
-        reps = int(min(4001, max(11, math.ceil(target_ms / est)))) | 1
-        pos = n_warm + 1
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        barrier()
-        torch.cuda.synchronize(device)
-        # all repetitions are enqueued back to back (no host sync in between), so the GPU front end never waits
-        # for the host between one repetition's closing event and the next one's opening event
-        for r in range(reps):
-            g, _ = graphs[(pos + r) % len(offs)]
-            evs[r][0].record()
-            g.replay()
-            evs[r][1].record()
-        torch.cuda.synchronize(device)
-        barrier()
-        times = sorted(a.elapsed_time(b) for a, b in evs)
-        med = times[reps // 2]
-        launches = sum(graphs[(pos + r) % len(offs)][1] for r in range(reps))
-        out = dict(ms=med, repeats=reps, launches=launches, launches_per_rep=graphs[0][1],
-                   spread_ms={"min": times[0], "p10": times[reps // 10], "median": med, "p90": times[(reps * 9) // 10],
-                              "max": times[-1]},
-                   mode=f"median of {reps} repetitions of exactly {steps} steps (one CUDA graph each, {len(offs)} rotating ring "
-                        "offsets, every graph exec replayed un-timed first, repetitions enqueued back to back)")
-    else:
-        chunk = max(R, (1024 // R) * R)           # a multiple of the ring: consecutive replays continue the ring
-        full, rem = divmod(steps, chunk)
-        g_full, n_full = capture(envs, acts, chunk, 0)
-        g_rem, n_rem = capture(envs, acts, rem, 0) if rem else (None, 0)
-        for _ in range(max(1, -(-warmup // chunk))):
-            g_full.replay()
-        if g_rem is not None:
-            g_rem.replay()                        # the remainder exec is warm as well
-        torch.cuda.synchronize(device)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(device)
-        ev0.record()
+    repeats = max(1, -(-target_steps // steps))
+    total = steps * repeats
+    chunk = max(R, (1024 // R) * R)               # a multiple of the ring: consecutive replays continue the ring
+    full, rem = divmod(total, chunk)
+    g_full, n_full = capture(envs, acts, chunk, 0) if full else (None, 0)
+    g_rem, n_rem = capture(envs, acts, rem, (full * chunk) % R) if rem else (None, 0)
+
+    def stream_once():
         for _ in range(full):
             g_full.replay()
         if g_rem is not None:
             g_rem.replay()
+
+    for _ in range(max(1, -(-warmup // total))):   # warm-up: >= `warmup` steps, through the SAME graph execs
+        stream_once()
+    torch.cuda.synchronize(device)
+    regions = []
+    for _ in range(3):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        ev0.record()
+        stream_once()
         ev1.record()
         torch.cuda.synchronize(device)
         barrier()
-        out = dict(ms=ev0.elapsed_time(ev1), repeats=1, launches=full * n_full + n_rem, launches_per_rep=full * n_full + n_rem,
-                   spread_ms=None, mode=f"one timed region of {steps} steps ({full} replays of a {chunk}-step graph"
-                                        + (f" + one {rem}-step graph" if rem else "") + ", all execs replayed un-timed first)")
-    out["ms"] = reduce_max(out["ms"])
-    return out
+        regions.append(reduce_max(ev0.elapsed_time(ev1)))
+    regions.sort()
+    ms_total = regions[1]
+    return dict(ms=ms_total / repeats, repeats=repeats, launches=(full * n_full + n_rem), launches_per_rep=(full * n_full + n_rem) // repeats,
+                spread_ms={"regions_ms": regions, "per_step_us": [r / total * 1e3 for r in regions]},
+                mode=f"{repeats} repetition(s) of exactly {steps} steps enqueued back to back as one contiguous stream of "
+                     f"{total} steps ({full} replays of a {chunk}-step CUDA graph" + (f" + one {rem}-step graph" if rem else "")
+                     + "; all graph execs replayed un-timed first), one event pair around the stream, median of 3 such regions, "
+                       "max over ranks")
 
 
 def timed_e2e(env, w, steps, warmup, device):
@@ -761,7 +740,8 @@ def run_gpu(args, name, w):
             ow = dict(WORKLOADS[oname])
             oring, _ = ring_size(ow)
             oenvs, oacts = build_ring(ow, ow["E"], oring, device, env_offset=rank * ow["E"])
-            ot = timed_graph_steps(oenvs, oacts, min(args.steps, 256), args.warmup, device, barrier, reduce_max, target_ms=15.0)
+            ot = timed_graph_steps(oenvs, oacts, min(args.steps, 256), args.warmup, device, barrier, reduce_max,
+                                   target_steps=2048 if not oenvs[0].tiled else 512)
             osteps = min(args.steps, 256)
             per = ot["ms"] * 1e-3 / osteps
             if rank == 0:

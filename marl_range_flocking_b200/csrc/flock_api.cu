@@ -85,6 +85,13 @@ Params make_params(const flock_env* e, float dt) {
     p.E = c.num_envs; p.N = c.num_agents; p.k = c.k; p.H = c.obs_hist;
     p.env_offset = c.env_offset;
     p.G = c.num_agents <= 32 ? 32 / c.num_agents : 0;
+    {   // developer knob (profiles/README.md, "envs per warp" experiment): fewer env groups per warp = more, shorter warps
+        static const int force_g = [] {
+            const char* v = getenv("FLOCK_FORCE_G");
+            return v != nullptr ? atoi(v) : 0;
+        }();
+        if (force_g > 0 && force_g < p.G) p.G = force_g;
+    }
     p.sstride = (c.num_agents + 3) & ~3;
     p.g_magic = (65536 + c.num_agents - 1) / c.num_agents;
     p.num_tasks = p.G > 0 ? (c.num_envs + p.G - 1) / p.G : 0;

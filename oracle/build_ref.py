@@ -2,7 +2,7 @@
 
 The reference is pure Python: its hot path is `MultiAgentEnv.step` of
 environments/gym_flock_v2.py, gym_flock_uw.py, gym_flock_uw_discrete.py. This recipe byte-compiles
-those three files FROM WHERE THEY LIE under /root/reference into `oracle/_ref/*.pyc` (outputs only;
+those three files FROM WHERE THEY LIE under /root/reference into `oracle/_ref/*.pyc.bin` (outputs only;
 no source is copied, `oracle/_ref/` is git-ignored but travels to the GPU box with the snapshot, like
 our own built `.so`). `oracle/ref_shim.py` loads the bytecode with importlib's sourceless loader when
 /root/reference itself is absent, which is what lets `bench.py` time the UNMODIFIED reference step on
@@ -26,10 +26,10 @@ def build_ref(force: bool = False) -> bool:
     """Returns True when oracle/_ref/ holds the three compiled modules afterwards."""
     src_dir = os.path.join(REFERENCE_ROOT, "environments")
     if not all(os.path.isfile(os.path.join(src_dir, f)) for f in ENV_FILES):
-        return all(os.path.isfile(os.path.join(REF_DIR, f + "c")) for f in ENV_FILES)
+        return all(os.path.isfile(os.path.join(REF_DIR, f + "c.bin")) for f in ENV_FILES)
     os.makedirs(REF_DIR, exist_ok=True)
     for f in ENV_FILES:
-        src, out = os.path.join(src_dir, f), os.path.join(REF_DIR, f + "c")
+        src, out = os.path.join(src_dir, f), os.path.join(REF_DIR, f + "c.bin")
         if force or not os.path.isfile(out) or os.path.getmtime(out) < os.path.getmtime(src):
             # unchecked hash-based pyc: valid wherever the same interpreter version runs, whatever the mtime
             py_compile.compile(src, cfile=out, dfile=f"<reference>/environments/{f}", doraise=True,

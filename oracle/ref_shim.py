@@ -60,7 +60,7 @@ def compiled_reference_available() -> bool:
                 return False
     except OSError:
         return False
-    return all(os.path.isfile(os.path.join(_REF_DIR, f + "c")) for f in _VARIANT_FILES.values())
+    return all(os.path.isfile(os.path.join(_REF_DIR, f + "c.bin")) for f in _VARIANT_FILES.values())
 
 
 def _install_stubs() -> None:
@@ -111,7 +111,7 @@ def load_reference(variant: str):
         path = os.path.join(REFERENCE_ROOT, "environments", _VARIANT_FILES[variant])
         spec = importlib.util.spec_from_file_location(name, path)
     elif compiled_reference_available():
-        path = os.path.join(_REF_DIR, _VARIANT_FILES[variant] + "c")
+        path = os.path.join(_REF_DIR, _VARIANT_FILES[variant] + "c.bin")
         spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, path))
     else:
         raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT} and no compiled copy in {_REF_DIR}")

@@ -220,6 +220,13 @@ def main(only=None):
     record_traj("traj_uwd_n8_k4", "uwd", dict(agents=8, k=4, range_start=[0, 50]), 400, ids, seed=4)
     record_traj("traj_uwd_n16_k4", "uwd",
                 dict(agents=16, k=4, collision_distance=0.5, range_start=[0, 100]), 200, ids, dt=0.2, seed=5)
+    # north-star horizon (1e-5 after 1000 steps) for the other two variants, at the BASELINE config 3 / 4 parameters
+    record_traj("traj_uw_n32_k3_1000", "uw",
+                dict(agents=32, k=3, collision_distance=0.5, range_start=(0, 200), sensor_range=7),
+                1000, uw_act, seed=7)
+    record_traj("traj_uwd_n16_k4_1000", "uwd",
+                dict(agents=16, k=4, collision_distance=0.5, range_start=[0, 100], sensor_range=7),
+                1000, ids, seed=8)
     record_edges()
 
 

@@ -165,3 +165,48 @@ def test_graphed_rollout_with_the_fused_actor_matches_the_python_loop():
     for name in ("x", "y", "_obs", "_reward", "_env_done", "_ep_len", "_ep_return_fx"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(buf_a, buf_b) and stats_a == stats_b
+
+
+def test_graphed_rollout_with_fused_ou_noise_draws_fresh_normals_every_replay():
+    """A host `step` is frozen inside a captured CUDA graph: every replay would redraw the same normals. With
+    `counters=env.noise_counters` (per-env DEVICE counters ep_len / reset_epoch added inside the kernel) the draws
+    advance with the env: (a) graph replay == the same steps launched eagerly, bit for bit; (b) the increments
+    of different replays differ; (c) with the host step alone they repeat -- which is what the counters are for."""
+    from marl_range_flocking_b200 import VecEnv
+    from marl_range_flocking_b200.rollout import GraphedRollout, collect
+    dev = torch.device("cuda:0")
+    E, N, k, SPR = 128, 6, 3, 4
+    mk = lambda: VecEnv("uw", E, N, k, 0.5, range_start=(0, 80), sensor_range=7.0, seed=3, device="cuda:0")
+    actors = _actors(N, 4 * k, 5, dev)
+    kw = dict(ou_theta=0.0, ou_mu=0.0, ou_sigma=0.15, ou_dt=1e-2, seed=21, step=0)    # theta = 0: x is the plain sum of the draws
+    actors.forward_fused(torch.zeros(E, N, 4 * k, device=dev))     # pack + one-time kernel configuration outside any capture
+    torch.cuda.synchronize()
+
+    def run(env, ou, buf, with_counters, graphed):
+        pol = lambda obs: actors.forward_fused(obs, out=buf, ou_state=ou, counters=env.noise_counters if with_counters else None, **kw)
+        snaps = []
+        if graphed:
+            env.reset()
+            gr = GraphedRollout(env, pol, steps_per_replay=SPR, max_episode_steps=1000, warmup_steps=0)
+            for _ in range(3):
+                gr.run(1)
+                snaps.append(ou.clone())
+        else:
+            for r in range(3):
+                collect(env, pol, SPR, max_episode_steps=1000, reset_first=(r == 0))
+                snaps.append(ou.clone())
+        torch.cuda.synchronize()
+        return snaps
+
+    z = lambda: torch.zeros(E, N, 2, device=dev)
+    g = run(mk(), z(), torch.empty(E, N, 2, device=dev), True, True)
+    e = run(mk(), z(), torch.empty(E, N, 2, device=dev), True, False)
+    for a, b in zip(g, e):
+        assert torch.equal(a, b)                                   # (a) replay-safe: graph == eager
+    inc = [g[0], g[1] - g[0], g[2] - g[1]]                         # sum of SPR draws per replay
+    assert not torch.allclose(inc[0], inc[1]) and not torch.allclose(inc[1], inc[2])          # (b)
+    zz = torch.cat([i.flatten() for i in inc]) / (0.15 * 1e-1 * SPR ** 0.5)
+    assert abs(zz.mean().item()) < 0.05 and abs(zz.std().item() - 1.0) < 0.05
+    frozen = run(mk(), z(), torch.empty(E, N, 2, device=dev), False, True)
+    live = frozen[0] != 0                                          # (c) host step only: identical draws every launch
+    assert torch.allclose((frozen[1] - frozen[0])[live], frozen[0][live], rtol=1e-4, atol=1e-6)

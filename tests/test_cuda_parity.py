@@ -115,7 +115,8 @@ def test_small_path_bit_exact(case):
 @pytest.mark.parametrize("mode", [1, 2], ids=["thread-per-row", "warp-per-row-bitonic"])
 @pytest.mark.parametrize("case", TILED, ids=[f"{c[0]}-E{c[1]}-N{c[2]}-k{c[3]}" for c in TILED])
 def test_tiled_path_bit_exact(case, mode):
-    _run_parity(*case, T=12, tiled_mode=mode)
+    # T >= 40: crosses two 16-step row-order refreshes (hint_slots invalidated and rebuilt through `inv`)
+    _run_parity(*case, T=40, tiled_mode=mode)
 
 
 def test_rigid_boundary_bit_exact():
@@ -285,9 +286,10 @@ def test_auto_reset_resets_exactly_the_done_envs(variant, E, N, k, B):
 
 
 FULL = [
-    ("v2", 4096, 10, 4, 2.5, (0, 50), 14.0, 1000),    # BASELINE config 2, 1000 free-running steps
-    ("uw", 4096, 32, 3, 0.5, (0, 200), 7.0, 100),     # BASELINE config 3
-    ("uwd", 8192, 16, 4, 0.5, (0, 100), 7.0, 100),    # BASELINE config 4 (in-kernel Philox actuation noise)
+    # the three BASELINE batch configs, 1000 free-running steps each (the north-star horizon)
+    ("v2", 4096, 10, 4, 2.5, (0, 50), 14.0, 1000),    # BASELINE config 2
+    ("uw", 4096, 32, 3, 0.5, (0, 200), 7.0, 1000),    # BASELINE config 3
+    ("uwd", 8192, 16, 4, 0.5, (0, 100), 7.0, 1000),   # BASELINE config 4 (in-kernel Philox actuation noise)
 ]
 
 
@@ -314,18 +316,114 @@ def test_full_size_configs_bit_exact(case):
     assert bool(((nn >= 0) & (nn < N)).all())
 
 
+@pytest.mark.parametrize("auto_reset", [False, True], ids=["masked-reset", "auto-reset"])
 @pytest.mark.parametrize("mode", [1, 2], ids=["thread-per-row", "warp-per-row-bitonic"])
-def test_large_swarm_config5_bit_exact(mode):
-    # BASELINE config 5 shape (E reduced to keep the CPU oracle fast): 2048 agents, k = 8
-    env, orc = make_pair("v2", 4, 2048, 8, 0.05, (0, 2000), 100.0, seed=0x5EED, tiled_mode=mode)
+def test_large_swarm_config5_bit_exact(mode, auto_reset):
+    """BASELINE config 5 shape (E reduced to 8 to keep the CPU oracle fast): 2048 agents, k = 8, 72 steps = four
+    16-step row-order refreshes of the pruned kernel (its neighbour hints are invalidated and rebuilt through the
+    inverse row order each time), with a masked reset of a subset in the middle of a refresh period -- or, in the
+    auto-reset variant, a world dense enough that envs finish and restart on their own."""
+    cd = 0.3 if auto_reset else 0.05
+    kw = dict(auto_reset=True, max_reset_attempts=16) if auto_reset else {}
+    env, orc = make_pair("v2", 8, 2048, 8, cd, (0, 2000), 100.0, seed=0x5EED, tiled_mode=mode, **kw)
     env.reset()
-    orc.reset()
+    orc.reset(max_attempts=16 if auto_reset else 64)
     compare_all(env, orc, tag="reset:")
+    T = 72
+    restarted = 0
+    for t in range(T):
+        a = orc.random_actions()
+        dt = 0.1 if t % 5 else 0.5
+        orc.step(a, dt)
+        if auto_reset:
+            restarted += int(orc.env_done.sum())
+            orc.reset(mask=orc.env_done.copy(), keep_outputs=True, max_attempts=16)
+        env.step(torch.from_numpy(a).cuda(), dt)
+        if t < 4 or t % 4 == 3 or t in (16, 17, 32, 33, 41, 42, 48, 49, 64, 65):
+            compare_all(env, orc, tag=f"step{t}:")
+        if not auto_reset and t == 40:            # mid-period masked reset: envs 1, 4, 7 restart, hints of the rest stay
+            mask = np.zeros(8, np.uint8)
+            mask[1::3] = 1
+            orc.reset(mask=mask)
+            env.reset(mask=torch.from_numpy(mask).cuda().bool())
+            compare_all(env, orc, tag="masked reset:")
+    compare_all(env, orc, tag="final:")
+    if auto_reset:
+        assert restarted > 0 and env.stats()["episodes"] == int(orc.stats[0]) > 0
+    # domain properties: ranges ascending and clamped, self never a neighbour, indices in range
+    d, nn = env.distances_to_nearest_neighbors, env.nearest_neighbors
+    assert bool((d[..., 1:] >= d[..., :-1]).all()) and bool((d >= 0).all()) and bool((d <= 100.0).all())
+    assert not bool((nn == torch.arange(2048, device=nn.device)[None, :, None]).any())
+    assert bool(((nn >= 0) & (nn < 2048)).all())
+
+
+def test_two_large_swarm_envs_of_different_size_share_a_device():
+    """The dynamic shared-memory opt-in is per FUNCTION, not per handle: a smaller large-swarm env created after
+    a bigger one must not lower the limit under it (8192 agents need > 48 KB). Both are stepped alternately and
+    the smaller one is checked against the oracle."""
+    from marl_range_flocking_b200 import VecEnv
+    big = VecEnv("v2", 1, 8192, 8, 0.02, range_start=(0, 4000), sensor_range=100.0, seed=3)
+    small, orc = make_pair("v2", 1, 4096, 8, 0.02, (0, 3000), 100.0, seed=4)
+    big.reset()
+    small.reset()
+    orc.reset()
     for t in range(3):
+        big.step(big.random_actions(), 0.1)
         a = orc.random_actions()
         orc.step(a, 0.1)
-        env.step(torch.from_numpy(a).cuda(), 0.1)
-        compare_all(env, orc, tag=f"step{t}:")
+        small.step(torch.from_numpy(a).cuda(), 0.1)
+        big.step(big.random_actions(), 0.1)
+    torch.cuda.synchronize()
+    compare_all(small, orc, tag="4096 next to 8192:")
+    d = big.distances_to_nearest_neighbors
+    assert bool(torch.isfinite(d).all()) and bool((d[..., 1:] >= d[..., :-1]).all())
+
+
+@pytest.mark.parametrize("variant,E,N,k", [("v2", 64, 10, 4), ("uw", 32, 32, 3), ("uwd", 48, 16, 4), ("v2", 2, 96, 8)])
+def test_get_state_set_state_round_trip_continues_bit_equal(variant, E, N, k):
+    """Checkpoint / restore: a twin env that receives `get_state()` of a running env must continue
+    with identical bits -- state, observation window, episode counters, Philox epochs, statistics."""
+    from marl_range_flocking_b200 import VecEnv
+    mk = lambda seed: VecEnv(variant, E, N, k, 0.5, range_start=(0, 60), sensor_range=9.0, seed=seed, device="cuda:0")
+    a = mk(5)
+    a.reset()
+    a.step_n(13, 0.1)
+    a.reset(mask=a.dones[1].clone())                       # some envs mid-episode, some freshly restarted
+    a.step_n(3, 0.1)
+    state = {k_: v_.cpu() for k_, v_ in a.get_state().items()}   # through host memory, as a checkpoint file would
+    b = mk(5)                                               # same seed = same Philox key; everything else from `state`
+    b.set_state(state)
+    for t in range(6):
+        act = a.random_actions()
+        assert torch.equal(act, b.random_actions())
+        a.step(act, 0.1)
+        b.step(act, 0.1)
+    a.step_n(5, 0.1)                                        # in-kernel Philox actions + (uwd) actuation noise
+    b.step_n(5, 0.1)
+    a.reset(mask=a.dones[1].clone())
+    b.reset(mask=b.dones[1].clone())
+    torch.cuda.synchronize()
+    for name in ("x", "y", "headings", "_prev_h", "_obs", "_reward", "_agent_done", "_env_done", "_ep_len",
+                 "_ep_return_fx", "_reset_epoch", "_stats"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+def test_misaligned_action_views_are_copied_not_faulted():
+    """A contiguous float32 view with an odd element offset is not 8-byte aligned; the kernels read action pairs
+    as float2, so VecEnv must copy such an input (and the C ABI must refuse it) instead of faulting."""
+    env, orc = make_pair("v2", 16, 10, 4, 2.5, (0, 50), 14.0)
+    env.reset()
+    orc.reset()
+    a = orc.random_actions()
+    buf = torch.zeros(1 + a.size, device="cuda")
+    buf[1:] = torch.from_numpy(a).cuda().reshape(-1)
+    view = buf[1:].view(16, 10, 2)
+    assert view.data_ptr() % 8 == 4
+    orc.step(a, 0.1)
+    env.step(view, 0.1)
+    compare_all(env, orc, tag="misaligned view:")
+    rc = env.lib.flock_step(env._h, view.data_ptr(), 0.1, None, None)
+    assert rc == -1 and b"aligned" in env.lib.flock_last_error()
 
 
 def test_batched_rollout_matches_per_step_oracle_loop():
@@ -466,28 +564,41 @@ def test_bench_line_satisfies_the_contract():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "1", "--steps", "64", "--warmup", "8",
-                          "--ring", "2", "--no-sweep"], capture_output=True, text=True, timeout=600)
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "1", "--steps", "20", "--warmup", "5",
+                          "--no-sweep"], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     j = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "clocks", "e2e", "gpu_launches"):
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "clocks", "e2e", "gpu_launches",
+                "repeats", "configs"):
         assert key in j, key
-    assert j["steps"] == 64 and j["warmup"] == 8 and j["n_gpus"] == 1 and j["scaling"] == "weak"
+    assert j["steps"] == 20 and j["warmup"] == 5 and j["n_gpus"] == 1 and j["scaling"] == "weak"
     assert j["vs_baseline"] is None and j["dtype"] == "f32" and j["data"] == "synthetic" and j["higher_is_better"] is True
-    assert "workload" in j["config"] and "model" not in j["config"]
+    sys.path.insert(0, root)
+    import bench
+    assert j["config"] == bench.config_of("cfg2", bench.WORKLOADS["cfg2"]) and "model" not in j["config"]
     r = j["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or r["traffic"] > 0
+    assert abs(r["achieved"] - 4096 * 10 * 53 / (j["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
     c = j["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and "sample" in c and c["port"]["value"] > 0
+    if c["kind"] == "reference":        # the unmodified reference step: orders of magnitude below its own C port
+        assert c["value"] < c["port"]["value"] and c["reference_pytorch"]["threads_1"]["env_steps_per_s"] > 0
     e = j["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 * 10 * 2 * 4
     assert e["d2h_bytes_per_step"] == 4096 * 10 * (4 * 4 + 4 + 1) + 4096 and e["value"] < j["value"]
-    assert j["gpu_launches"] == 64 and j["value"] > 1e8
+    assert e["value_is"] in ("pipelined", "sync_per_step") and e["sync_per_step"]["value"] > 0 and e["pipelined"]["value"] > 0
+    # exactly 20 steps per timed repetition, one fused kernel each; the median over `repeats` repetitions
+    assert j["repeats"] >= 11 and j["gpu_launches"] == 20 * j["repeats"] and j["gpu_launches_per_repetition"] == 20
+    assert j["value"] > 1e9 and abs(j["value"] - 4096 * 10 / (j["ms_per_step"] * 1e-3)) < 1e-6 * j["value"]
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert j["stats_allreduce"]["episodes"] > 0
+    for name in ("cfg3", "cfg4", "cfg5"):
+        sub = j["configs"][name]
+        assert sub["value"] > 1e8 and sub["ms_per_step"] > 0 and 0 < sub["roofline"]["frac"] < 1.5
 
 
 def test_randomised_configuration_sweep_bit_exact():
