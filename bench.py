@@ -38,7 +38,9 @@ WORKLOADS = {
                  env_kw=dict(track_velocities=False),   # `velocities` is an optional extra of SURVEY 8d (+8 B), not in the 53 B
                  desc="gym_flock_v2 batched 4096 envs x 10 agents, k=4, random actions (BASELINE configs[1])"),
     "cfg3": dict(variant="uw", E=4096, N=32, k=3, cd=0.5, rs=(0, 200), sr=7.0, kw={}, bytes=41,
-                 env_kw=dict(track_neighbors=False, track_velocities=False),   # the reference discards the indices in uw (gym_flock_uw.py:141-144)
+                 # the reference discards the indices in uw (gym_flock_uw.py:141-144); ring layout: only the new range row is
+                 # written per step (41 B), consumers read the history in place
+                 env_kw=dict(track_neighbors=False, track_velocities=False, obs_layout="ring"),
                  desc="gym_flock_uw 4096 envs x 32 agents, k=3, random actions, ring-buffer observation history (BASELINE configs[2])"),
     "cfg4": dict(variant="uwd", E=8192, N=16, k=4, cd=0.5, rs=(0, 100), sr=7.0,
                  kw=dict(reset_collision_distance=1.0), bytes=49,
@@ -468,7 +470,7 @@ def timed_e2e(env, w, steps, warmup, device):
     torch.cuda.synchronize(device)
     wall = time.perf_counter() - t0
     h2d = host_acts[0].numel() * 4
-    d2h = env._obs.numel() * 4 + E * N * 4 + E * N + E
+    d2h = env._obs_buf.numel() * 4 + E * N * 4 + E * N + E
     return max(ev0.elapsed_time(ev1) * 1e-3, wall), h2d, d2h
 
 
@@ -765,8 +767,8 @@ def run_gpu(args, name, w):
     if rank == 0 and w["variant"] != "uwd" and (args.policy == "actor" or w["variant"] == "uw"):
         from marl_range_flocking_b200.policies import BatchedActors
         env = envs[0]
-        obs = env.observation
-        in_dims = obs[0, 0].numel()
+        in_dims = env.obs_hist * env.k
+        policy_obs = (lambda: env.obs_handle) if env.obs_ring else (lambda: env.observation)   # ring: read in place
         extra["actor_rollout"] = {}
         for dtype, pname in (((torch.float32, "fp32"), (torch.bfloat16, "bf16")) if args.policy == "actor" else ()):
             actors = BatchedActors(N, in_dims, 400, 300, 2, device=device, dtype=dtype)
@@ -788,7 +790,7 @@ def run_gpu(args, name, w):
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                actors.forward_fused(env.observation, out=abuf)
+                actors.forward_fused(policy_obs(), out=abuf)
                 env.step(abuf, DT)
             side.synchronize()
             reps, inner = 20, 50
@@ -796,7 +798,7 @@ def run_gpu(args, name, w):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
                     for _ in range(inner):
-                        actors.forward_fused(env.observation, out=abuf)
+                        actors.forward_fused(policy_obs(), out=abuf)
                         if with_env:
                             env.step(abuf, DT)
                 g.replay()

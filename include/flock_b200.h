@@ -78,7 +78,14 @@ typedef struct flock_buffers_t {
     float *x, *y, *h;               /* [E][N] positions and headings, updated in place (both kernel paths) */
     float *prev_h;                  /* [E][N] `prev_headings` (uw reward term, gym_flock_uw.py:201) */
     float *vx, *vy;                 /* [E][N] last displacement = reference `velocities`; nullable */
-    float *obs;                     /* [E][N][obs_hist][k] newest first (gym_flock_uw.py:120-123) */
+    float *obs;                     /* window layout (obs_head == NULL): [E][N][obs_hist][k] newest first
+                                       (gym_flock_uw.py:120-123); ring layout (uw, obs_head != NULL):
+                                       [E][obs_hist][N][k], see obs_head */
+    int32_t *obs_head;              /* [E], uw only, nullable. Non-NULL selects the RING layout of the observation
+                                       history: row r of the newest-first window lives in slot (obs_head[e] + r) %
+                                       obs_hist; a step moves the head back by one slot and writes ONLY the new row
+                                       (4k bytes per agent instead of reading 36 and writing 48 at H = 4, k = 3).
+                                       flock_obs_window() materialises the window on request */
     int32_t *nn_idx;                /* [E][N][k] `nearest_neighbors` (v2:150); nullable */
     float *reward;                  /* [E][N] (reference shape (N,1)) */
     uint8_t *agent_done;            /* [E][N] `dones[0]` (v2:314) */
@@ -147,6 +154,26 @@ FLOCK_API int flock_set_auto_reset(flock_env_t *env, int enabled, int max_attemp
  * gym_flock_uw_discrete.py:98). N <= 32: one persistent launch with the state in registers;
  * N > 32: T launches. Outputs hold the last step. */
 FLOCK_API int flock_step_n(flock_env_t *env, int num_steps, float dt, void *stream);
+
+/* Streamed rollout: `num_steps` consecutive steps in ONE launch (N <= 32, no sensing noise; otherwise num_steps launches
+ * plus copies), the batched form of the reference's episode loop (main.py:24-51) feeding a replay buffer
+ * (learners/maddpg_official_rnn/memory_rnn.py:53-67). The state stays in registers; per step the kernel reads that step's
+ * actions and writes that step's results into TIME-MAJOR trajectory buffers (all device pointers):
+ *   actions_T    float[T][E][N][2] (float[T][E][N] for uwd), or NULL = the canonical Philox random actions of flock_step_n
+ *   obs_T        float[T][E][N][k]   the new range row of every step (for uw the (4, k) window of step t is rows t, t-1,
+ *                                    t-2, t-3 of this buffer: a time-major history needs no separate window)
+ *   reward_T     float[T][E][N],  agent_done_T uint8[T][E][N],  env_done_T uint8[T][E]
+ *   nn_T         int32[T][E][N][k] or NULL (needs a bound nn_idx buffer)
+ * With flock_set_auto_reset enabled, an env whose step ends with a collision is re-drawn inside the kernel before the
+ * next step, exactly as flock_step does: reward / dones of slice t are those of the finishing step, obs_T[t] (and
+ * nn_T[t]) of a restarted env are those of its new first state. Afterwards the env's own buffers hold the state and
+ * the outputs of the last step, as after flock_step_n. Bit-identical to num_steps calls of flock_step. */
+FLOCK_API int flock_rollout_n(flock_env_t *env, int num_steps, const float *actions_T, float dt, float *obs_T,
+                              float *reward_T, uint8_t *agent_done_T, uint8_t *env_done_T, int32_t *nn_T, void *stream);
+
+/* uw ring layout only: write the newest-first window [E][N][obs_hist][k] (the reference's observation,
+ * gym_flock_uw.py:120-123) into `out` (device). The fused actor kernel and flock_rollout_n never need it. */
+FLOCK_API int flock_obs_window(flock_env_t *env, float *out, void *stream);
 
 /* Fill `actions` (device, layout as in flock_step) with the canonical random actions that
  * flock_step_n would use `step_offset` steps from now. Philox4x32-10 stream layout: key = seed,
@@ -243,6 +270,15 @@ FLOCK_API int flock_actor_forward_ou(const void *packed, const float *obs, float
                            int input_dims, float *ou_state, float theta, float mu, float sigma, float dt,
                            uint64_t seed, uint32_t step, int env_offset, const flock_noise_counters_t *counters,
                            void *stream);
+
+/* The same actor reading the env's observation history IN PLACE from the uw ring layout (flock_buffers_t.obs_head):
+ * obs_ring [E][obs_hist][N][k], obs_head [E]; input feature r * k + c of (env, agent) is row r of the newest-first
+ * window = slot (obs_head[env] + r) % obs_hist, exactly what obs.reshape(N, -1) feeds the reference actor
+ * (train_flock.py:115). input_dims = obs_hist * k (obs_hist <= 4, k <= 3). ou_state NULL = no exploration noise. */
+FLOCK_API int flock_actor_forward_ring(const void *packed, const float *obs_ring, const int32_t *obs_head, float *actions,
+                             int num_envs, int num_agents, int obs_hist, int k, float *ou_state, float theta, float mu,
+                             float sigma, float dt, uint64_t seed, uint32_t step, int env_offset,
+                             const flock_noise_counters_t *counters, void *stream);
 
 /* Fused recurrent MADDPG actor -- the policy of the reference's default main.py loop: `Actor` of
  * learners/maddpg_official_rnn/net.py:14-72 (fce(in,32) - GRUCell(32,32) - fc1(32,400) - ReLU - fc2(400,300) - ReLU -

@@ -42,7 +42,7 @@ class FlockCfg(ctypes.Structure):
     ]
 
 
-BUFFER_FIELDS = ("x", "y", "h", "prev_h", "vx", "vy", "obs", "nn_idx", "reward",
+BUFFER_FIELDS = ("x", "y", "h", "prev_h", "vx", "vy", "obs", "obs_head", "nn_idx", "reward",
                  "agent_done", "env_done", "reset_epoch", "ep_return_fx", "ep_len", "stats")
 
 
@@ -87,6 +87,8 @@ def load_library() -> ctypes.CDLL:
         "flock_step": (i32, [vp, vp, f32, vp, vp]),
         "flock_step_n": (i32, [vp, i32, f32, vp]),
         "flock_random_actions": (i32, [vp, u32, vp, vp]),
+        "flock_rollout_n": (i32, [vp, i32, vp, f32, vp, vp, vp, vp, vp, vp]),
+        "flock_obs_window": (i32, [vp, vp, vp]),
         "flock_step_host": (i32, [vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "flock_step_host_async": (i32, [vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "flock_wait_host": (i32, [vp]),
@@ -101,6 +103,7 @@ def load_library() -> ctypes.CDLL:
         "flock_actor_pack": (i32, [i32, i32, i32, i32, i32, ctypes.POINTER(vp), vp, vp]),
         "flock_actor_forward": (i32, [vp, vp, vp, i32, i32, i32, vp]),
         "flock_actor_forward_ou": (i32, [vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32, u64, u32, i32, vp, vp]),
+        "flock_actor_forward_ring": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, f32, f32, f32, u64, u32, i32, vp, vp]),
         "flock_rnn_actor_packed_bytes": (ctypes.c_size_t, [i32]),
         "flock_rnn_actor_pack": (i32, [i32, i32, i32, i32, i32, ctypes.POINTER(vp), vp, vp]),
         "flock_rnn_actor_forward": (i32, [vp, ctypes.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, vp]),

@@ -41,6 +41,7 @@ struct flock_env {
     uint64_t launches;
     float* stage_actions;  // device staging for host-call / step_n(tiled) actions
     float* stage_noise;
+    float* stage_window;   // uw ring layout: materialised window for the host-call path (allocated on first use)
     unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
     int* tile_perm;               // tiled thread-per-row path: spatially sorted row order [E][N]
     int* tile_inv;                // its inverse (agent -> slot)
@@ -115,6 +116,7 @@ Params make_params(const flock_env* e, float dt) {
     p.x = b.x; p.y = b.y; p.h = b.h;       // the state is updated in place on both paths
     p.xo = b.x; p.yo = b.y; p.ho = b.h;
     p.prev_h = b.prev_h; p.vx = b.vx; p.vy = b.vy; p.obs = b.obs; p.nn = b.nn_idx;
+    p.obs_head = c.obs_hist > 1 ? b.obs_head : nullptr;
     p.reward = b.reward; p.agent_done = b.agent_done; p.env_done = b.env_done;
     p.reset_epoch = b.reset_epoch;
     p.ep_return_fx = reinterpret_cast<long long*>(b.ep_return_fx);
@@ -177,13 +179,21 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
         p.m_env_done = mirrors->env_done;
     }
     cudaError_t err;
-    const bool fused_reset = e->auto_reset && e->path == 0 && mirrors == nullptr && e->cfg.range_noise_std == 0.0f;
+    const bool noisy = e->cfg.range_noise_std > 0.0f;
+    const bool fused_reset = e->auto_reset && e->path == 0 && mirrors == nullptr && !noisy;
+    // sensing noise rides in the step kernel's epilogue (small path, no host mirrors, no auto-reset);
+    // otherwise it is the follow-up kernel of flock_small.cu
+    const bool fused_noise = noisy && e->path == 0 && mirrors == nullptr && !e->auto_reset;
     if (e->path == 0) {
+        int mode = flock::kSmallModeStep;
+        if (mirrors != nullptr) mode = flock::kSmallModeMirror;
+        else if (fused_reset) mode = flock::kSmallModeAutoReset;
+        else if (fused_noise) mode = flock::kSmallModeNoise;
         if (fused_reset) {
             p.fused_auto_reset = 1;
             p.max_attempts = e->auto_reset_attempts;
         }
-        err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, false, e->sm_count, s);
+        err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, mode, e->sm_count, s);
         e->launches += 1;
     } else {
         // keep the warps of the thread-per-row kernel spatially coherent: refresh the row order
@@ -207,8 +217,8 @@ int step_device(flock_env* e, const float* actions, float dt, const float* noise
     }
     if (err != cudaSuccess) return cuda_fail(err, "step kernel launch");
     e->step_index += 1;
-    if (e->cfg.range_noise_std > 0.0f) {     // optional sensing noise, separate launch (see flock_small.cu)
-        Params q = make_params(e, dt);        // after the slot flip: reads the current counters
+    if (noisy && !fused_noise) {             // optional sensing noise as a separate launch (see flock_small.cu)
+        Params q = make_params(e, dt);        // reads the counters the step has just advanced
         err = flock::launch_range_noise(q, e->sm_count, s);
         e->launches += 1;
         if (err != cudaSuccess) return cuda_fail(err, "range noise kernel launch");
@@ -228,9 +238,20 @@ int copy_results_to_host(flock_env* e, float* h_obs, float* h_reward, uint8_t* h
     // Python host does), the four results travel as one D2H copy instead of four.
     const size_t obs_bytes = EN * e->cfg.obs_hist * e->cfg.k * sizeof(float);
     const size_t rew_bytes = EN * sizeof(float);
+    const bool ring = e->cfg.obs_hist > 1 && e->b.obs_head != nullptr;
+    const float* d_obs = e->b.obs;
+    if (ring && h_obs != nullptr) {   // the host wants the reference's newest-first window: materialise it first
+        if (e->stage_window == nullptr && cudaMalloc(&e->stage_window, obs_bytes) != cudaSuccess)
+            return cuda_fail(cudaGetLastError(), "window staging buffer");
+        Params q = make_params(e, 0.0f);
+        err = flock::launch_obs_window(q, e->stage_window, e->sm_count, s);
+        e->launches += 1;
+        if (err != cudaSuccess) return cuda_fail(err, "obs window kernel launch");
+        d_obs = e->stage_window;
+    }
     const char* d0 = reinterpret_cast<const char*>(e->b.obs);
     char* h0 = reinterpret_cast<char*>(h_obs);
-    const bool packed = h_obs && h_reward && h_agent_done && h_env_done &&
+    const bool packed = !ring && h_obs && h_reward && h_agent_done && h_env_done &&
                         reinterpret_cast<const char*>(e->b.reward) == d0 + obs_bytes &&
                         reinterpret_cast<const char*>(e->b.agent_done) == d0 + obs_bytes + rew_bytes &&
                         reinterpret_cast<const char*>(e->b.env_done) == d0 + obs_bytes + rew_bytes + EN &&
@@ -242,7 +263,7 @@ int copy_results_to_host(flock_env* e, float* h_obs, float* h_reward, uint8_t* h
                               cudaMemcpyDeviceToHost, s);
     } else {
         if (h_obs != nullptr && err == cudaSuccess)
-            err = cudaMemcpyAsync(h_obs, e->b.obs, obs_bytes, cudaMemcpyDeviceToHost, s);
+            err = cudaMemcpyAsync(h_obs, d_obs, obs_bytes, cudaMemcpyDeviceToHost, s);
         if (h_reward != nullptr && err == cudaSuccess)
             err = cudaMemcpyAsync(h_reward, e->b.reward, rew_bytes, cudaMemcpyDeviceToHost, s);
         if (h_agent_done != nullptr && err == cudaSuccess)
@@ -330,6 +351,7 @@ void flock_destroy(flock_env_t* e) {
     if (e == nullptr) return;
     cudaFree(e->stage_actions);
     cudaFree(e->stage_noise);
+    cudaFree(e->stage_window);
     cudaFree(e->tile_scratch);
     cudaFree(e->tile_perm);
     cudaFree(e->tile_inv);
@@ -395,7 +417,7 @@ int flock_step_n(flock_env_t* e, int num_steps, float dt, void* stream) {
     if (e->path == 0 && e->cfg.range_noise_std == 0.0f) {   // sensing noise needs the per-step follow-up kernel
         Params p = make_params(e, dt);
         p.num_steps = num_steps;
-        cudaError_t err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, true, e->sm_count, s);
+        cudaError_t err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, flock::kSmallModeMulti, e->sm_count, s);
         e->launches += 1;
         if (err != cudaSuccess) return cuda_fail(err, "step_n kernel launch");
         e->step_index += (uint32_t)num_steps;
@@ -409,6 +431,74 @@ int flock_step_n(flock_env_t* e, int num_steps, float dt, void* stream) {
     }
     e->auto_reset = saved_auto_reset;
     return rc;
+}
+
+int flock_rollout_n(flock_env_t* e, int num_steps, const float* actions_T, float dt, float* obs_T, float* reward_T,
+                    uint8_t* agent_done_T, uint8_t* env_done_T, int32_t* nn_T, void* stream) {
+    int rc = check_bound(e);
+    if (rc != FLOCK_OK) return rc;
+    if (num_steps < 1) return fail(FLOCK_E_INVALID, "num_steps must be >= 1");
+    if (obs_T == nullptr || reward_T == nullptr || agent_done_T == nullptr || env_done_T == nullptr)
+        return fail(FLOCK_E_INVALID, "a trajectory buffer is NULL");
+    if (nn_T != nullptr && e->b.nn_idx == nullptr) return fail(FLOCK_E_INVALID, "nn_T needs a bound nn_idx buffer");
+    const bool uwd = e->cfg.variant == FLOCK_UWD;
+    if ((reinterpret_cast<uintptr_t>(actions_T) & (uwd ? 3u : 7u)) || (reinterpret_cast<uintptr_t>(obs_T) & 15u) ||
+        (reinterpret_cast<uintptr_t>(nn_T) & 15u) || (reinterpret_cast<uintptr_t>(reward_T) & 3u))
+        return fail(FLOCK_E_INVALID, "trajectory buffers must be aligned (obs / nn 16 bytes, actions 8, reward 4)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t EN = (size_t)e->cfg.num_envs * e->cfg.num_agents, k = (size_t)e->cfg.k;
+    if (e->path == 0 && e->cfg.range_noise_std == 0.0f) {
+        Params p = make_params(e, dt);
+        p.num_steps = num_steps;
+        p.traj_actions = actions_T;
+        p.traj_obs = obs_T;
+        p.traj_reward = reward_T;
+        p.traj_agent_done = agent_done_T;
+        p.traj_env_done = env_done_T;
+        p.traj_nn = nn_T;
+        if (e->auto_reset) {
+            p.fused_auto_reset = 1;
+            p.max_attempts = e->auto_reset_attempts;
+        }
+        cudaError_t err = flock::launch_step_small(e->cfg.variant, e->cfg.periodic != 0, p, flock::kSmallModeRollout, e->sm_count, s);
+        e->launches += 1;
+        if (err != cudaSuccess) return cuda_fail(err, "rollout kernel launch");
+        e->step_index += (uint32_t)num_steps;
+        return FLOCK_OK;
+    }
+    // large swarms / sensing noise: one step at a time, results copied into the slices (device to device)
+    const size_t aw = uwd ? 1 : 2, E = (size_t)e->cfg.num_envs;
+    for (int t = 0; t < num_steps; ++t) {
+        const float* act = actions_T != nullptr ? actions_T + (size_t)t * EN * aw : e->stage_actions;
+        if (actions_T == nullptr) {
+            rc = flock_random_actions(e, 0u, e->stage_actions, stream);
+            if (rc != FLOCK_OK) return rc;
+        }
+        rc = step_device(e, act, dt, nullptr, s);
+        if (rc != FLOCK_OK) return rc;
+        Params q = make_params(e, dt);
+        cudaError_t err = flock::launch_newest_row(q, obs_T + (size_t)t * EN * k, e->sm_count, s);
+        e->launches += 1;
+        if (err == cudaSuccess) err = cudaMemcpyAsync(reward_T + (size_t)t * EN, e->b.reward, EN * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(agent_done_T + (size_t)t * EN, e->b.agent_done, EN, cudaMemcpyDeviceToDevice, s);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(env_done_T + (size_t)t * E, e->b.env_done, E, cudaMemcpyDeviceToDevice, s);
+        if (err == cudaSuccess && nn_T != nullptr)
+            err = cudaMemcpyAsync(nn_T + (size_t)t * EN * k, e->b.nn_idx, EN * k * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+        if (err != cudaSuccess) return cuda_fail(err, "rollout slice copy");
+    }
+    return FLOCK_OK;
+}
+
+int flock_obs_window(flock_env_t* e, float* out, void* stream) {
+    int rc = check_bound(e);
+    if (rc != FLOCK_OK) return rc;
+    if (out == nullptr) return fail(FLOCK_E_INVALID, "out is NULL");
+    if (e->cfg.obs_hist < 2 || e->b.obs_head == nullptr)
+        return fail(FLOCK_E_INVALID, "flock_obs_window needs the uw ring layout (obs_head bound); the window layout IS the window");
+    Params p = make_params(e, 0.0f);
+    cudaError_t err = flock::launch_obs_window(p, out, e->sm_count, static_cast<cudaStream_t>(stream));
+    e->launches += 1;
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "obs window kernel launch");
 }
 
 static int step_host_impl(flock_env_t* e, const float* h_actions, float dt, const float* h_noise, float* h_obs,
@@ -458,7 +548,8 @@ static int step_host_impl(flock_env_t* e, const float* h_actions, float dt, cons
             return v != nullptr && v[0] == '1';
         }();
         const bool zc_inputs = e->zc_ok && e->path == 0 && zc_mode != 0 && (sync || async_zc_inputs);
-        const bool zc_outputs = sync && zc_inputs && e->cfg.range_noise_std == 0.0f && !e->auto_reset &&   // post-step launches
+        const bool ring = e->cfg.obs_hist > 1 && e->b.obs_head != nullptr;   // the host mirrors hold the window, not the ring
+        const bool zc_outputs = sync && zc_inputs && e->cfg.range_noise_std == 0.0f && !e->auto_reset && !ring &&   // post-step launches
                                 (zc_mode == 1 || out_bytes <= (size_t)3 << 20);
         if (zc_outputs) {
             HostMirrors mir;
@@ -585,7 +676,8 @@ static flock::NoiseCounters noise_counters(const flock_noise_counters_t* c) {
 
 static int actor_forward_impl(const void* packed, const float* obs, float* actions, int num_envs, int num_agents, int in_dims,
                               float* ou_state, float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step,
-                              int env_offset, const flock_noise_counters_t* counters, void* stream) {
+                              int env_offset, const flock_noise_counters_t* counters, void* stream,
+                              const int32_t* obs_head = nullptr, int ring_h = 0, int ring_k = 0) {
     int rc = actor_check_dims(num_agents, in_dims, 400, 300, 2);
     if (rc != FLOCK_OK) return rc;
     if (packed == nullptr || obs == nullptr || actions == nullptr) return fail(FLOCK_E_INVALID, "null argument");
@@ -593,8 +685,10 @@ static int actor_forward_impl(const void* packed, const float* obs, float* actio
     if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(obs) & 15u) ||
         (reinterpret_cast<uintptr_t>(actions) & 7u) || (reinterpret_cast<uintptr_t>(ou_state) & 7u))
         return fail(FLOCK_E_INVALID, "actor buffers must be 16-byte aligned");
+    if (obs_head != nullptr && (ring_h < 1 || ring_h > 4 || ring_k < 1 || ring_k > 3 || ring_h * ring_k != in_dims))
+        return fail(FLOCK_E_INVALID, "observation ring %d x %d does not match input_dims %d (obs_hist <= 4, k <= 3)", ring_h, ring_k, in_dims);
     cudaError_t err = flock::launch_actor_forward(packed, obs, actions, num_envs, num_agents, in_dims, ou_state, theta, mu, sigma,
-                                                  dt, seed, step, env_offset, noise_counters(counters),
+                                                  dt, seed, step, env_offset, noise_counters(counters), obs_head, ring_h, ring_k,
                                                   static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "actor forward kernel launch");
 }
@@ -612,6 +706,15 @@ int flock_actor_forward_ou(const void* packed, const float* obs, float* actions,
     if (!(dt >= 0.0f) || !(sigma >= 0.0f)) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
     return actor_forward_impl(packed, obs, actions, num_envs, num_agents, in_dims, ou_state, theta, mu, sigma, dt, seed, step,
                               env_offset, counters, stream);
+}
+
+int flock_actor_forward_ring(const void* packed, const float* obs_ring, const int32_t* obs_head, float* actions, int num_envs,
+                             int num_agents, int obs_hist, int k, float* ou_state, float theta, float mu, float sigma, float dt,
+                             uint64_t seed, uint32_t step, int env_offset, const flock_noise_counters_t* counters, void* stream) {
+    if (obs_head == nullptr) return fail(FLOCK_E_INVALID, "obs_head is NULL");
+    if (ou_state != nullptr && (!(dt >= 0.0f) || !(sigma >= 0.0f))) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
+    return actor_forward_impl(packed, obs_ring, actions, num_envs, num_agents, obs_hist * k, ou_state, theta, mu, sigma, dt, seed,
+                              step, env_offset, counters, stream, obs_head, obs_hist, k);
 }
 
 size_t flock_rnn_actor_packed_bytes(int num_agents) {

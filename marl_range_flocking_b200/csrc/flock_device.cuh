@@ -45,6 +45,7 @@ struct Params {
     float* prev_h;
     float *vx, *vy;
     float* obs;
+    int32_t* obs_head;  // uw ring layout: [E] slot of the newest row (nullptr = materialised window layout)
     int32_t* nn;
     float* reward;
     uint8_t* agent_done;
@@ -64,7 +65,24 @@ struct Params {
     float* m_reward;
     uint8_t* m_agent_done;
     uint8_t* m_env_done;
+    // streamed rollout (flock_rollout_n): time-major trajectory buffers, slice t = step t of the launch
+    const float* traj_actions;   // [T][E][N][2] or [T][E][N] (uwd); nullptr = canonical Philox random actions
+    float* traj_obs;             // [T][E][N][k] newest range row of every step
+    float* traj_reward;          // [T][E][N]
+    uint8_t* traj_agent_done;    // [T][E][N]
+    uint8_t* traj_env_done;      // [T][E]
+    int32_t* traj_nn;            // [T][E][N][k], nullable
 };
+
+// uw observation history (gym_flock_uw.py:120-123), two layouts:
+//   window (obs_head == nullptr): obs[E][N][H][k], newest row first, shifted by one row every step -- the
+//          reference's materialised view (36 B read + 48 B written per agent-step at H = 4, k = 3);
+//   ring:  obs[E][H][N][k] + obs_head[E]: row r of the window lives in slot (head + r) % H. A step moves the head back
+//          by one and writes ONLY the new row: k floats per agent, one contiguous run per env, nothing read.
+__device__ __forceinline__ int ring_prev_slot(int head, int H) { return head == 0 ? H - 1 : head - 1; }
+__device__ __forceinline__ float* ring_row(const Params& p, int env, int slot, int a) {
+    return p.obs + (((size_t)env * p.H + slot) * p.N + a) * (size_t)p.k;
+}
 
 // Programmatic dependent launch (PDL): a step kernel lets the NEXT kernel of the stream start
 // launching immediately (its index prologue overlaps our execution) and itself waits for the

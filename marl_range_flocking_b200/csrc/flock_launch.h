@@ -39,8 +39,13 @@ struct NoiseCounters {
     const uint32_t* env_epoch = nullptr;
 };
 
-// flock_small.cu (N <= 32)
-cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool multi, int sm_count, cudaStream_t s);
+// flock_small.cu (N <= 32); kernel modes of flock_small_impl.cuh as seen by the API
+enum : int { kSmallModeStep = 0, kSmallModeMirror = 1, kSmallModeAutoReset = 2, kSmallModeMulti = 3, kSmallModeRollout = 4,
+             kSmallModeNoise = 5 };
+// mode: the kernel modes of flock_small_impl.cuh (0 step, 1 host mirror, 2 fused auto-reset, 3 step_n, 4 rollout_n, 5 fused sensing noise)
+cudaError_t launch_step_small(int variant, bool periodic, const Params& p, int mode, int sm_count, cudaStream_t s);
+cudaError_t launch_newest_row(const Params& p, float* out, int sm_count, cudaStream_t s);    // [E][N][k] newest range row
+cudaError_t launch_obs_window(const Params& p, float* out, int sm_count, cudaStream_t s);   // uw ring -> newest-first window
 cudaError_t launch_reset_small(const Params& p, int sm_count, cudaStream_t s);
 cudaError_t launch_random_actions(int variant, const Params& p, float* out, int sm_count, cudaStream_t s);
 cudaError_t launch_range_noise(const Params& p, int sm_count, cudaStream_t s);
@@ -67,7 +72,8 @@ void actor_dims(int* fc1, int* fc2, int* n_actions);
 cudaError_t launch_actor_pack(int agents, int in_dims, const float* const* ptrs, void* blobs, cudaStream_t s);
 cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* actions, int E, int N, int in_dims,
                                  float* ou_state, float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed,
-                                 uint32_t step, int env_offset, NoiseCounters ctr, cudaStream_t s);
+                                 uint32_t step, int env_offset, NoiseCounters ctr, const int32_t* obs_head, int ring_h, int ring_k,
+                                 cudaStream_t s);
 
 // flock_qnet.cu (fused VDN Q-network forward + epsilon-greedy action selection, fp32)
 int qnet_max_obs();

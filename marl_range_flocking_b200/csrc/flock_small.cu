@@ -54,7 +54,8 @@ __global__ void flock_range_noise_kernel(const __grid_constant__ Params p) {
         const int env = (int)(i / p.N), a = (int)(i - (size_t)env * p.N);
         if (p.env_mask != nullptr && p.env_mask[env] == 0) continue;
         const uint32_t epoch = (uint32_t)p.ep_len[env], word = stream_word(kTagRange, p.reset_epoch[env]);
-        float* o = p.obs + i * (size_t)(p.H * k);
+        // newest row: first row of the window, or the head slot of the ring
+        float* o = (p.H > 1 && p.obs_head != nullptr) ? ring_row(p, env, p.obs_head[env], a) : p.obs + i * (size_t)(p.H * k);
         for (int c = 0; c * 4 < k; ++c) {
             const uint4 r = philox4x32_10((uint32_t)(p.env_offset + env), (uint32_t)a + 65536u * (uint32_t)c, epoch, word,
                                           p.seed_lo, p.seed_hi);
@@ -68,6 +69,35 @@ __global__ void flock_range_noise_kernel(const __grid_constant__ Params p) {
                 o[c * 4 + s] = d;
             }
         }
+    }
+}
+
+// Materialise the newest-first (E, N, H, k) window of a ring-layout env (uw): out[e][a][r][:] = ring[e][(head[e] + r) % H][a][:].
+// On request only (single-env facade, host copy-out, PyTorch policies): the consumers we own read the ring in place.
+__global__ void flock_obs_window_kernel(const __grid_constant__ Params p, float* out) {
+    const int H = p.H, k = p.k, N = p.N;
+    const size_t n = (size_t)p.E * N * H * k;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % k);
+        const size_t q = i / k;
+        const int r = (int)(q % H);
+        const size_t ea = q / H;
+        const int a = (int)(ea % N), env = (int)(ea / N);
+        const int slot = (p.obs_head[env] + r) % H;
+        out[i] = ring_row(p, env, slot, a)[c];
+    }
+}
+
+// newest range row of every agent -> out[E][N][k] (rollout fallback for large swarms / sensing noise)
+__global__ void flock_newest_row_kernel(const __grid_constant__ Params p, float* out) {
+    const int k = p.k, N = p.N;
+    const size_t n = (size_t)p.E * N * k;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % k);
+        const size_t ea = i / k;
+        const int a = (int)(ea % N), env = (int)(ea / N);
+        const float* o = (p.H > 1 && p.obs_head != nullptr) ? ring_row(p, env, p.obs_head[env], a) : p.obs + ea * (size_t)(p.H * k);
+        out[i] = o[c];
     }
 }
 
@@ -93,30 +123,30 @@ __global__ void flock_debug_philox_kernel(const uint32_t* ck, int n, uint32_t* o
 // `nearest_neighbors` in v2 (gym_flock_v2.py:150, VecEnv default track_neighbors=True) and discards
 // the indices in uw / uwd; without the buffer the values-only selection network is used.
 // -------------------------------------------------------------------------------------------------
-extern template cudaError_t launch_step_small_vpi<FLOCK_V2, true, true>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_V2, false, true>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_V2, true, false>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_V2, false, false>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_UW, false, true>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_UW, false, false>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, true>(const Params&, bool, int, cudaStream_t);
-extern template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, false>(const Params&, bool, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_V2, true, true>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_V2, false, true>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_V2, true, false>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_V2, false, false>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_UW, false, true>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_UW, false, false>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, true>(const Params&, int, int, cudaStream_t);
+extern template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, false>(const Params&, int, int, cudaStream_t);
 
-cudaError_t launch_step_small(int variant, bool periodic, const Params& p, bool multi, int sm_count, cudaStream_t s) {
+cudaError_t launch_step_small(int variant, bool periodic, const Params& p, int mode, int sm_count, cudaStream_t s) {
     const bool idx = p.nn != nullptr;
     switch (variant) {
         case FLOCK_V2:
             if (idx)
-                return periodic ? launch_step_small_vpi<FLOCK_V2, true, true>(p, multi, sm_count, s)
-                                : launch_step_small_vpi<FLOCK_V2, false, true>(p, multi, sm_count, s);
-            return periodic ? launch_step_small_vpi<FLOCK_V2, true, false>(p, multi, sm_count, s)
-                            : launch_step_small_vpi<FLOCK_V2, false, false>(p, multi, sm_count, s);
+                return periodic ? launch_step_small_vpi<FLOCK_V2, true, true>(p, mode, sm_count, s)
+                                : launch_step_small_vpi<FLOCK_V2, false, true>(p, mode, sm_count, s);
+            return periodic ? launch_step_small_vpi<FLOCK_V2, true, false>(p, mode, sm_count, s)
+                            : launch_step_small_vpi<FLOCK_V2, false, false>(p, mode, sm_count, s);
         case FLOCK_UW:
-            return idx ? launch_step_small_vpi<FLOCK_UW, false, true>(p, multi, sm_count, s)
-                       : launch_step_small_vpi<FLOCK_UW, false, false>(p, multi, sm_count, s);
+            return idx ? launch_step_small_vpi<FLOCK_UW, false, true>(p, mode, sm_count, s)
+                       : launch_step_small_vpi<FLOCK_UW, false, false>(p, mode, sm_count, s);
         default:
-            return idx ? launch_step_small_vpi<FLOCK_UWD, false, true>(p, multi, sm_count, s)
-                       : launch_step_small_vpi<FLOCK_UWD, false, false>(p, multi, sm_count, s);
+            return idx ? launch_step_small_vpi<FLOCK_UWD, false, true>(p, mode, sm_count, s)
+                       : launch_step_small_vpi<FLOCK_UWD, false, false>(p, mode, sm_count, s);
     }
 }
 
@@ -145,6 +175,24 @@ cudaError_t launch_range_noise(const Params& p, int sm_count, cudaStream_t s) {
     if (grid > sm_count * 8) grid = sm_count * 8;
     if (grid < 1) grid = 1;
     flock_range_noise_kernel<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_newest_row(const Params& p, float* out, int sm_count, cudaStream_t s) {
+    const size_t n = (size_t)p.E * p.N * p.k;
+    int grid = (int)((n + 255) / 256);
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    if (grid < 1) grid = 1;
+    flock_newest_row_kernel<<<grid, 256, 0, s>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obs_window(const Params& p, float* out, int sm_count, cudaStream_t s) {
+    const size_t n = (size_t)p.E * p.N * p.H * p.k;
+    int grid = (int)((n + 255) / 256);
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    if (grid < 1) grid = 1;
+    flock_obs_window_kernel<<<grid, 256, 0, s>>>(p, out);
     return cudaGetLastError();
 }
 

@@ -58,13 +58,26 @@ __device__ __forceinline__ void store_row(T* dst, const T (&v)[MAXN], int n) {
         if (s < n) dst[s] = v[s];
 }
 
-// obs row(s) of one agent. H == 1: obs[idx][k]. H == 4 (uw): shift the window by one slot and put
-// the new ranges first (gym_flock_uw.py:120-123); `fresh` = window is all zeros (reset).
+// obs row(s) of one agent after a step (`fresh` = false) or a reset (`fresh` = true: the history is zero-filled,
+// gym_flock_uw.py:100-102). H == 1: obs[idx][k]. H > 1 (uw): window layout = shift by one row and put the new
+// ranges first (gym_flock_uw.py:120-123); ring layout = write the new row into slot `slot` (the env's NEW head
+// after a step, its unchanged head after a reset) and, when fresh, zero the other slots.
 template <int K>
-__device__ __forceinline__ void write_obs(const Params& p, size_t idx, const float (&dist)[K], bool fresh) {
+__device__ __forceinline__ void write_obs(const Params& p, int env, int a, size_t idx, const float (&dist)[K], bool fresh,
+                                          int slot) {
     const int k = p.k;
     if (p.H == 1) {
         store_row<float, K>(p.obs + idx * k, dist, k);
+        return;
+    }
+    if (p.obs_head != nullptr) {
+        for (int sl = 0; sl < p.H; ++sl) {
+            if (sl != slot && !fresh) continue;
+            float* o = ring_row(p, env, sl, a);
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                if (s < k) o[s] = (sl == slot) ? dist[s] : 0.0f;
+        }
         return;
     }
     float* o = p.obs + idx * (size_t)(p.H * k);
@@ -86,6 +99,33 @@ __device__ __forceinline__ void write_obs(const Params& p, size_t idx, const flo
 #pragma unroll
     for (int s = 0; s < K; ++s)
         if (s < k) o[s] = dist[s];
+}
+
+// Optional sensing noise fused into the step epilogue (north-star extension; the reference has none): the new row of
+// range observations becomes clamp(d + std * z, 0, sensor_range), z ~ N(0,1) from the Philox stream (global env,
+// agent + 65536 * chunk, ep_len AFTER the step, tag 3 + 4 * reset_epoch). Same arithmetic, same stream as the stand-alone
+// flock_range_noise_kernel (which still serves resets and the tiled path); collisions, dones and rewards keep the true ranges.
+template <int K>
+__device__ __forceinline__ void add_range_noise(const Params& p, int env_global, int agent, uint32_t epoch, uint32_t repoch,
+                                                float (&dist)[K]) {
+    const uint32_t word = stream_word(kTagRange, repoch);
+#pragma unroll
+    for (int c = 0; c * 4 < K; ++c) {
+        if (c * 4 >= p.k) break;
+        const uint4 r = philox4x32_10((uint32_t)env_global, (uint32_t)agent + 65536u * (uint32_t)c, epoch, word, p.seed_lo, p.seed_hi);
+        float z[4];
+        normal2(r.x, r.y, z[0], z[1]);
+        normal2(r.z, r.w, z[2], z[3]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (c * 4 + s < K && c * 4 + s < p.k) {
+                const float nz = p.range_noise_std * z[s];
+                float d = dist[c * 4 + s] + nz;
+                d = fminf(fmaxf(d, 0.0f), p.sensor_range);
+                dist[c * 4 + s] = d;
+            }
+        }
+    }
 }
 
 // Sum over one env group of reward_fx(reward), order free and exact: rewards take at most 8 values
@@ -188,25 +228,45 @@ __device__ __forceinline__ float seq_sum(const float* s, int N) {
 
 // -------------------------------------------------------------------------------------------------
 // step: MultiAgentEnv.step of the three variants (gym_flock_v2.py:71-83, gym_flock_uw.py:69-81,
-// gym_flock_uw_discrete.py:110-122). NSTEPS > 1 (flock_step_n) keeps the state in registers and
-// draws the canonical random actions in-kernel.
+// gym_flock_uw_discrete.py:110-122).
 // -------------------------------------------------------------------------------------------------
 template <int K>
+struct ResetResult {      // what a caller that keeps the state in registers needs back from reset_groups()
+    float x, y, h;
+    float dist[K];
+    int idx[K];
+};
+
+template <int K>
 __device__ __forceinline__ void reset_groups(const Params& p, const LaneMap& m, float* sx, float* sy, int env,
-                                             size_t idx, bool want, bool keep_outputs);
+                                             size_t idx, bool want, bool keep_outputs, float* row_dst = nullptr,
+                                             int* nn_dst = nullptr, ResetResult<K>* res = nullptr);
 
 template <int K, bool IDX>
 struct ListOf { using type = TopK<K>; };
 template <int K>
 struct ListOf<K, false> { using type = TopKValues<K>; };
 
-// MIRROR: also write the results to device-visible host memory (flock_step_host zero-copy path);
-// AUTORESET: env groups whose step ended with a collision are re-drawn in the same launch (reward
-// and done flags of the finishing step stay, obs becomes the first observation of the new episode).
-// Both are separate instantiations because even an untaken branch costs ~3 % in the plain kernel.
+// Kernel modes -- separate instantiations, because even an untaken branch costs ~3 % in the plain kernel:
+//   Step       one step, actions from p.actions
+//   Mirror     Step + the results also written to device-visible HOST memory (flock_step_host zero-copy path)
+//   AutoReset  Step + env groups whose step ended with a collision are re-drawn in the same launch (reward and done
+//              flags of the finishing step stay, obs becomes the first observation of the new episode)
+//   Noise      Step + Philox range-sensing noise on the stored observation row (range_noise_std > 0)
+//   Multi      flock_step_n: p.num_steps steps, state in registers, canonical Philox random actions, outputs = last step
+//   Rollout    flock_rollout_n: Multi + actions read from and obs | reward | dones written to time-major trajectory
+//              buffers every step, optional in-kernel auto-reset (p.fused_auto_reset)
+enum : int { kModeStep = kSmallModeStep, kModeMirror = kSmallModeMirror, kModeAutoReset = kSmallModeAutoReset, kModeMulti = kSmallModeMulti,
+             kModeRollout = kSmallModeRollout, kModeNoise = kSmallModeNoise };
+
 // IDX = false: neighbour indices are not tracked (values-only selection network).
-template <int V, int K, bool PER, bool MULTI, int NJ4, bool MIRROR, bool AUTORESET, bool IDX>
+template <int V, int K, bool PER, int MODE, int NJ4, bool IDX>
 __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const __grid_constant__ Params p) {
+    constexpr bool MULTI = MODE == kModeMulti || MODE == kModeRollout;
+    constexpr bool ROLLOUT = MODE == kModeRollout;
+    constexpr bool MIRROR = MODE == kModeMirror;
+    constexpr bool AUTORESET = MODE == kModeAutoReset;
+    constexpr bool NOISE = MODE == kModeNoise;
     __shared__ __align__(16) float s_stage[kSmallWarps][3][kSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* sx = s_stage[wib][0];
@@ -221,6 +281,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
 
     const int GN = G * N;
     const unsigned EN = (unsigned)p.E * (unsigned)N;
+    const bool ring = (V == FLOCK_UW) && p.obs_head != nullptr;
     for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
         // the warp's agents are one contiguous run: index = task*G*N + lane, so the loads below can
         // issue after two integer operations (the env / agent split is only needed later).
@@ -229,25 +290,27 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
         const unsigned flat = (unsigned)task * (unsigned)GN + (unsigned)lane;
         const bool live = lane < GN && flat < EN;
         const size_t idx = live ? flat : 0u;
-        const int env = task * G + m.g;
+        const int env = live ? task * G + m.g : 0;
         float x = 0.f, y = 0.f, h = 0.f, prev_h = 0.f;
         float prev_h_in = 0.f;
-        uint32_t ep0 = 0u, repoch = 0u;   // per-env Philox epoch (episode step, reset epoch)
+        uint32_t ep_base = 0u, repoch = 0u;   // per-env Philox epoch (episode step of this launch's step 0, reset epoch)
         // Every global load of the step is issued here, up front, so the warp pays ONE DRAM round
         // trip: the read-modify-write operands of the epilogue (episode counters, uw obs window)
         // are prefetched into registers together with the state and the actions.
         long long ep_ret0 = 0;
         float act0 = 0.f, act1 = 0.f, nz0 = 0.f, nz1 = 0.f;
         float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0;   // uw window (k = 3 fast path)
-        const bool fast_win = (V == FLOCK_UW) && !MULTI && k == 3 && p.H == 4;
+        const bool fast_win = (V == FLOCK_UW) && !MULTI && !ring && k == 3 && p.H == 4;
+        int head = 0;                          // uw ring: slot of the newest row before this launch
         if (live) {
-            ep0 = (uint32_t)p.ep_len[env];
-            if (MULTI || V == FLOCK_UWD) repoch = p.reset_epoch[env];
+            ep_base = (uint32_t)p.ep_len[env];
+            if (MULTI || NOISE || V == FLOCK_UWD) repoch = p.reset_epoch[env];
             if (m.a == 0 && p.ep_return_fx != nullptr) ep_ret0 = p.ep_return_fx[env];
             x = p.x[idx];
             y = p.y[idx];
             h = p.h[idx];
             if (V == FLOCK_UW) prev_h = prev_h_in = p.prev_h[idx];
+            if (ring) head = p.obs_head[env];
             if (!MULTI) {
                 if (V == FLOCK_UWD) {
                     act0 = p.actions[idx];
@@ -267,6 +330,14 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     w1 = o4[1];
                     w2 = o4[2];
                 }
+            } else if (ROLLOUT && p.traj_actions != nullptr) {   // actions of step 0; step t+1 is prefetched during step t
+                if (V == FLOCK_UWD) {
+                    act0 = p.traj_actions[idx];
+                } else {
+                    const float2 act = reinterpret_cast<const float2*>(p.traj_actions)[idx];
+                    act0 = act.x;
+                    act1 = act.y;
+                }
             }
         }
         float vx = 0.f, vy = 0.f, rew = 0.f;
@@ -275,18 +346,34 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
         List t;
         bool coll = false, env_coll = false;
         long long ret_fx = 0;
-        float hist[(V == FLOCK_UW) ? 3 * K : 1];
+        float hist[(V == FLOCK_UW) ? 3 * K : 1];   // rows 1..3 of the window after the current step (MULTI)
         if (MULTI && V == FLOCK_UW && live) {
-            const float* o = p.obs + idx * (size_t)(4 * k);
 #pragma unroll
-            for (int s = 0; s < 3 * K; ++s) hist[s] = (s % K < k) ? o[(s / K) * k + (s % K)] : 0.0f;
+            for (int r = 0; r < 3; ++r) {
+                const float* o = ring ? ring_row(p, env, (head + r) % p.H, m.a) : p.obs + idx * (size_t)(4 * k) + r * k;
+#pragma unroll
+                for (int s = 0; s < K; ++s) hist[r * K + s] = (s < k) ? o[s] : 0.0f;
+            }
         }
 
         for (int st = 0; st < nsteps; ++st) {
             float a0 = 0.f, a1 = 0.f, nzu = 0.f, nzw = 0.f;
             if (live) {
-                const uint32_t step = ep0 + (uint32_t)st;
-                if (MULTI) {
+                const uint32_t step = ep_base + (uint32_t)st;
+                if (ROLLOUT && p.traj_actions != nullptr) {
+                    a0 = act0;
+                    a1 = act1;
+                    if (st + 1 < nsteps) {   // prefetch the next step's action under this step's arithmetic
+                        const size_t nidx = (size_t)(st + 1) * EN + idx;
+                        if (V == FLOCK_UWD) {
+                            act0 = p.traj_actions[nidx];
+                        } else {
+                            const float2 act = reinterpret_cast<const float2*>(p.traj_actions)[nidx];
+                            act0 = act.x;
+                            act1 = act.y;
+                        }
+                    }
+                } else if (MULTI) {
                     random_action<V>(p, p.env_offset + env, m.a, step, repoch, a0, a1);
                 } else {
                     a0 = act0;
@@ -313,6 +400,12 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 const float* syg = sy + m.g * sstride;
                 float comx = 0.f, comy = 0.f, hmean = 0.f, sumx, sumy;
                 if (V == FLOCK_UWD) hmean = mean_of_sum(p, seq_sum(sh + m.g * sstride, N));  // uwd:256
+                if (MULTI && V == FLOCK_UW && st > 0) {
+#pragma unroll
+                    for (int s = 3 * K - 1; s >= K; --s) hist[s] = hist[s - K];   // K-strided shift of the window
+#pragma unroll
+                    for (int s = 0; s < K; ++s) hist[s] = dist[s];
+                }
                 knn_small<K, PER, NJ4, V == FLOCK_UW, List>(sxg, syg, m.a, N, sstride, x, y, p.B, t, sumx, sumy);
                 if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
                     comx = mean_of_sum(p, sumx);
@@ -322,17 +415,59 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 reward_flags<V>(p, x, y, h, prev_h, comx, comy, hmean, f1, f2);
                 rew = reward_from_flags<V>(coll, f1, f2);
                 if (V == FLOCK_UW) prev_h = h;
-                if (MULTI && V == FLOCK_UW && st + 1 < nsteps) {
-#pragma unroll
-                    for (int s = 3 * K - 1; s >= K; --s) hist[s] = hist[s - K];   // K-strided copy of the window
-#pragma unroll
-                    for (int s = 0; s < K; ++s) hist[s] = dist[s];
-                }
             }
             // env-level reductions: warp-wide ballots, each env reads its own lane group
             unsigned bc;
             ret_fx += group_return_fx<V>(m.gmask, live && coll, live && f1, live && f2, bc);
             env_coll = bc != 0u;
+            if (ROLLOUT) {
+                // this step's slice of the trajectory: obs row | reward | agent_done | env_done (| nn)
+                const size_t tidx = (size_t)st * EN + idx;
+                if (live) {
+                    store_row<float, K>(p.traj_obs + tidx * k, dist, k);
+                    if constexpr (IDX) {
+                        if (p.traj_nn != nullptr) store_row<int, K>(p.traj_nn + tidx * k, t.idx, k);
+                    }
+                    p.traj_reward[tidx] = rew;
+                    p.traj_agent_done[tidx] = coll ? 1 : 0;
+                    if (m.a == 0) p.traj_env_done[(size_t)st * p.E + env] = env_coll ? 1 : 0;
+                }
+                const bool want = live && env_coll && p.fused_auto_reset != 0;
+                if (__any_sync(0xffffffffu, want)) {
+                    // the batched "caller resets on done[1]" (main.py:31-51) inside the rollout: close the episode
+                    // counters of the finished envs in memory, re-draw them, and continue from the new state
+                    if (want && m.a == 0) {
+                        p.ep_len[env] = (int)(ep_base + (uint32_t)st + 1u);
+                        if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = ep_ret0 + ret_fx;
+                    }
+                    __syncwarp();
+                    ResetResult<K> rr;
+                    reset_groups<K>(p, m, sx, sy, env, idx, want, true, p.traj_obs + tidx * k,
+                                    (IDX && p.traj_nn != nullptr) ? p.traj_nn + tidx * k : nullptr, &rr);
+                    if (want) {
+                        x = rr.x;
+                        y = rr.y;
+                        h = rr.h;
+                        prev_h = 0.0f;
+                        vx = 0.0f;
+                        vy = 0.0f;
+#pragma unroll
+                        for (int s = 0; s < K; ++s) dist[s] = rr.dist[s];
+                        if constexpr (IDX) {
+#pragma unroll
+                            for (int s = 0; s < K; ++s) t.idx[s] = rr.idx[s];
+                        }
+                        if (V == FLOCK_UW) {
+#pragma unroll
+                            for (int s = 0; s < 3 * K; ++s) hist[s] = 0.0f;
+                        }
+                        ep_base = 0u - (uint32_t)(st + 1);      // episode step 0 at launch step st + 1
+                        repoch = p.reset_epoch[env];
+                        ep_ret0 = 0;
+                        ret_fx = 0;
+                    }
+                }
+            }
         }
 
         pdl_launch_dependents();   // the next kernel may start launching while we store the results
@@ -345,15 +480,25 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                 p.vx[idx] = vx;
                 p.vy[idx] = vy;
             }
-            if (MULTI && V == FLOCK_UW && nsteps > 1) {
-                // window after nsteps: newest first = dist, then the K-strided register history
-                float* o = p.obs + idx * (size_t)(4 * k);
-                for (int s = 0; s < k; ++s) o[s] = dist[s];
+            if (NOISE) add_range_noise<K>(p, p.env_offset + env, m.a, ep_base + (uint32_t)nsteps, repoch, dist);
+            if (MULTI && V == FLOCK_UW) {
+                // window after the launch: newest first = dist, then the K-strided register history
+                const int new_head = ring ? (head + p.H - (nsteps % p.H)) % p.H : 0;
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < 4; ++r) {
+                    float* o = ring ? ring_row(p, env, (new_head + r) % p.H, m.a) : p.obs + idx * (size_t)(4 * k) + r * k;
 #pragma unroll
                     for (int s = 0; s < K; ++s)
-                        if (s < k) o[(r + 1) * k + s] = hist[r * K + s];
+                        if (s < k) o[s] = (r == 0) ? dist[s] : hist[(r == 0 ? 0 : r - 1) * K + s];
+                }
+                if (ring && m.a == 0) p.obs_head[env] = new_head;
+            } else if (ring) {
+                const int new_head = ring_prev_slot(head, p.H);
+                float* o = ring_row(p, env, new_head, m.a);
+#pragma unroll
+                for (int s = 0; s < K; ++s)
+                    if (s < k) o[s] = dist[s];
+                if (m.a == 0) p.obs_head[env] = new_head;
             } else if (fast_win) {
                 float4* o4 = reinterpret_cast<float4*>(p.obs + idx * 12);   // shift by one row of 3, newest first
                 o4[0] = make_float4(dist[0], dist[1], dist[2 % K], w0.x);
@@ -362,7 +507,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             } else if (V != FLOCK_UW) {
                 store_row<float, K>(p.obs + idx * k, dist, k);      // H == 1
             } else {
-                write_obs<K>(p, idx, dist, false);
+                write_obs<K>(p, env, m.a, idx, dist, false, 0);
             }
             if constexpr (IDX) {
                 if (p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
@@ -372,7 +517,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             if (m.a == 0) {
                 p.env_done[env] = env_coll ? 1 : 0;
                 if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = ep_ret0 + ret_fx;
-                p.ep_len[env] = (int)ep0 + nsteps;
+                p.ep_len[env] = (int)(ep_base + (uint32_t)nsteps);
             }
             if (MIRROR) {
                 // host-call path: the results also go straight to mapped host memory (posted PCIe
@@ -384,7 +529,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     o4[2] = make_float4(w1.y, w1.z, w1.w, w2.x);
                 } else if (V != FLOCK_UW) {
                     store_row<float, K>(p.m_obs + idx * k, dist, k);
-                } else {
+                } else {   // generic window (the ring layout never takes the zero-copy path)
                     const size_t hk = (size_t)p.H * k;
                     for (size_t u = 0; u < hk; ++u) p.m_obs[idx * hk + u] = p.obs[idx * hk + u];
                 }
@@ -405,11 +550,14 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
 // gym_flock_uw_discrete.py:124-156) with a BOUNDED rejection loop, masked and batched.
 // reset_groups() (re)draws the env groups of the calling warp whose lanes pass `want` (uniform per
 // group); ALL 32 lanes must call it. It is the body of the reset kernel and, with keep_outputs, the
-// fused auto-reset tail of the step kernel.
+// fused auto-reset tail of the step / rollout kernels (row_dst / nn_dst: the first observation row and
+// neighbour list go to a trajectory slice instead of the env's buffers; res: the new state for a caller
+// that keeps it in registers).
 // -------------------------------------------------------------------------------------------------
 template <int K>
 __device__ __forceinline__ void reset_groups(const Params& p, const LaneMap& m, float* sx, float* sy, int env,
-                                             size_t idx, bool want, bool keep_outputs) {
+                                             size_t idx, bool want, bool keep_outputs, float* row_dst, int* nn_dst,
+                                             ResetResult<K>* res) {
     const int N = p.N, k = p.k, sstride = p.sstride;
     const size_t EN = (size_t)p.E * N;
     float x = 0.f, y = 0.f, h = 0.f;
@@ -467,8 +615,23 @@ __device__ __forceinline__ void reset_groups(const Params& p, const LaneMap& m, 
             p.vx[idx] = 0.0f;                                     // v2:94
             p.vy[idx] = 0.0f;
         }
-        write_obs<K>(p, idx, dist, true);
-        if (p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
+        if (row_dst != nullptr) {
+            store_row<float, K>(row_dst, dist, k);
+        } else {
+            write_obs<K>(p, env, m.a, idx, dist, true, p.obs_head != nullptr ? p.obs_head[env] : 0);
+        }
+        if (nn_dst != nullptr) store_row<int, K>(nn_dst, t.idx, k);
+        else if (row_dst == nullptr && p.nn != nullptr) store_row<int, K>(p.nn + idx * k, t.idx, k);
+        if (res != nullptr) {
+            res->x = x;
+            res->y = y;
+            res->h = h;
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                res->dist[s] = dist[s];
+                res->idx[s] = t.idx[s];
+            }
+        }
         if (!keep_outputs) {
             p.reward[idx] = 0.0f;
             p.agent_done[idx] = coll ? 1 : 0;
@@ -506,16 +669,19 @@ inline int small_grid(const Params& p, int sm_count) {
 }
 
 template <int V, int K, bool PER, int NJ4, bool IDX>
-cudaError_t launch_step_small_vkpni(const Params& p, bool multi, int sm_count, cudaStream_t s) {
+cudaError_t launch_step_small_vkpni(const Params& p, int mode, int sm_count, cudaStream_t s) {
     const int grid = small_grid(p, sm_count);
-    if (multi) {
-        flock_step_small_kernel<V, K, PER, true, NJ4, false, false, IDX><<<grid, kSmallThreads, 0, s>>>(p);
-        return cudaGetLastError();
-    }
-    const bool mirror = p.m_obs != nullptr;
-    if (p.fused_auto_reset && !mirror) {   // step + restart of the finished envs in one launch
-        flock_step_small_kernel<V, K, PER, false, NJ4, false, true, IDX><<<grid, kSmallThreads, 0, s>>>(p);
-        return cudaGetLastError();
+    switch (mode) {
+        case kModeMulti:
+            flock_step_small_kernel<V, K, PER, kModeMulti, NJ4, IDX><<<grid, kSmallThreads, 0, s>>>(p);
+            return cudaGetLastError();
+        case kModeRollout:
+            flock_step_small_kernel<V, K, PER, kModeRollout, NJ4, IDX><<<grid, kSmallThreads, 0, s>>>(p);
+            return cudaGetLastError();
+        case kModeAutoReset:   // step + restart of the finished envs in one launch
+            flock_step_small_kernel<V, K, PER, kModeAutoReset, NJ4, IDX><<<grid, kSmallThreads, 0, s>>>(p);
+            return cudaGetLastError();
+        default: break;
     }
     // Programmatic dependent launch (default on, FLOCK_PDL=0 disables): the kernel triggers its
     // dependents right before its epilogue, so the next step's launch overlaps our result stores.
@@ -523,11 +689,6 @@ cudaError_t launch_step_small_vkpni(const Params& p, bool multi, int sm_count, c
         const char* v = getenv("FLOCK_PDL");
         return v == nullptr || v[0] != '0';
     }();
-    if (!use_pdl) {
-        if (mirror) flock_step_small_kernel<V, K, PER, false, NJ4, true, false, IDX><<<grid, kSmallThreads, 0, s>>>(p);
-        else flock_step_small_kernel<V, K, PER, false, NJ4, false, false, IDX><<<grid, kSmallThreads, 0, s>>>(p);
-        return cudaGetLastError();
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kSmallThreads);
@@ -537,28 +698,29 @@ cudaError_t launch_step_small_vkpni(const Params& p, bool multi, int sm_count, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (mirror) return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, true, false, IDX>, p);
-    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, false, NJ4, false, false, IDX>, p);
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    if (mode == kModeMirror) return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, kModeMirror, NJ4, IDX>, p);
+    if (mode == kModeNoise) return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, kModeNoise, NJ4, IDX>, p);
+    return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, kModeStep, NJ4, IDX>, p);
 }
 
 // unrolled pair loops for the strides of the BASELINE configs (N = 9..12, 13..16, 29..32)
 template <int V, int K, bool PER, bool IDX>
-cudaError_t launch_step_small_vkpi(const Params& p, bool multi, int sm_count, cudaStream_t s) {
+cudaError_t launch_step_small_vkpi(const Params& p, int mode, int sm_count, cudaStream_t s) {
     switch (p.sstride) {
-        case 12: return launch_step_small_vkpni<V, K, PER, 3, IDX>(p, multi, sm_count, s);
-        case 16: return launch_step_small_vkpni<V, K, PER, 4, IDX>(p, multi, sm_count, s);
-        case 32: return launch_step_small_vkpni<V, K, PER, 8, IDX>(p, multi, sm_count, s);
-        default: return launch_step_small_vkpni<V, K, PER, 0, IDX>(p, multi, sm_count, s);
+        case 12: return launch_step_small_vkpni<V, K, PER, 3, IDX>(p, mode, sm_count, s);
+        case 16: return launch_step_small_vkpni<V, K, PER, 4, IDX>(p, mode, sm_count, s);
+        case 32: return launch_step_small_vkpni<V, K, PER, 8, IDX>(p, mode, sm_count, s);
+        default: return launch_step_small_vkpni<V, K, PER, 0, IDX>(p, mode, sm_count, s);
     }
 }
 
 // one explicit instantiation of this per translation unit (flock_small_<variant>.cu)
 template <int V, bool PER, bool IDX>
-cudaError_t launch_step_small_vpi(const Params& p, bool multi, int sm_count, cudaStream_t s) {
-    if (p.k <= 3) return launch_step_small_vkpi<V, 3, PER, IDX>(p, multi, sm_count, s);
-    if (p.k == 4) return launch_step_small_vkpi<V, 4, PER, IDX>(p, multi, sm_count, s);
-    return launch_step_small_vkpi<V, 8, PER, IDX>(p, multi, sm_count, s);
+cudaError_t launch_step_small_vpi(const Params& p, int mode, int sm_count, cudaStream_t s) {
+    if (p.k <= 3) return launch_step_small_vkpi<V, 3, PER, IDX>(p, mode, sm_count, s);
+    if (p.k == 4) return launch_step_small_vkpi<V, 4, PER, IDX>(p, mode, sm_count, s);
+    return launch_step_small_vkpi<V, 8, PER, IDX>(p, mode, sm_count, s);
 }
 
 }  // namespace flock

@@ -3,5 +3,5 @@
 #include "flock_small_impl.cuh"
 
 namespace flock {
-template cudaError_t launch_step_small_vpi<FLOCK_UW, false, true>(const Params&, bool, int, cudaStream_t);
+template cudaError_t launch_step_small_vpi<FLOCK_UW, false, true>(const Params&, int, int, cudaStream_t);
 }  // namespace flock

@@ -3,5 +3,5 @@
 #include "flock_small_impl.cuh"
 
 namespace flock {
-template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, false>(const Params&, bool, int, cudaStream_t);
+template cudaError_t launch_step_small_vpi<FLOCK_UWD, false, false>(const Params&, int, int, cudaStream_t);
 }  // namespace flock

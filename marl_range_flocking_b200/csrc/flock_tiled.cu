@@ -201,10 +201,22 @@ __device__ __forceinline__ void store_row_t(T* dst, const T (&v)[MAXN], int n) {
 }
 
 template <int K>
-__device__ __forceinline__ void write_obs_t(const Params& p, size_t idx, const float (&dist)[K], bool fresh) {
+__device__ __forceinline__ void write_obs_t(const Params& p, int env, int a, size_t idx, const float (&dist)[K], bool fresh) {
     const int k = p.k;
     if (p.H == 1) {
         store_row_t<float, K>(p.obs + idx * k, dist, k);
+        return;
+    }
+    if (p.obs_head != nullptr) {   // uw ring layout (flock_device.cuh): only the new row is written; a reset zero-fills the rest
+        const int head = p.obs_head[env];                       // published by the env's last CTA AFTER all rows are written
+        const int slot = fresh ? head : ring_prev_slot(head, p.H);
+        for (int sl = 0; sl < p.H; ++sl) {
+            if (sl != slot && !fresh) continue;
+            float* o = ring_row(p, env, sl, a);
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                if (s < k) o[s] = (sl == slot) ? dist[s] : 0.0f;
+        }
         return;
     }
     float* o = p.obs + idx * (size_t)(p.H * k);
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         const float rew = agent_reward<V>(p, coll, x, y, h, prev_h, comx, comy, hmean);
         fx = reward_fx(rew);
         if (V == FLOCK_UW && !(prev_h == h)) p.prev_h[idx] = h;
-        write_obs_t<K>(p, idx, dist, false);
+        write_obs_t<K>(p, env, i, idx, dist, false);
         if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
         p.reward[idx] = rew;
         p.agent_done[idx] = coll ? 1 : 0;
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
             const unsigned c = atomicExch(collide, 0u);
             p.env_done[env] = c != 0u ? 1 : 0;
             p.ep_len[env] += 1;
+            if (p.H > 1 && p.obs_head != nullptr) p.obs_head[env] = ring_prev_slot(p.obs_head[env], p.H);
             *arrive = 0u;
         }
     }
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         const size_t idx = base + i;
         const float rew = reward_from_flags<FLOCK_V2>(coll, false, false);
         fx = reward_fx(rew);
-        write_obs_t<K>(p, idx, dist, false);
+        write_obs_t<K>(p, env, 0, idx, dist, false);   // v2: H == 1
         // list entries are (agent id << 16 | slot): ids go to the neighbour list, slots to next step's hints
         int ids[K];
         unsigned hw[4] = {~0u, ~0u, ~0u, ~0u};
@@ -645,6 +658,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
             const unsigned c = atomicExch(collide, 0u);
             p.env_done[env] = c != 0u ? 1 : 0;
             p.ep_len[env] += 1;
+            if (p.H > 1 && p.obs_head != nullptr) p.obs_head[env] = ring_prev_slot(p.obs_head[env], p.H);
             *arrive = 0u;
         }
     }
@@ -903,7 +917,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(con
             fx_acc += reward_fx(rew);
             coll_any = coll_any || coll;
             if (V == FLOCK_UW && !(prev_h == h)) p.prev_h[idx] = h;
-            write_obs_t<K>(p, idx, dist, false);
+            write_obs_t<K>(p, env, i, idx, dist, false);
             if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
             p.reward[idx] = rew;
             p.agent_done[idx] = coll ? 1 : 0;
@@ -925,6 +939,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(con
             const unsigned c = atomicExch(collide, 0u);
             p.env_done[env] = c != 0u ? 1 : 0;
             p.ep_len[env] += 1;
+            if (p.H > 1 && p.obs_head != nullptr) p.obs_head[env] = ring_prev_slot(p.obs_head[env], p.H);
             *arrive = 0u;
         }
     }
@@ -994,7 +1009,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(cons
                 p.vx[idx] = 0.0f;
                 p.vy[idx] = 0.0f;
             }
-            write_obs_t<K>(p, idx, dist, true);
+            write_obs_t<K>(p, env, i, idx, dist, true);
             if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
             if (!keep) {
                 p.reward[idx] = 0.0f;

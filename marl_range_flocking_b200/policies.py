@@ -101,26 +101,39 @@ class BatchedActors(torch.nn.Module):
         lib = _lib.load_library()
         if getattr(self, "_packed", None) is None:
             self.pack_fused()
-        E, N = obs.shape[0], obs.shape[1]
-        x = obs.reshape(E, N, -1)
+        ring = hasattr(obs, "ring") and hasattr(obs, "head")        # vec_env.ObsRing: the env's history, read in place
+        if ring:
+            E, H, N, k = obs.ring.shape
+            x, in_dims = obs.ring, H * k
+        else:
+            E, N = obs.shape[0], obs.shape[1]
+            x = obs.reshape(E, N, -1)
+            in_dims = x.shape[2]
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         if out is None:
             out = torch.empty(E, N, 2, dtype=torch.float32, device=x.device)
+        if ou_state is not None and (ou_state.shape != (E, N, 2) or ou_state.dtype != torch.float32 or not ou_state.is_contiguous()):
+            raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            if ou_state is None:
-                _lib.check(lib.flock_actor_forward(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2], stream))
+            if ring:
+                _lib.check(lib.flock_actor_forward_ring(
+                    self._packed.data_ptr(), x.data_ptr(), obs.head.data_ptr(), out.data_ptr(), E, N, H, k,
+                    None if ou_state is None else ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
+                    float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset), _lib.noise_counters(counters), stream))
+            elif ou_state is None:
+                _lib.check(lib.flock_actor_forward(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, in_dims, stream))
             else:
-                if ou_state.shape != (E, N, 2) or ou_state.dtype != torch.float32 or not ou_state.is_contiguous():
-                    raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
-                _lib.check(lib.flock_actor_forward_ou(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, x.shape[2],
+                _lib.check(lib.flock_actor_forward_ou(self._packed.data_ptr(), x.data_ptr(), out.data_ptr(), E, N, in_dims,
                                                       ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
                                                       float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
                                                       _lib.noise_counters(counters), stream))
         return out
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        if hasattr(obs, "window"):            # vec_env.ObsRing: the PyTorch path works on the materialised window
+            obs = obs.window()
         E, N = obs.shape[0], obs.shape[1]
         x = obs.reshape(E, N, -1).transpose(0, 1).to(self.w1.dtype)              # (N, E, in)
         x = torch.baddbmm(self.b1, x, self.w1)

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, NamedTuple, Optional, Tuple
 
 import torch
 
@@ -32,6 +32,30 @@ def _f32(v: float) -> float:
     return float(torch.tensor(v, dtype=torch.float32).item())
 
 
+class ObsRing(NamedTuple):
+    """Handle of a uw env's observation history in the ring layout: `ring` is `(E, H, N, k)`, `head` `(E,)` int32;
+    row r of the reference's newest-first `(N, H, k)` window is `ring[e, (head[e] + r) % H]`. The fused actor kernel
+    (`BatchedActors.forward_fused`) and the replay writer take the handle as it is; anything else calls `window()`."""
+    ring: torch.Tensor
+    head: torch.Tensor
+
+    def window(self) -> torch.Tensor:
+        """The materialised `(E, N, H, k)` window (plain torch gather; `VecEnv.observation` uses the library kernel)."""
+        E, H, N, k = self.ring.shape
+        slot = (self.head.long()[:, None] + torch.arange(H, device=self.ring.device)[None, :]) % H        # (E, H)
+        rows = self.ring[torch.arange(E, device=self.ring.device)[:, None], slot]                        # (E, H, N, k)
+        return rows.permute(0, 2, 1, 3).contiguous()
+
+
+class Trajectory(NamedTuple):
+    """Time-major buffers written by `VecEnv.rollout_n` (flock_rollout_n): slice t = step t of the launch."""
+    obs: torch.Tensor          # (T, E, N, k) the new range row of every step
+    reward: torch.Tensor       # (T, E, N, 1)
+    agent_done: torch.Tensor   # (T, E, N) bool
+    env_done: torch.Tensor     # (T, E) bool
+    nn: Optional[torch.Tensor]  # (T, E, N, k) int32 or None
+
+
 class VecEnv:
     """Batched, device-resident version of the reference `MultiAgentEnv`.
 
@@ -41,7 +65,10 @@ class VecEnv:
     are the batched extensions: `seed` / `env_offset` (Philox key and global env index of env 0),
     `auto_reset` (finished envs restart in place after each step), `tiled_mode` (kernel choice for
     N > 32, see flock_set_tiled_mode), `range_noise_std` (optional N(0, std) sensing noise on the
-    observed ranges; 0 = the reference's noise-free sensing).
+    observed ranges; 0 = the reference's noise-free sensing), `obs_layout` (uw only: "window" keeps the
+    reference's materialised newest-first `(N, 4, k)` window in HBM, shifted every step; "ring" keeps a
+    4-slot ring per env and writes only the new row -- 41 instead of 125 bytes per agent-step; the
+    consumers of this package read the ring in place, `observation` materialises the window on request).
     """
 
     def __init__(self, variant: str, num_envs: int, agents: int, k: int = 4, collision_distance: float = 3,
@@ -51,12 +78,14 @@ class VecEnv:
                  max_reset_attempts: int = 64, reset_collision_distance: Optional[float] = None,
                  act_noise_std: Optional[float] = None, periodic: Optional[bool] = None,
                  track_velocities: bool = True, track_neighbors: bool = True, tiled_mode: int = 0,
-                 range_noise_std: float = 0.0):
+                 range_noise_std: float = 0.0, obs_layout: str = "window"):
         if variant not in VARIANT_IDS:
             raise ValueError(f"variant must be one of {sorted(VARIANT_IDS)}, got {variant!r}")
         if normalize_distance:
             raise NotImplementedError("normalize_distance=True is never enabled by the reference (make_env passes "
                                       "False, gym_flock_v2.py:424) and is not implemented")
+        if obs_layout not in ("window", "ring"):
+            raise ValueError(f"obs_layout must be 'window' or 'ring', got {obs_layout!r}")
         self.lib = _lib.load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("marl_range_flocking_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -107,7 +136,11 @@ class VecEnv:
         self._vy = z(E, N) if track_velocities else None
         # obs | reward | agent_done | env_done share one allocation so that the host-call path moves
         # the step results with a single device->host copy
-        self._out_slab, (self._obs, self._reward, self._agent_done, self._env_done) = self._alloc_outputs(self.device)
+        self._out_slab, (self._obs_buf, self._reward, self._agent_done, self._env_done) = self._alloc_outputs(self.device)
+        # uw ring layout: the slab's obs region holds [E][H][N][k] slots; row r of the window is slot (head + r) % H
+        self.obs_ring = obs_layout == "ring" and self.obs_hist > 1
+        self._obs_head = z(E, dtype=torch.int32) if self.obs_ring else None
+        self._obs_window = None            # materialised on request (ring layout only)
         self._nn = z(E, N, self.k, dtype=torch.int32) if track_neighbors else None
         self._reset_epoch = z(E, dtype=torch.int32)          # uint32 counter, int32 storage
         self._ep_return_fx = z(E, dtype=torch.int64)
@@ -115,7 +148,8 @@ class VecEnv:
         self._stats = z(8, dtype=torch.int64)
         ptr = lambda t: None if t is None else t.data_ptr()
         bufs = FlockBuffers(
-            ptr(self._x), ptr(self._y), ptr(self._hd), ptr(self._prev_h), ptr(self._vx), ptr(self._vy), ptr(self._obs), ptr(self._nn), ptr(self._reward),
+            ptr(self._x), ptr(self._y), ptr(self._hd), ptr(self._prev_h), ptr(self._vx), ptr(self._vy), ptr(self._obs_buf),
+            ptr(self._obs_head), ptr(self._nn), ptr(self._reward),
             ptr(self._agent_done), ptr(self._env_done), ptr(self._reset_epoch), ptr(self._ep_return_fx),
             ptr(self._ep_len), ptr(self._stats))
         check(self.lib.flock_bind(self._h, ctypes.byref(bufs)))
@@ -123,7 +157,11 @@ class VecEnv:
         self._host_async = None   # side stream + validated action buffers of step_host_async
         self._dev_index = self.device.index
         self._act_shape = torch.Size((E, N) if variant == "uwd" else (E, N, 2))
-        self._obs_view = self._obs if self.obs_hist > 1 else self._obs[:, :, 0, :]
+        if self.obs_ring:       # the same bytes, viewed as [E][H][N][k] slots
+            self._ring = ObsRing(self._obs_buf.view(E, H, N, self.k), self._obs_head)
+            self._obs_view = self._ring
+        else:
+            self._obs_view = self._obs_buf if self.obs_hist > 1 else self._obs_buf[:, :, 0, :]
 
     # ------------------------------------------------------------------------------------------
     def _alloc_outputs(self, device, pin: bool = False):
@@ -148,6 +186,25 @@ class VecEnv:
 
     def close(self):
         self.__del__()
+
+    @property
+    def _obs(self) -> torch.Tensor:
+        """(E, N, H, k) newest-first observation buffer. Window layout: the env's own buffer (zero copy). Ring
+        layout: materialised on request by flock_obs_window into a buffer that the next request overwrites."""
+        if not self.obs_ring:
+            return self._obs_buf
+        if self._obs_window is None:
+            self._obs_window = torch.empty_like(self._obs_buf)
+        with self._dev_guard():
+            check(self.lib.flock_obs_window(self._h, self._obs_window.data_ptr(), self._stream()))
+        return self._obs_window
+
+    @property
+    def obs_handle(self) -> ObsRing:
+        """The observation ring (uw, obs_layout="ring") for consumers that read it in place."""
+        if not self.obs_ring:
+            raise RuntimeError("VecEnv was not built with obs_layout='ring'")
+        return self._ring
 
     def _stream(self) -> int:
         # raw handle of torch's current stream on our device (follows stream contexts and graph capture)
@@ -215,7 +272,10 @@ class VecEnv:
 
     @property
     def distances_to_nearest_neighbors(self) -> torch.Tensor:
-        return self._obs[:, :, 0, :]
+        if self.obs_ring:    # the newest row = the head slot of every env's ring
+            E = self.num_envs
+            return self._ring.ring[torch.arange(E, device=self.device), self._obs_head.long()]
+        return self._obs_buf[:, :, 0, :]
 
     @property
     def collisions(self) -> torch.Tensor:
@@ -224,8 +284,8 @@ class VecEnv:
 
     @property
     def observation(self) -> torch.Tensor:
-        """(E, N, k) for v2 / uwd, (E, N, 4, k) newest first for uw."""
-        return self._obs if self.obs_hist > 1 else self._obs[:, :, 0, :]
+        """(E, N, k) for v2 / uwd, (E, N, 4, k) newest first for uw (materialised on request in the ring layout)."""
+        return self._obs if self.obs_hist > 1 else self._obs_buf[:, :, 0, :]
 
     @property
     def reward(self) -> torch.Tensor:
@@ -280,7 +340,8 @@ class VecEnv:
         """Batched `step(action, dt)`: actions (E, N, 2) [v2, uw] or (E, N) float ids [uwd].
 
         Returns `(obs, reward (E,N,1), (agent_done (E,N) bool, env_done (E,) bool), {})`; all are
-        views of env-owned device tensors."""
+        views of env-owned device tensors. With `obs_layout="ring"` (uw) `obs` is the `ObsRing` handle, which
+        the fused actor kernel and the replay writer consume in place; `observation` materialises the window."""
         a = self._as_input(actions, self._act_shape, "actions")
         nz = None if noise is None else self._as_input(noise, torch.Size((self.num_envs, self.num_particles, 2)), "noise")
         with self._dev_guard():
@@ -295,6 +356,50 @@ class VecEnv:
         with self._dev_guard():
             check(self.lib.flock_step_n(self._h, int(num_steps), float(dt), self._stream()))
         return self.observation, self._reward, (self._agent_done, self._env_done), {}
+
+    def alloc_trajectory(self, num_steps: int, with_neighbors: bool = False) -> Trajectory:
+        """Time-major buffers for `rollout_n` (obs | reward | agent_done | env_done of every step)."""
+        T, E, N, k = int(num_steps), self.num_envs, self.num_particles, self.k
+        dev = self.device
+        return Trajectory(torch.zeros(T, E, N, k, device=dev), torch.zeros(T, E, N, 1, device=dev),
+                          torch.zeros(T, E, N, dtype=torch.bool, device=dev), torch.zeros(T, E, dtype=torch.bool, device=dev),
+                          torch.zeros(T, E, N, k, dtype=torch.int32, device=dev) if with_neighbors else None)
+
+    def rollout_bytes_per_agent_step(self, with_actions: bool = True) -> int:
+        """Algorithmic HBM bytes of one agent-step inside `rollout_n`: that step's action in, its range row, reward and
+        done flag out (the state never leaves the registers)."""
+        aw = 4 if self.variant == "uwd" else 8
+        return (aw if with_actions else 0) + 4 * self.k + 4 + 1
+
+    def rollout_n(self, actions: Optional[torch.Tensor], out: Trajectory, dt: float = 0.1) -> Trajectory:
+        """Streamed rollout (flock_rollout_n): `T = out.obs.shape[0]` steps in ONE kernel launch (N <= 32), the state in
+        registers; step t reads `actions[t]` (`(T, E, N, 2)`, or `(T, E, N)` ids for uwd; None = the canonical Philox
+        random actions) and writes slice t of `out`. With `auto_reset=True` finished envs restart inside the kernel as
+        they would between `step()` calls. Bit-identical to T calls of `step()`; afterwards the env holds the state and
+        the outputs of the last step. The buffers of a `replay.DeviceReplay` can be passed as `out` (zero copy)."""
+        T = out.obs.shape[0]
+        E, N, k = self.num_envs, self.num_particles, self.k
+        if (out.obs.shape != (T, E, N, k) or out.reward.numel() != T * E * N or out.agent_done.shape != (T, E, N)
+                or out.env_done.shape != (T, E)):
+            raise ValueError("trajectory buffers do not match (T, E, N, k)")
+        for t_ in (out.obs, out.reward, out.agent_done, out.env_done):
+            if not t_.is_contiguous() or t_.device != self.device:
+                raise ValueError("trajectory buffers must be contiguous tensors on the env's device")
+        if out.obs.dtype != torch.float32 or out.reward.dtype != torch.float32 or out.agent_done.element_size() != 1:
+            raise ValueError("trajectory dtypes: obs / reward float32, dones bool or uint8")
+        a_ptr = None
+        if actions is not None:
+            a = self._as_input(actions, torch.Size((T,) + tuple(self._act_shape)), "actions")
+            a_ptr = a.data_ptr()
+        nn_ptr = None
+        if out.nn is not None:
+            if out.nn.shape != (T, E, N, k) or out.nn.dtype != torch.int32 or not out.nn.is_contiguous():
+                raise ValueError("trajectory nn must be a contiguous int32 (T, E, N, k) tensor")
+            nn_ptr = out.nn.data_ptr()
+        with self._dev_guard():
+            check(self.lib.flock_rollout_n(self._h, T, a_ptr, float(dt), out.obs.data_ptr(), out.reward.data_ptr(),
+                                           out.agent_done.data_ptr(), out.env_done.data_ptr(), nn_ptr, self._stream()))
+        return out
 
     def random_actions(self, step_offset: int = 0) -> torch.Tensor:
         """The canonical random actions `step_n` would apply `step_offset` steps from now."""
@@ -382,7 +487,12 @@ class VecEnv:
         if "prev_headings" in state:
             self._prev_h.copy_(state["prev_headings"])
         if "obs" in state:
-            self._obs.copy_(state["obs"].reshape(self._obs.shape))
+            win = state["obs"].reshape(self._obs_buf.shape)                       # (E, N, H, k) newest first
+            if self.obs_ring:                                                      # ring with head 0: slot r = row r
+                self._ring.ring.copy_(win.permute(0, 2, 1, 3))
+                self._obs_head.zero_()
+            else:
+                self._obs_buf.copy_(win)
         for key, buf in (("reset_epoch", self._reset_epoch), ("ep_len", self._ep_len),
                          ("ep_return_fx", self._ep_return_fx), ("stats", self._stats)):
             if key in state:
