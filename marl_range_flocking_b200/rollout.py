@@ -32,17 +32,21 @@ def collect(env: VecEnv, policy: Policy, num_steps: int, max_episode_steps: int 
       gets `time_limit_bonus` added to every agent's reward (`main.py:38-40`) and is restarted, as is
       any env whose step ended with a collision (`done[1]`).
     * `sink`, if given, receives one dict per step with device tensors `obs`, `actions`, `reward`,
-      `next_obs`, `agent_done`, `episode_end` -- the batched form of `replay_buffer.add_record`
+      `next_obs`, `agent_done`, `env_done` (collision, the VDN terminal flag of vdn/train_flock.py:101),
+      `episode_end` (collision or time limit) -- the batched form of `replay_buffer.add_record`
       (`learners/maddpg_official_rnn/memory_rnn.py:53-67`). Tensors are views that the next step
       overwrites: a sink must copy what it keeps (e.g. one `index_copy_` into a replay tensor).
     """
     if env.auto_reset:
         raise ValueError("collect() drives the resets itself; build the VecEnv with auto_reset=False")
     obs = env.reset() if reset_first else env.observation
+    if hasattr(obs, "window"):            # uw ring layout: this Python loop works on the materialised window
+        obs = env.observation
     for _ in range(int(num_steps)):
         prev_obs = obs.clone() if sink is not None else None
         actions = policy(obs)
-        obs, reward, (agent_done, env_done), _ = env.step(actions, dt)
+        _, reward, (agent_done, env_done), _ = env.step(actions, dt)
+        obs = env.observation
         timed_out = (env._ep_len >= max_episode_steps) & ~env_done
         if time_limit_bonus:
             reward += timed_out.to(reward.dtype)[:, None, None] * time_limit_bonus
@@ -54,7 +58,7 @@ def collect(env: VecEnv, policy: Policy, num_steps: int, max_episode_steps: int 
         env.reset(mask=episode_end, keep_outputs=True)       # obs of restarted envs = first obs of the new episode
         if sink is not None:
             sink(dict(obs=prev_obs, actions=actions, reward=reward, next_obs=terminal_obs, agent_done=agent_done,
-                      episode_end=episode_end))
+                      env_done=env_done, episode_end=episode_end))
         obs = env.observation
     return env.stats()
 

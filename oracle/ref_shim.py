@@ -97,6 +97,19 @@ def _install_stubs() -> None:
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
+        # the learner networks finish their constructors with self.to(cuda device)
+        # (learners/maddpg_shared_critic/ddpg_network.py:128-130): a no-op on a CPU-only machine
+        if not getattr(torch.nn.Module.to, "_flock_shim", False):
+            _orig_to = torch.nn.Module.to
+
+            def _to(self, *a, **k):
+                dev = a[0] if a else k.get("device")
+                if isinstance(dev, (str, torch.device)) and torch.device(dev).type == "cuda":
+                    return self
+                return _orig_to(self, *a, **k)
+
+            _to._flock_shim = True
+            torch.nn.Module.to = _to
 
 
 _loaded: dict = {}
@@ -126,6 +139,45 @@ def load_reference(variant: str):
         os.chdir(cwd)
     _loaded[variant] = mod
     return mod
+
+
+def load_learner_module(relpath: str):
+    """Load a learner module of the reference tree by path relative to its root, e.g.
+    "learners/vdn/net.py" (test infrastructure: pins policies.py / replay.py to the reference's own classes).
+    Only possible where the source tree exists (the build container)."""
+    key = "learner:" + relpath
+    if key in _loaded:
+        return _loaded[key]
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
+    _install_stubs()
+    name = "_flock_reference_" + relpath.replace("/", "_").replace(".py", "")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    cwd = os.getcwd()
+    scratch = tempfile.mkdtemp(prefix="flock_ref_")
+    os.makedirs(os.path.join(scratch, "tmp"), exist_ok=True)   # Actor.__init__ does os.mkdir("tmp\\ddpg") style paths
+    os.chdir(scratch)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        os.chdir(cwd)
+    mod._flock_scratch = scratch
+    _loaded[key] = mod
+    return mod
+
+
+@contextlib.contextmanager
+def scratch_cwd(mod=None):
+    """Run reference constructors that create directories in the cwd from a scratch directory."""
+    cwd = os.getcwd()
+    d = getattr(mod, "_flock_scratch", None) or tempfile.mkdtemp(prefix="flock_ref_")
+    os.chdir(d)
+    try:
+        yield d
+    finally:
+        os.chdir(cwd)
 
 
 class NoiseInjector(contextlib.AbstractContextManager):

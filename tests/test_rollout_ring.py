@@ -213,3 +213,44 @@ def test_rollout_n_full_size_properties():
     assert torch.equal(traj.obs[-1], a.observation)
     d = traj.obs
     assert bool((d[..., 1:] >= d[..., :-1]).all()) and bool((d >= 0).all()) and bool((d <= 14.0).all())
+
+
+def test_rollout_n_writes_straight_into_the_replay_and_the_uw_windows_come_back():
+    """flock_rollout_n -> TrajectoryReplay, zero copy: the kernel's time-major range rows ARE the replay storage; the
+    (4, k) uw windows a learner samples are rebuilt from the row stream and must equal what a window-layout twin env
+    showed step by step (auto-reset restarts included)."""
+    from marl_range_flocking_b200 import VecEnv
+    from marl_range_flocking_b200.replay import TrajectoryReplay
+    E, N, k, T = 48, 8, 3, 20
+    mk = lambda layout: VecEnv("uw", E, N, k, 2.0, range_start=(0, 25), sensor_range=7.0, seed=12, auto_reset=True,
+                               max_reset_attempts=8, reset_collision_distance=2.0, obs_layout=layout)
+    env, twin = mk("ring"), mk("window")
+    env.reset()
+    twin.reset()
+    rp = TrajectoryReplay(E, N, k, 2, capacity_steps=2 * T, device="cuda", chunk_size=5, window=4)
+    before, after, term = [], [], []
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for chunk in range(2):
+        acts = torch.rand(T, E, N, 2, device="cuda", generator=gen) * 2 - 1
+        rp.begin(env.distances_to_nearest_neighbors)
+        views = rp.next_views(T)
+        assert views.obs.data_ptr() == rp.rows[chunk * T + 1].data_ptr()          # zero copy: views of the storage
+        env.rollout_n(acts, views, 0.1)
+        rp.commit(T, acts)
+        for t in range(T):
+            before.append(twin.observation.clone())
+            twin.step(acts[t], 0.1)
+            after.append(twin.observation.clone())
+            term.append(twin.dones[1].clone())
+    torch.cuda.synchronize()
+    assert int(torch.stack(term).sum()) > 0                                       # episodes did end inside the rollouts
+    starts = torch.tensor([0, 7, 16, 23, 35]).cuda()
+    envs = torch.tensor([0, 5, 17, 30, 47]).cuda()
+    s, a, r, s2, d = rp.sample_chunk(5, 5, starts=starts, envs=envs)
+    for b in range(5):
+        for c in range(5):
+            t, e = int(starts[b]) + c, int(envs[b])
+            assert torch.equal(s[b, c], before[t][e].reshape(N, 4 * k)), (b, c)
+            assert torch.equal(s2[b, c], after[t][e].reshape(N, 4 * k)), (b, c)
+            assert float(d[b, c, 0]) == float(term[t][e])
+    assert torch.equal(env.observation, twin.observation)
