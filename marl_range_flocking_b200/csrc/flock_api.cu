@@ -43,6 +43,7 @@ struct flock_env {
     float* stage_noise;
     float* stage_window;   // uw ring layout: materialised window for the host-call path (allocated on first use)
     unsigned int* tile_scratch;   // tiled path: per-env arrival / collision counters
+    uint8_t* reset_need;          // tiled path: per-env "still colliding" flags of the multi-CTA reset
     int* tile_perm;               // tiled thread-per-row path: spatially sorted row order [E][N]
     int* tile_inv;                // its inverse (agent -> slot)
     float* sorted_xy;             // pruned path: per-env staging record (positions by slot, boxes, ids)
@@ -146,8 +147,10 @@ int reset_device(flock_env* e, const uint8_t* env_mask, const float* init_state,
     p.reset_flags = flags;
     // reset installs the state into the CURRENT copy
     p.xo = const_cast<float*>(p.x); p.yo = const_cast<float*>(p.y); p.ho = const_cast<float*>(p.h);
-    cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s) : flock::launch_reset_tiled(p, s);
-    e->launches += 1;
+    int n_launch = 1;
+    cudaError_t err = e->path == 0 ? flock::launch_reset_small(p, e->sm_count, s)
+                                   : flock::launch_reset_tiled(p, e->reset_need, &n_launch, s);
+    e->launches += (uint64_t)n_launch;
     if (err != cudaSuccess) return cuda_fail(err, "reset kernel launch");
     if (env_mask == nullptr) e->perm_age = 0; // every env was redrawn: refresh the row order at the next step
     if (e->cfg.range_noise_std > 0.0f) {
@@ -320,6 +323,8 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
     if (err == cudaSuccess && e->path == 1) {
         err = cudaMalloc(&e->tile_scratch, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
         if (err == cudaSuccess) err = cudaMemset(e->tile_scratch, 0, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
+        if (err == cudaSuccess) err = cudaMalloc(&e->reset_need, (size_t)cfg->num_envs);
+        if (err == cudaSuccess) err = cudaMemset(e->reset_need, 0, (size_t)cfg->num_envs);
         if (err == cudaSuccess) err = cudaMalloc(&e->tile_perm, (size_t)cfg->num_envs * cfg->num_agents * sizeof(int));
         if (err == cudaSuccess) err = cudaMalloc(&e->tile_inv, (size_t)cfg->num_envs * cfg->num_agents * sizeof(int));
         if (err == cudaSuccess)
@@ -333,6 +338,7 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
     }
     if (err != cudaSuccess) {
         cudaFree(e->tile_scratch);
+        cudaFree(e->reset_need);
         cudaFree(e->tile_perm);
         cudaFree(e->tile_inv);
         cudaFree(e->sorted_xy);
@@ -353,6 +359,7 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->stage_noise);
     cudaFree(e->stage_window);
     cudaFree(e->tile_scratch);
+    cudaFree(e->reset_need);
     cudaFree(e->tile_perm);
     cudaFree(e->tile_inv);
     cudaFree(e->sorted_xy);

@@ -55,6 +55,7 @@ struct Params {
     int32_t* ep_len;
     unsigned long long* stats;
     unsigned int* tile_scratch;   // tiled path: [E] CTA arrival counters, [E] collision counters (self-resetting)
+    uint8_t* reset_need;          // tiled reset: [E] envs that still collide after the attempt launches so far
     const int* perm;              // tiled thread-per-row path: [E][N] row order (spatially sorted), nullable = identity
     unsigned long long* pair_counter;   // pruned kernel: row x neighbour pairs actually evaluated (nullable)
     const int* inv;               // inverse of perm (agent -> slot)

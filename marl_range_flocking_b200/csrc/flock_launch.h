@@ -57,7 +57,7 @@ cudaError_t launch_debug_philox(const uint32_t* ck, int n, uint32_t* out, cudaSt
 cudaError_t tiled_configure(int num_agents);   // opt in to the dynamic shared memory the env needs
 size_t tiled_smem_bytes(int num_agents, int rows, bool need_sh);
 cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int sm_count, int tiled_mode, cudaStream_t s);
-cudaError_t launch_reset_tiled(const Params& p, cudaStream_t s);
+cudaError_t launch_reset_tiled(const Params& p, uint8_t* need, int* launches, cudaStream_t s);   // need: [E] device scratch
 cudaError_t launch_perm_refresh(const Params& p, int* perm, int* inv, cudaStream_t s);   // spatial row order
 size_t pruned_scratch_floats(int N, int E);
 size_t pruned_hint_bytes(int N, int E);

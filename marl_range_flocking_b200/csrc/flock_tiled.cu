@@ -945,9 +945,12 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(con
     }
 }
 
-// reset, grid = E, one CTA per env, bounded rejection loop (gym_flock_v2.py:85-108)
+// reset, grid = E, one CTA per env, bounded rejection loop (gym_flock_v2.py:85-108). The CTA is as wide as the
+// hardware allows (1024 threads, one row each per pass): a restart is a latency problem -- typically one env of a
+// batch restarts while the rest of the GPU waits for the stream -- so the env's rows are spread over 32 warps.
+constexpr int kResetThreads = 1024;
 template <int K>
-__global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kResetThreads) flock_reset_tiled_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, k = p.k;
     const int env = blockIdx.x;
@@ -957,7 +960,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(cons
     const size_t EN = (size_t)p.E * N;
     const uint32_t epoch = p.reset_epoch[env];
     const int max_att = p.init_state != nullptr ? 1 : p.max_attempts;
-    int attempts = 0;
+    int attempts = (int)p.step_offset;   // > 0: continues where the multi-CTA attempt launches stopped (env_mask = their need flags)
     int env_coll = 1;
     const bool keep = (p.reset_flags & FLOCK_RESET_KEEP_OUTPUTS) != 0;
     if (threadIdx.x < padded_agents(N) - N) {
@@ -1024,6 +1027,144 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_reset_tiled_kernel(cons
         for (int t = threadIdx.x; t < PS; t += blockDim.x) hs[t] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     if (threadIdx.x == 0) {
+        if (!keep) p.env_done[env] = env_coll ? 1 : 0;
+        if (p.init_state == nullptr) p.reset_epoch[env] = epoch + (uint32_t)attempts;
+        const int len = p.ep_len[env];
+        if (p.stats != nullptr) {
+            if (len > 0) {
+                atomicAdd(&p.stats[FLOCK_STAT_EPISODES], 1ULL);
+                atomicAdd(&p.stats[FLOCK_STAT_EP_STEPS], (unsigned long long)len);
+                if (p.ep_return_fx != nullptr)
+                    atomicAdd(&p.stats[FLOCK_STAT_EP_RETURN_FX], (unsigned long long)p.ep_return_fx[env]);
+            }
+            if (p.init_state == nullptr) {
+                atomicAdd(&p.stats[FLOCK_STAT_RESET_ATTEMPTS], (unsigned long long)attempts);
+                if (env_coll) atomicAdd(&p.stats[FLOCK_STAT_RESET_GAVE_UP], 1ULL);
+            }
+        }
+        p.ep_len[env] = 0;
+        if (p.ep_return_fx != nullptr) p.ep_return_fx[env] = 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Large-swarm reset, one rejection attempt per launch, grid = (tiles, E): the env's rows are spread over several
+// CTAs (one CTA per env does 2048^2 pairs on ONE SM: 315 us for a single restarting env of 2048 agents).
+// Attempt `p.step_offset` of this flock_reset call: every CTA of an active env re-draws the WHOLE env into shared
+// memory (N / rows Philox draws per thread -- cheap next to N pairs per row, and no inter-CTA dependency), senses
+// its own rows, and the last CTA of the env to finish (arrival counter, as in the step kernels) decides: collision
+// free (or out of attempts) -> close the episode counters exactly as flock_reset_tiled_kernel does; otherwise
+// p.reset_need[env] stays set and the next attempt launch (or the single-CTA loop kernel, which continues at
+// attempt `step_offset` for the rare env that needs more than kFastResetAttempts) re-draws it.
+// Same draws, same arithmetic, same outputs as the single-CTA kernel (gym_flock_v2.py:85-108).
+template <int K>
+__global__ void __launch_bounds__(kMaxTileThreads) flock_reset_attempt_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_last;
+    const int N = p.N, k = p.k;
+    const int env = blockIdx.y;
+    const int attempt = (int)p.step_offset;
+    const bool active = attempt == 0 ? (p.env_mask == nullptr || p.env_mask[env] != 0) : (p.reset_need[env] != 0);
+    if (!active) {
+        if (attempt == 0 && blockIdx.x == 0 && threadIdx.x == 0) p.reset_need[env] = 0;
+        return;
+    }
+    const TileSmem sm = carve(smem, N, false);
+    const size_t base = (size_t)env * N;
+    const size_t EN = (size_t)p.E * N;
+    const uint32_t epoch = p.reset_epoch[env];
+    const int max_att = p.init_state != nullptr ? 1 : p.max_attempts;
+    const bool keep = (p.reset_flags & FLOCK_RESET_KEEP_OUTPUTS) != 0;
+    const int row0 = blockIdx.x * blockDim.x;
+    if (threadIdx.x < padded_agents(N) - N) {
+        sm.sx[N + threadIdx.x] = kInf;
+        sm.sy[N + threadIdx.x] = 0.0f;
+    }
+    for (int a = threadIdx.x; a < N; a += blockDim.x) {
+        float x, y, h;
+        if (p.init_state != nullptr) {
+            x = p.init_state[base + a];
+            y = p.init_state[EN + base + a];
+            h = p.init_state[2 * EN + base + a];
+        } else {
+            const uint4 r = philox4x32_10((uint32_t)(p.env_offset + env), (uint32_t)a, epoch + (uint32_t)attempt, kTagReset,
+                                          p.seed_lo, p.seed_hi);
+            const float span = p.range_lo - p.reset_hi;
+            const float tx = span * u24(r.x);
+            x = tx + p.reset_hi;
+            const float ty = span * u24(r.y);
+            y = ty + p.reset_hi;
+            const float th = (0.0f - p.heading_hi) * u24(r.z);
+            h = th + p.heading_hi;
+        }
+        x = wrap_coord(x, p.B, p.fill_hi, p.fill_lo);
+        y = wrap_coord(y, p.B, p.fill_hi, p.fill_lo);
+        sm.sx[a] = x;
+        sm.sy[a] = y;
+        if (a >= row0 && a < row0 + (int)blockDim.x) {   // this CTA's rows: install the state
+            p.xo[base + a] = x;
+            p.yo[base + a] = y;
+            p.ho[base + a] = h;
+            p.prev_h[base + a] = 0.0f;
+            if (p.vx != nullptr) {
+                p.vx[base + a] = 0.0f;
+                p.vy[base + a] = 0.0f;
+            }
+        }
+    }
+    __syncthreads();
+    const int i = row0 + threadIdx.x;
+    const bool has_row = i < N;
+    TopK<K> t;
+    const float x = sm.sx[has_row ? i : 0], y = sm.sy[has_row ? i : 0];
+    knn_tiled<K, false>(sm.sx, sm.sy, sm.cand + threadIdx.x, i, N, x, y, p.B, has_row ? kFltMax : -1.0f, t);
+    bool coll = false;
+    if (has_row) {
+        float dist[K];
+        coll = finish_row<K>(t, k, p.sensor_range, p.reset_cd, dist);
+        const size_t idx = base + i;
+        write_obs_t<K>(p, env, i, idx, dist, true);
+        if (p.nn != nullptr) store_row_t<int, K>(p.nn + idx * k, t.idx, k);
+        if (!keep) {
+            p.reward[idx] = 0.0f;
+            p.agent_done[idx] = coll ? 1 : 0;
+        }
+    }
+    const int cta_coll = __syncthreads_or(coll ? 1 : 0);
+    unsigned int* arrive = p.tile_scratch + env;
+    unsigned int* collide = p.tile_scratch + p.E + env;
+    if (threadIdx.x == 0) {
+        if (cta_coll) atomicAdd(collide, 1u);
+        __threadfence();
+        const unsigned prev = atomicAdd(arrive, 1u);
+        s_last = prev == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last CTA of the env for this attempt
+    __threadfence();
+    int env_coll = 0, again = 0;
+    if (threadIdx.x == 0) {
+        env_coll = atomicExch(collide, 0u) != 0u ? 1 : 0;
+        *arrive = 0u;
+        again = env_coll && attempt + 1 < max_att;
+        s_last = again ? 2 : (env_coll ? 3 : 1);
+    }
+    __syncthreads();
+    again = s_last == 2;
+    env_coll = s_last >= 2;
+    if (again) {
+        if (threadIdx.x == 0) p.reset_need[env] = 1;
+        return;
+    }
+    if (p.hint_slots != nullptr) {   // the pruned kernel's slot hints describe the old episode: drop them
+        const int PS = ((N + 31) / 32) * 32;
+        uint4* hs = reinterpret_cast<uint4*>(p.hint_slots) + (size_t)env * PS;
+        for (int tt = threadIdx.x; tt < PS; tt += blockDim.x) hs[tt] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    if (threadIdx.x == 0) {
+        const int attempts = attempt + 1;
+        p.reset_need[env] = 0;
         if (!keep) p.env_done[env] = env_coll ? 1 : 0;
         if (p.init_state == nullptr) p.reset_epoch[env] = epoch + (uint32_t)attempts;
         const int len = p.ep_len[env];
@@ -1130,12 +1271,39 @@ cudaError_t launch_step_tiled(int variant, bool periodic, const Params& p, int s
     }
 }
 
-cudaError_t launch_reset_tiled(const Params& p, cudaStream_t s) {
-    const int rows = kMaxTileThreads;
-    const size_t smem = tiled_smem_bytes(p.N, rows, true);
-    if (p.k <= 3) flock_reset_tiled_kernel<3><<<p.E, rows, smem, s>>>(p);
-    else if (p.k == 4) flock_reset_tiled_kernel<4><<<p.E, rows, smem, s>>>(p);
-    else flock_reset_tiled_kernel<8><<<p.E, rows, smem, s>>>(p);
+// Large-swarm reset = up to kFastResetAttempts multi-CTA attempt launches (the common case: a sparse world accepts the
+// first draw) + the single-CTA loop kernel for the envs that still collide and have attempts left.
+constexpr int kFastResetAttempts = 2;
+cudaError_t launch_reset_tiled(const Params& p, uint8_t* need, int* launches, cudaStream_t s) {
+    const int max_att = p.init_state != nullptr ? 1 : p.max_attempts;
+    const int fast = need == nullptr ? 0 : (max_att < kFastResetAttempts ? max_att : kFastResetAttempts);
+    int rows = (p.N + 31) & ~31;
+    if (rows > kMaxTileThreads) rows = kMaxTileThreads;
+    const dim3 grid((p.N + rows - 1) / rows, p.E);
+    const size_t smem_a = tiled_smem_bytes(p.N, rows, false);
+    *launches = 0;
+    for (int a = 0; a < fast; ++a) {
+        Params q = p;
+        q.step_offset = (uint32_t)a;
+        q.reset_need = need;
+        if (p.k <= 3) flock_reset_attempt_kernel<3><<<grid, rows, smem_a, s>>>(q);
+        else if (p.k == 4) flock_reset_attempt_kernel<4><<<grid, rows, smem_a, s>>>(q);
+        else flock_reset_attempt_kernel<8><<<grid, rows, smem_a, s>>>(q);
+        *launches += 1;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (max_att <= fast) return cudaSuccess;
+    Params q = p;
+    q.step_offset = (uint32_t)fast;
+    if (fast > 0) q.env_mask = need;      // only the envs the attempt launches left colliding
+    int rows1 = (p.N + 31) & ~31;
+    if (rows1 > kResetThreads) rows1 = kResetThreads;
+    const size_t smem = tiled_smem_bytes(p.N, rows1, true);
+    if (p.k <= 3) flock_reset_tiled_kernel<3><<<p.E, rows1, smem, s>>>(q);
+    else if (p.k == 4) flock_reset_tiled_kernel<4><<<p.E, rows1, smem, s>>>(q);
+    else flock_reset_tiled_kernel<8><<<p.E, rows1, smem, s>>>(q);
+    *launches += 1;
     return cudaGetLastError();
 }
 
@@ -1177,9 +1345,13 @@ cudaError_t tiled_configure(int /*num_agents*/) {
     FLOCK_OPT_RW(FLOCK_V2, 8, false) FLOCK_OPT_RW(FLOCK_UW, 4, false) FLOCK_OPT_RW(FLOCK_UW, 8, false)
     FLOCK_OPT_RW(FLOCK_UWD, 4, false) FLOCK_OPT_RW(FLOCK_UWD, 8, false)
 #undef FLOCK_OPT_RW
-    if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<3>, b);
-    if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<4>, b);
-    if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<8>, b);
+    if (e == cudaSuccess) e = opt_in(flock_reset_attempt_kernel<3>, b);
+    if (e == cudaSuccess) e = opt_in(flock_reset_attempt_kernel<4>, b);
+    if (e == cudaSuccess) e = opt_in(flock_reset_attempt_kernel<8>, b);
+    const size_t br2 = tiled_smem_bytes(num_agents, kResetThreads, true);
+    if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<3>, br2);
+    if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<4>, br2);
+    if (e == cudaSuccess) e = opt_in(flock_reset_tiled_kernel<8>, br2);
     return e;
 }
 

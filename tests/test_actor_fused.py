@@ -210,3 +210,33 @@ def test_graphed_rollout_with_fused_ou_noise_draws_fresh_normals_every_replay():
     frozen = run(mk(), z(), torch.empty(E, N, 2, device=dev), False, True)
     live = frozen[0] != 0                                          # (c) host step only: identical draws every launch
     assert torch.allclose((frozen[1] - frozen[0])[live], frozen[0][live], rtol=1e-4, atol=1e-6)
+
+
+def test_bf16_actor_leaves_the_closed_loop_episode_statistics_unchanged():
+    """The fused actor rounds its MLP operands to bf16 (<= 4e-2 on a tanh output, 1.6e-2 typical). Closed loop, that
+    must not change what a learner sees in aggregate: the same policy run in fp32 PyTorch and through the fused kernel
+    on twin envs gives the same episode statistics (thousands of episodes; individual trajectories do diverge)."""
+    from marl_range_flocking_b200 import VecEnv
+    dev = torch.device("cuda:0")
+    E, N, k, T = 2048, 8, 3, 160
+    mk = lambda: VecEnv("uw", E, N, k, 1.5, range_start=(0, 30), sensor_range=7.0, seed=77, device="cuda:0", auto_reset=True,
+                        max_reset_attempts=16, reset_collision_distance=1.5)
+    actors = _actors(N, 4 * k, 21, dev)
+    stats = []
+    for fused in (False, True):
+        env = mk()
+        env.reset()
+        buf = torch.empty(E, N, 2, device=dev)
+        rew = torch.zeros((), device=dev, dtype=torch.float64)
+        with torch.no_grad():
+            for t in range(T):
+                a = actors.forward_fused(env.observation, out=buf) if fused else actors(env.observation)
+                _, r, _, _ = env.step(a, 0.1)
+                rew += r.double().sum()
+        torch.cuda.synchronize()
+        s = env.stats()
+        stats.append((s["episodes"], s["mean_episode_length"], s["mean_episode_return"], float(rew) / (E * N * T)))
+    (e0, l0, r0, m0), (e1, l1, r1, m1) = stats
+    assert e0 > 2000 and e1 > 2000
+    assert abs(e1 - e0) / e0 < 0.05 and abs(l1 - l0) / l0 < 0.05, stats
+    assert abs(r1 - r0) <= 0.05 * abs(r0) + 0.05 and abs(m1 - m0) <= 0.05 * abs(m0) + 1e-3, stats

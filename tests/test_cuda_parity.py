@@ -255,7 +255,8 @@ def test_step_host_matches_device_path():
                                              ("v2", 97, 7, 3, 15), ("v2", 6, 64, 4, 60)])
 def test_auto_reset_resets_exactly_the_done_envs(variant, E, N, k, B):
     """auto_reset: step + restart of the finished envs (one fused launch for N <= 32; integrate
-    pre-pass, sensing kernel and a follow-up masked reset for N > 32) == oracle step followed by reset(mask = env_done, keep_outputs)."""
+    pre-pass, sensing kernel and a follow-up masked multi-CTA reset for N > 32) == oracle step followed by
+    reset(mask = env_done, keep_outputs)."""
     env, orc = make_pair(variant, E, N, k, 2.5, (0, B), 14.0, auto_reset=True, reset_collision_distance=2.5,
                          max_reset_attempts=16)
     env.reset()
@@ -271,8 +272,8 @@ def test_auto_reset_resets_exactly_the_done_envs(variant, E, N, k, B):
     launches = env.launch_count - launches0
     if N <= 32:
         assert launches == T                     # fused: one kernel per step
-    else:                                         # integrate pre-pass + sensing kernel + masked reset (+ row-order refreshes)
-        assert 3 * T <= launches <= 3 * T + T // 16 + 1
+    else:    # integrate pre-pass + sensing kernel + masked reset (two multi-CTA attempts + the loop kernel) (+ row-order refreshes)
+        assert 5 * T <= launches <= 5 * T + T // 16 + 1
     s = env.stats()
     assert s["episodes"] == int(orc.stats[0]) and s["episodes"] > 0
     # host-buffer path with auto-reset: the host sees the restarted envs' first observation too
@@ -851,3 +852,26 @@ def test_graphed_rollout_is_identical_to_the_python_loop(variant, N, k):
         ta, tb = getattr(a, name), getattr(b, name)
         assert torch.equal(ta, tb), name
     assert stats_a == stats_b and stats_a["episodes"] > 0
+
+
+@pytest.mark.parametrize("variant,N,k,B,cd", [("v2", 300, 8, 60.0, 1.0), ("uw", 96, 3, 40.0, 1.0), ("uwd", 130, 4, 50.0, 1.0)])
+def test_large_swarm_reset_needing_many_attempts_matches_the_oracle(variant, N, k, B, cd):
+    """Dense large-swarm worlds: most envs need several rejection rounds, some more than the two multi-CTA attempt
+    launches (then the single-CTA loop kernel continues at attempt 2), some give up at max_attempts -- draws,
+    attempt counters, Philox epochs and statistics must match the oracle's single loop exactly."""
+    env, orc = make_pair(variant, 12, N, k, cd, (0, B), 9.0, seed=4, reset_collision_distance=cd, max_reset_attempts=5)
+    for rnd in range(3):
+        env.reset()
+        orc.reset(max_attempts=5)
+        compare_all(env, orc, tag=f"reset round {rnd}:")
+        for t in range(3):
+            a = orc.random_actions()
+            orc.step(a, 0.1)
+            env.step(torch.from_numpy(a).cuda(), 0.1)
+        mask = np.zeros(12, np.uint8)
+        mask[rnd::3] = 1
+        orc.reset(mask=mask, max_attempts=5)
+        env.reset(mask=torch.from_numpy(mask).cuda().bool())
+        compare_all(env, orc, tag=f"masked reset round {rnd}:")
+    s = orc.stats
+    assert int(s[3]) > 3 * 12 and int(s[4]) >= 0          # more attempts than resets: the rejection loop really looped
