@@ -322,6 +322,28 @@ FLOCK_API int flock_qnet_forward(const float *const *params, int recurrent, cons
                        int n_actions, float epsilon, uint64_t seed, uint32_t step, int env_offset,
                        const flock_noise_counters_t *counters, void *stream);
 
+/* The recurrent front ends of the two policies above ON THE TENSOR CORES (csrc/flock_gru_tc.cu): every layer is a
+ * tcgen05.mma over tiles of 128 env rows with split bf16 operands (v = hi + lo, four MMAs per product: fp32-level
+ * accuracy, hidden state and Q-values within 1e-5 of the fp32 modules), accumulators in TMEM, activations never leave
+ * the SM. `mode` 0 = recurrent MADDPG actor front (fce + GRUCell, net.py:53-58), 1 = recurrent VDN QNet (net.py:27-58).
+ *   flock_gru_tc_packed_bytes / flock_gru_tc_pack: packed parameter image; `params` as in flock_rnn_actor_forward
+ *     (mode 0: the 6 front pointers) resp. flock_qnet_forward (mode 1: the 10 pointers). Call again after an update.
+ *   flock_qnet_forward_tc: flock_qnet_forward (recurrent) with the packed image: same outputs, same exploration stream.
+ *   flock_rnn_actor_forward_tc: flock_rnn_actor_forward[_ou] with the front end on the tensor cores (two launches:
+ *     front, MLP); ou_state NULL = no exploration noise. */
+FLOCK_API size_t flock_gru_tc_packed_bytes(int mode, int num_agents);
+FLOCK_API int flock_gru_tc_pack(int mode, int num_agents, int n_obs, int n_actions, const float *const *params,
+                                void *packed, void *stream);
+FLOCK_API int flock_qnet_forward_tc(const void *packed, const float *obs, const float *hidden_in, float *q_out,
+                                    float *hidden_out, float *actions, int num_envs, int num_agents, int n_obs,
+                                    int n_actions, float epsilon, uint64_t seed, uint32_t step, int env_offset,
+                                    const flock_noise_counters_t *counters, void *stream);
+FLOCK_API int flock_rnn_actor_forward_tc(const void *packed_mlp, const void *packed_front, const float *obs,
+                                         const float *hidden_in, float *hidden_out, float *actions, int num_envs,
+                                         int num_agents, int n_obs, float *ou_state, float theta, float mu, float sigma,
+                                         float dt, uint64_t seed, uint32_t step, int env_offset,
+                                         const flock_noise_counters_t *counters, void *stream);
+
 /* Debug / test hooks for the canonical arithmetic (device arrays, n elements). */
 FLOCK_API int flock_debug_sincos(const float *h, int n, float *sn, float *cs, void *stream);
 FLOCK_API int flock_debug_normal2(const uint32_t *words, int n_pairs, float *z, void *stream);

@@ -110,6 +110,10 @@ def load_library() -> ctypes.CDLL:
         "flock_rnn_actor_forward_ou": (i32, [vp, ctypes.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32,
                                            u64, u32, i32, vp, vp]),
         "flock_qnet_forward": (i32, [ctypes.POINTER(vp), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u32, i32, vp, vp]),
+        "flock_gru_tc_packed_bytes": (ctypes.c_size_t, [i32, i32]),
+        "flock_gru_tc_pack": (i32, [i32, i32, i32, i32, ctypes.POINTER(vp), vp, vp]),
+        "flock_qnet_forward_tc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, u32, i32, vp, vp]),
+        "flock_rnn_actor_forward_tc": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, f32, f32, f32, f32, u64, u32, i32, vp, vp]),
         "flock_last_error": (ctypes.c_char_p, []),
         "flock_abi_version": (i32, []),
         "flock_debug_sincos": (i32, [vp, i32, vp, vp, vp]),

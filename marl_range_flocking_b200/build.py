@@ -16,8 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libflock_b200.so")
 SOURCES = ["flock_small_v2p.cu", "flock_small_v2e.cu", "flock_small_v2pn.cu", "flock_small_v2en.cu", "flock_small_uw.cu", "flock_small_uwn.cu", "flock_small_uwd.cu",
-           "flock_small_uwdn.cu", "flock_small.cu", "flock_tiled.cu", "flock_actor.cu", "flock_rnn_actor.cu", "flock_qnet.cu", "flock_api.cu"]
-FAST_MATH_OK = {"flock_actor.cu", "flock_rnn_actor.cu", "flock_qnet.cu"}
+           "flock_small_uwdn.cu", "flock_small.cu", "flock_tiled.cu", "flock_actor.cu", "flock_rnn_actor.cu", "flock_qnet.cu", "flock_gru_tc.cu", "flock_api.cu"]
+FAST_MATH_OK = {"flock_actor.cu", "flock_rnn_actor.cu", "flock_qnet.cu", "flock_gru_tc.cu"}
 HEADERS = ["flock_device.cuh", "flock_small_impl.cuh", "flock_launch.h", "flock_tc.cuh", os.path.join("..", "..", "include", "flock_b200.h")]
 
 # -fmad=false: no implicit FMA contraction (canonical arithmetic); explicit fmaf()/fma()

@@ -806,6 +806,69 @@ int flock_qnet_forward(const float* const* params, int recurrent, const float* o
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "qnet kernel launch");
 }
 
+size_t flock_gru_tc_packed_bytes(int mode, int num_agents) {
+    return (num_agents > 0 && (mode == 0 || mode == 1)) ? (size_t)num_agents * flock::gru_tc_blob_bytes(mode) : 0;
+}
+
+int flock_gru_tc_pack(int mode, int num_agents, int n_obs, int n_actions, const float* const* params, void* packed, void* stream) {
+    if (mode != 0 && mode != 1) return fail(FLOCK_E_INVALID, "mode %d not in {0 (recurrent actor front), 1 (VDN QNet)}", mode);
+    if (num_agents < 1 || num_agents > 65535) return fail(FLOCK_E_INVALID, "num_agents %d not in [1, 65535]", num_agents);
+    if (n_obs < 1 || n_obs > flock::gru_tc_max_obs()) return fail(FLOCK_E_INVALID, "n_obs %d not in [1, %d]", n_obs, flock::gru_tc_max_obs());
+    if (mode == 1 && (n_actions < 1 || n_actions > flock::gru_tc_max_actions()))
+        return fail(FLOCK_E_INVALID, "n_actions %d not in [1, %d]", n_actions, flock::gru_tc_max_actions());
+    if (params == nullptr || packed == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    for (int i = 0; i < (mode == 1 ? 10 : 6); ++i)
+        if (params[i] == nullptr) return fail(FLOCK_E_INVALID, "parameter %d is NULL", i);
+    if (reinterpret_cast<uintptr_t>(packed) & 15u) return fail(FLOCK_E_INVALID, "packed must be 16-byte aligned");
+    cudaError_t err = flock::launch_gru_tc_pack(mode, num_agents, n_obs, n_actions, params, packed, static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "gru pack kernel launch");
+}
+
+static int gru_tc_check(const void* packed, const float* obs, const float* hidden_in, const float* hidden_out, int num_envs,
+                        int num_agents, int n_obs) {
+    if (packed == nullptr || obs == nullptr || hidden_in == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    if (num_envs < 1 || num_agents < 1 || num_agents > 65535) return fail(FLOCK_E_INVALID, "bad num_envs / num_agents");
+    if (n_obs < 1 || n_obs > flock::gru_tc_max_obs()) return fail(FLOCK_E_INVALID, "n_obs %d not in [1, %d]", n_obs, flock::gru_tc_max_obs());
+    if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (reinterpret_cast<uintptr_t>(hidden_in) & 15u) ||
+        (reinterpret_cast<uintptr_t>(hidden_out) & 15u) || (reinterpret_cast<uintptr_t>(obs) & 3u))
+        return fail(FLOCK_E_INVALID, "packed / hidden state buffers must be 16-byte aligned");
+    return FLOCK_OK;
+}
+
+int flock_qnet_forward_tc(const void* packed, const float* obs, const float* hidden_in, float* q_out, float* hidden_out,
+                          float* actions, int num_envs, int num_agents, int n_obs, int n_actions, float epsilon, uint64_t seed,
+                          uint32_t step, int env_offset, const flock_noise_counters_t* counters, void* stream) {
+    int rc = gru_tc_check(packed, obs, hidden_in, hidden_out, num_envs, num_agents, n_obs);
+    if (rc != FLOCK_OK) return rc;
+    if (n_actions < 1 || n_actions > flock::gru_tc_max_actions())
+        return fail(FLOCK_E_INVALID, "n_actions %d not in [1, %d]", n_actions, flock::gru_tc_max_actions());
+    if (!(epsilon >= 0.0f)) return fail(FLOCK_E_INVALID, "epsilon must be >= 0");
+    cudaError_t err = flock::launch_gru_tc_forward(1, packed, obs, hidden_in, hidden_out, q_out, actions, num_envs, num_agents, n_obs,
+                                                   n_actions, epsilon, seed, step, env_offset, noise_counters(counters),
+                                                   static_cast<cudaStream_t>(stream));
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "qnet tensor-core kernel launch");
+}
+
+int flock_rnn_actor_forward_tc(const void* packed_mlp, const void* packed_front, const float* obs, const float* hidden_in,
+                               float* hidden_out, float* actions, int num_envs, int num_agents, int n_obs, float* ou_state,
+                               float theta, float mu, float sigma, float dt, uint64_t seed, uint32_t step, int env_offset,
+                               const flock_noise_counters_t* counters, void* stream) {
+    int rc = gru_tc_check(packed_front, obs, hidden_in, hidden_out, num_envs, num_agents, n_obs);
+    if (rc != FLOCK_OK) return rc;
+    if (packed_mlp == nullptr || hidden_out == nullptr || actions == nullptr) return fail(FLOCK_E_INVALID, "null argument");
+    if ((reinterpret_cast<uintptr_t>(packed_mlp) & 15u) || (reinterpret_cast<uintptr_t>(actions) & 7u) ||
+        (reinterpret_cast<uintptr_t>(ou_state) & 7u))
+        return fail(FLOCK_E_INVALID, "recurrent actor buffers must be 16-byte aligned");
+    if (ou_state != nullptr && (!(dt >= 0.0f) || !(sigma >= 0.0f))) return fail(FLOCK_E_INVALID, "OU dt and sigma must be >= 0");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t err = flock::launch_gru_tc_forward(0, packed_front, obs, hidden_in, hidden_out, nullptr, nullptr, num_envs, num_agents,
+                                                   n_obs, 0, 0.0f, 0ULL, 0u, 0, flock::NoiseCounters(), s);
+    if (err != cudaSuccess) return cuda_fail(err, "rnn front tensor-core kernel launch");
+    err = flock::launch_rnn_actor_forward(packed_mlp, nullptr, obs, hidden_out, hidden_out, actions, num_envs, num_agents, n_obs,
+                                          ou_state, theta, mu, sigma, dt, seed, step, env_offset, noise_counters(counters), s);
+    return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor MLP kernel launch");
+}
+
 int flock_debug_sincos(const float* h, int n, float* sn, float* cs, void* stream) {
     cudaError_t err = flock::launch_debug_sincos(h, n, sn, cs, static_cast<cudaStream_t>(stream));
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "debug_sincos");

@@ -90,4 +90,13 @@ cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* fron
                                      float* hidden_out, float* actions, int E, int N, int n_obs, float* ou_state,
                                      float ou_theta, float ou_mu, float ou_sigma, float ou_dt, uint64_t seed, uint32_t step,
                                      int env_offset, NoiseCounters ctr, cudaStream_t s);
+
+// flock_gru_tc.cu (the recurrent front ends on the tensor cores: mode 0 = recurrent MADDPG actor front, 1 = VDN QNet)
+size_t gru_tc_blob_bytes(int mode);
+int gru_tc_max_obs();
+int gru_tc_max_actions();
+cudaError_t launch_gru_tc_pack(int mode, int agents, int n_obs, int n_act, const float* const* params, void* blobs, cudaStream_t s);
+cudaError_t launch_gru_tc_forward(int mode, const void* blobs, const float* obs, const float* hidden_in, float* hidden_out,
+                                  float* q_out, float* actions, int E, int A, int n_obs, int n_act, float epsilon, uint64_t seed,
+                                  uint32_t step, int env_offset, NoiseCounters ctr, cudaStream_t s);
 }  // namespace flock

@@ -539,12 +539,15 @@ cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* fron
     if (configured != cudaSuccess) return configured;
     // launch 1 of 2: fce + GRUCell (fp32); the hidden state may be updated in place (each thread reads its own
     // row before it writes it)
-    rnn::FrontArgs fa{front[0], front[1], front[2], front[3], front[4], front[5], obs, hidden_in, hidden_out, E, N, n_obs};
-    const size_t fbytes = ((size_t)n_obs * rnn::kHid + rnn::kHid + 2 * (rnn::kHid * 3 * rnn::kHid + 3 * rnn::kHid)) * sizeof(float);
-    const dim3 fgrid((unsigned)N, (unsigned)((E + rnn::kFrontThreads - 1) / rnn::kFrontThreads));
-    rnn::flock_rnn_front_kernel<<<fgrid, rnn::kFrontThreads, fbytes, s>>>(fa);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess;
+    if (front != nullptr) {   // nullptr: the caller has already run the front end (flock_gru_tc.cu) into hidden_out
+        rnn::FrontArgs fa{front[0], front[1], front[2], front[3], front[4], front[5], obs, hidden_in, hidden_out, E, N, n_obs};
+        const size_t fbytes = ((size_t)n_obs * rnn::kHid + rnn::kHid + 2 * (rnn::kHid * 3 * rnn::kHid + 3 * rnn::kHid)) * sizeof(float);
+        const dim3 fgrid((unsigned)N, (unsigned)((E + rnn::kFrontThreads - 1) / rnn::kFrontThreads));
+        rnn::flock_rnn_front_kernel<<<fgrid, rnn::kFrontThreads, fbytes, s>>>(fa);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
     // launch 2 of 2: the MLP on the tensor cores, input = the new hidden state
     const int tiles = (E + rnn::kRows - 1) / rnn::kRows;
     const int total = tiles * N;

@@ -209,15 +209,25 @@ class BatchedRnnActors(torch.nn.Module):
         front = [t.detach().float().contiguous() for t in (self.we, self.be, self.w_ih, self.b_ih, self.w_hh, self.b_hh)]
         self._packed, self._packed_srcs = packed, srcs
         self._front, self._front_ptrs = front, (ctypes.c_void_p * 6)(*[t.data_ptr() for t in front])
+        # the same front end for the tensor-core kernel (flock_gru_tc.cu): split-bf16 weight images
+        self._front_packed = None
+        if self.hidden_rnn == 32 and self.input_dims <= 16:
+            fp = torch.empty(lib.flock_gru_tc_packed_bytes(0, self.num_agents), dtype=torch.uint8, device=self.we.device)
+            with torch.cuda.device(self.we.device):
+                _lib.check(lib.flock_gru_tc_pack(0, self.num_agents, self.input_dims, 0, self._front_ptrs, fp.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream))
+            self._front_packed = fp
         return packed
 
     @torch.no_grad()
     def forward_fused(self, obs: torch.Tensor, hidden: torch.Tensor, out: Optional[torch.Tensor] = None,
                       hidden_out: Optional[torch.Tensor] = None, ou_state: Optional[torch.Tensor] = None,
                       ou_theta: float = 0.15, ou_mu: float = 0.0, ou_sigma: float = 0.2, ou_dt: float = 1e-2, seed: int = 0,
-                      step: int = 0, env_offset: int = 0, counters=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """`forward` in two kernel launches: fce + GRUCell in fp32 (the recurrent state stays exact), then the
-        32-400-300-2 MLP on the tensor cores (bf16 operands, fp32 accumulation). `hidden_out` may be `hidden`.
+                      step: int = 0, env_offset: int = 0, counters=None, impl: str = "tc") -> Tuple[torch.Tensor, torch.Tensor]:
+        """`forward` in two kernel launches: fce + GRUCell, then the 32-400-300-2 MLP on the tensor cores (bf16
+        operands, fp32 accumulation). `impl="tc"` (default): the front end runs on the tensor cores too, with split
+        bf16 operands (fp32-level accuracy, hidden state within 1e-5 of the fp32 module; csrc/flock_gru_tc.cu);
+        `impl="fp32"`: the CUDA-core front kernel. `hidden_out` may be `hidden`.
         With `ou_state` ((E, N, 2) float32, zeros after a reset) the learner's Ornstein-Uhlenbeck exploration noise
         (agent.py:61, utils.py:43-47) is added in the same launch, one process per (env, agent, action). Pass
         `counters=env.noise_counters` when the launch may be captured in a CUDA graph (see BatchedActors.forward_fused)."""
@@ -233,14 +243,22 @@ class BatchedRnnActors(torch.nn.Module):
             out = torch.empty(E, N, 2, dtype=torch.float32, device=x.device)
         if hidden_out is None:
             hidden_out = torch.empty(E, N, self.hidden_rnn, dtype=torch.float32, device=x.device)
+        if ou_state is not None and (ou_state.shape != (E, N, 2) or ou_state.dtype != torch.float32 or not ou_state.is_contiguous()):
+            raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
+        if impl not in ("tc", "fp32"):
+            raise ValueError("impl must be 'tc' or 'fp32'")
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            if ou_state is None:
+            if impl == "tc" and self._front_packed is not None:
+                _lib.check(lib.flock_rnn_actor_forward_tc(
+                    self._packed.data_ptr(), self._front_packed.data_ptr(), x.data_ptr(), h.data_ptr(), hidden_out.data_ptr(),
+                    out.data_ptr(), E, N, x.shape[2], None if ou_state is None else ou_state.data_ptr(), float(ou_theta),
+                    float(ou_mu), float(ou_sigma), float(ou_dt), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
+                    _lib.noise_counters(counters), stream))
+            elif ou_state is None:
                 _lib.check(lib.flock_rnn_actor_forward(self._packed.data_ptr(), self._front_ptrs, x.data_ptr(), h.data_ptr(),
                                                        hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2], stream))
             else:
-                if ou_state.shape != (E, N, 2) or ou_state.dtype != torch.float32 or not ou_state.is_contiguous():
-                    raise ValueError("ou_state must be a contiguous float32 (E, N, 2) tensor")
                 _lib.check(lib.flock_rnn_actor_forward_ou(self._packed.data_ptr(), self._front_ptrs, x.data_ptr(), h.data_ptr(),
                                                           hidden_out.data_ptr(), out.data_ptr(), E, N, x.shape[2],
                                                           ou_state.data_ptr(), float(ou_theta), float(ou_mu), float(ou_sigma),
@@ -337,7 +355,7 @@ class BatchedQNet(torch.nn.Module):
     # ---- fused path (csrc/flock_qnet.cu through the C ABI): one fp32 launch for all envs and agents ----
     @torch.no_grad()
     def _fused(self, obs, hidden, want_q: bool, want_actions: bool, epsilon: float, step: int, seed: int, env_offset: int,
-               out=None, hidden_out=None, counters=None):
+               out=None, hidden_out=None, counters=None, impl: str = "tc"):
         import ctypes
 
         from . import _lib
@@ -348,14 +366,23 @@ class BatchedQNet(torch.nn.Module):
         A = self.wq.shape[2]
         x = obs if (obs.dtype == torch.float32 and obs.is_contiguous()) else obs.float().contiguous()
         names = ["w1", "b1", "w2", "b2", "wq", "bq"] + (["w_ih", "b_ih", "w_hh", "b_hh"] if self.recurrent else [])
-        key = tuple(getattr(self, n).data_ptr() for n in names)
+        if impl not in ("tc", "fp32"):
+            raise ValueError("impl must be 'tc' or 'fp32'")
+        # parameters moved or were updated in place (optimiser step): rebuild the pointer table / the packed image
+        key = tuple((getattr(self, n).data_ptr(), getattr(self, n)._version) for n in names)
         cache = getattr(self, "_fused_ptrs", None)
-        if cache is None or cache[0] != key:     # the pointer table is rebuilt only when a parameter moved
+        if cache is None or cache[0] != key:
             srcs = [getattr(self, n).detach() for n in names]
             srcs = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in srcs]
             ptrs = (ctypes.c_void_p * 10)(*([t.data_ptr() for t in srcs] + [None] * (10 - len(srcs))))
-            cache = self._fused_ptrs = (key, ptrs, srcs)
-        ptrs = cache[1]
+            packed = None
+            if self.recurrent and self.hx_size == 32 and n_obs <= 16 and A <= 16 and self.w1.shape[2] == 64:
+                # tensor-core path (csrc/flock_gru_tc.cu): split-bf16 weight images, re-packed after every update
+                packed = torch.empty(lib.flock_gru_tc_packed_bytes(1, N), dtype=torch.uint8, device=x.device)
+                with torch.cuda.device(x.device):
+                    _lib.check(lib.flock_gru_tc_pack(1, N, n_obs, A, ptrs, packed.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            cache = self._fused_ptrs = (key, ptrs, srcs, packed)
+        ptrs, packed = cache[1], cache[3]
         dev = x.device
         q = torch.empty(E, N, A, dtype=torch.float32, device=dev) if want_q else None
         act = (out if out is not None else torch.empty(E, N, dtype=torch.float32, device=dev)) if want_actions else None
@@ -365,28 +392,35 @@ class BatchedQNet(torch.nn.Module):
             h_out = hidden_out if hidden_out is not None else torch.empty(E, N, self.hx_size, dtype=torch.float32, device=dev)
         p = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(dev):
-            _lib.check(lib.flock_qnet_forward(ptrs, int(self.recurrent), x.data_ptr(), p(h_in), p(q), p(h_out), p(act), E, N,
-                                              n_obs, A, float(epsilon), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
-                                              _lib.noise_counters(counters), torch.cuda.current_stream().cuda_stream))
+            if impl == "tc" and packed is not None:
+                _lib.check(lib.flock_qnet_forward_tc(packed.data_ptr(), x.data_ptr(), p(h_in), p(q), p(h_out), p(act), E, N, n_obs, A,
+                                                     float(epsilon), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
+                                                     _lib.noise_counters(counters), torch.cuda.current_stream().cuda_stream))
+            else:
+                _lib.check(lib.flock_qnet_forward(ptrs, int(self.recurrent), x.data_ptr(), p(h_in), p(q), p(h_out), p(act), E, N,
+                                                  n_obs, A, float(epsilon), int(seed), int(step) & 0xFFFFFFFF, int(env_offset),
+                                                  _lib.noise_counters(counters), torch.cuda.current_stream().cuda_stream))
         if h_out is None:
             h_out = torch.empty(E, N, self.hx_size, device=dev)      # like `forward`: unused without the GRU
         return q, h_out, act
 
-    def forward_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """`forward` in one kernel launch (fp32, same arithmetic up to summation order)."""
-        q, h, _ = self._fused(obs, hidden, True, False, 0.0, 0, 0, 0)
+    def forward_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None, impl: str = "tc") -> Tuple[torch.Tensor, torch.Tensor]:
+        """`forward` in one kernel launch. `impl="tc"` (default, recurrent nets): tcgen05 MMAs with split bf16 operands
+        (fp32-level accuracy: within 1e-5 of the fp32 module); `impl="fp32"`: the CUDA-core kernel (same arithmetic as
+        PyTorch up to summation order; also what non-recurrent nets use)."""
+        q, h, _ = self._fused(obs, hidden, True, False, 0.0, 0, 0, 0, impl=impl)
         return q, h
 
     def sample_action_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor], epsilon: float, step: int = 0,
                             seed: int = 0, env_offset: int = 0, out: Optional[torch.Tensor] = None,
-                            hidden_out: Optional[torch.Tensor] = None, counters=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                            hidden_out: Optional[torch.Tensor] = None, counters=None, impl: str = "tc") -> Tuple[torch.Tensor, torch.Tensor]:
         """`sample_action` (net.py:52-58) in one kernel launch: Q-values, argmax and the per-env epsilon-greedy
         decision never leave the SM. Exploration draws are Philox(seed; env_offset + env, agent, step), i.e.
         reproducible and invariant under env sharding -- pass the rollout step as `step`, or, when the launch may be
         captured in a CUDA graph (a host `step` is frozen there), `counters=env.noise_counters`. `out` (E, N) and
         `hidden_out` (E, N, 32; may be `hidden`) receive the results in place when given."""
         _, h, act = self._fused(obs, hidden, False, True, epsilon, step, seed, env_offset, out=out, hidden_out=hidden_out,
-                                counters=counters)
+                                counters=counters, impl=impl)
         return act, h
 
     @torch.no_grad()

@@ -18,9 +18,11 @@ def _net(N, n_obs, A, rec, seed, dev):
     return BatchedQNet(N, n_obs, A, recurrent=rec, device=dev)
 
 
+@pytest.mark.parametrize("impl", ["tc", "fp32"])      # tensor-core kernel with split bf16 operands / fp32 CUDA-core kernel
 @pytest.mark.parametrize("E,N,n_obs,A,rec", [(8192, 16, 4, 4, True), (8192, 16, 4, 4, False), (300, 5, 8, 8, True),
-                                             (257, 3, 3, 5, False), (1, 2, 4, 4, True), (100, 7, 16, 16, True)])
-def test_fused_qnet_matches_pytorch(E, N, n_obs, A, rec):
+                                             (257, 3, 3, 5, False), (1, 2, 4, 4, True), (100, 7, 16, 16, True),
+                                             (129, 4, 1, 2, True)])
+def test_fused_qnet_matches_pytorch(E, N, n_obs, A, rec, impl):
     dev = torch.device("cuda:0")
     net = _net(N, n_obs, A, rec, 3 + E, dev)
     torch.manual_seed(E + N)
@@ -33,8 +35,8 @@ def test_fused_qnet_matches_pytorch(E, N, n_obs, A, rec):
             q_ref, h_ref = net(obs, hidden)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    q, h = net.forward_fused(obs, hidden)
-    act, h2 = net.sample_action_fused(obs, hidden, epsilon=0.0)
+    q, h = net.forward_fused(obs, hidden, impl=impl)
+    act, h2 = net.sample_action_fused(obs, hidden, epsilon=0.0, impl=impl)
     torch.cuda.synchronize()
     assert torch.allclose(q, q_ref, atol=2e-5, rtol=2e-5), (q - q_ref).abs().max().item()
     if rec:

@@ -37,8 +37,9 @@ def _emulate(a, obs, hidden):
     return torch.cat([lin, ang], dim=-1).transpose(0, 1).contiguous(), h
 
 
-@pytest.mark.parametrize("E,N,n_obs", [(128, 1, 4), (300, 5, 4), (4096, 10, 4), (77, 3, 8), (1, 2, 12)])
-def test_fused_rnn_actor_matches_pytorch(E, N, n_obs):
+@pytest.mark.parametrize("impl", ["tc", "fp32"])      # front end: tensor cores with split bf16 operands / fp32 CUDA cores
+@pytest.mark.parametrize("E,N,n_obs", [(128, 1, 4), (300, 5, 4), (4096, 10, 4), (77, 3, 8), (1, 2, 12), (4096, 32, 16)])
+def test_fused_rnn_actor_matches_pytorch(E, N, n_obs, impl):
     dev = torch.device("cuda:0")
     a = _net(N, n_obs, 7 + E, dev)
     torch.manual_seed(E + N)
@@ -52,7 +53,7 @@ def test_fused_rnn_actor_matches_pytorch(E, N, n_obs):
             want16, _ = _emulate(a, obs, hidden)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    got, h = a.forward_fused(obs, hidden)
+    got, h = a.forward_fused(obs, hidden, impl=impl)
     torch.cuda.synchronize()
     assert got.shape == (E, N, 2) and h.shape == (E, N, 32)
     assert torch.isfinite(got).all()
