@@ -54,8 +54,12 @@ struct Layout {
     // fp32 parameters: b0 [kN0] | b2 [32] (vdn) | b_ih [96] | b_hh [96] | bq [16] (vdn)
     static constexpr int kPb0 = 0, kPb2 = kPb0 + kN0, kPbih = kPb2 + (kVdn ? kHx : 0), kPbhh = kPbih + kG,
                          kPbq = kPbhh + kG, kParamFloats = kPbq + (kVdn ? kActPad : 0);
-    static constexpr int kOffW0c = 2 * kPiece;                   // third piece of the observation-layer weights
-    static constexpr int kOffPar = kOffW0c + kW0;
+    // third pieces (see below): the observation-layer weights and, for the recurrent actor, W_ih (its input e = fce(obs) is
+    // not squashed: |e| ~ 10, so a two-piece split of e alone leaves 1e-4)
+    static constexpr int kX1Pieces = kVdn ? 2 : 3;
+    static constexpr int kOffW0c = 2 * kPiece;
+    static constexpr int kOffWihc = kOffW0c + kW0;
+    static constexpr int kOffPar = kOffWihc + (kVdn ? 0 : kWg);
     static constexpr int kBlobBytes = kOffPar + kParamFloats * 4;
     // shared memory: blob | A operand images (hi | lo each) | barriers
     static constexpr int kAx0 = kObsPad * kRows * 2;              // obs, K = 16
@@ -64,7 +68,7 @@ struct Layout {
     static constexpr int kOffBlob = 0;
     static constexpr int kOffX0 = (kBlobBytes + 127) & ~127;
     static constexpr int kOffX1 = kOffX0 + 3 * kAx0;
-    static constexpr int kOffH = kOffX1 + 2 * kAx1;
+    static constexpr int kOffH = kOffX1 + kX1Pieces * kAx1;
     static constexpr int kOffBar = kOffH + 2 * kAh;
     static constexpr int kNumBars = 12;
     static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 128;
@@ -159,22 +163,26 @@ __device__ __forceinline__ void mma_split(uint32_t tmem_d, uint32_t a_hi, uint32
     }
 }
 
-// observation layer, one K step, three pieces per operand: a1 b1 + a1 b2 + a2 b1 + a2 b2 + a1 b3 + a3 b1
-__device__ __forceinline__ void mma_split3(uint32_t tmem_d, const uint32_t (&a)[3], const uint32_t (&b)[3], int N, bool leader) {
+// three pieces per operand (24 significant bits): a1 b1 + a1 b2 + a2 b1 + a2 b2 + a1 b3 + a3 b1 per K step
+__device__ __forceinline__ void mma_split3(uint32_t tmem_d, const uint32_t (&a)[3], const uint32_t (&b)[3], int ksteps, int N,
+                                           bool leader) {
     if (!leader) return;
     const uint32_t idesc = umma_idesc(kRows, N);
-    uint64_t da[3], db[3];
+    const uint32_t a_step = 2 * kRows * 16, b_step = 2 * (uint32_t)N * 16;
+    for (int s = 0; s < ksteps; ++s) {
+        uint64_t da[3], db[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        da[i] = umma_desc(a[i], kRows * 16, 128);
-        db[i] = umma_desc(b[i], (uint32_t)N * 16, 128);
+        for (int i = 0; i < 3; ++i) {
+            da[i] = umma_desc(a[i] + s * a_step, kRows * 16, 128);
+            db[i] = umma_desc(b[i] + s * b_step, (uint32_t)N * 16, 128);
+        }
+        umma_bf16(tmem_d, da[0], db[0], idesc, s == 0 ? 0u : 1u);
+        umma_bf16(tmem_d, da[0], db[1], idesc, 1u);
+        umma_bf16(tmem_d, da[1], db[0], idesc, 1u);
+        umma_bf16(tmem_d, da[1], db[1], idesc, 1u);
+        umma_bf16(tmem_d, da[0], db[2], idesc, 1u);
+        umma_bf16(tmem_d, da[2], db[0], idesc, 1u);
     }
-    umma_bf16(tmem_d, da[0], db[0], idesc, 0u);
-    umma_bf16(tmem_d, da[0], db[1], idesc, 1u);
-    umma_bf16(tmem_d, da[1], db[0], idesc, 1u);
-    umma_bf16(tmem_d, da[1], db[1], idesc, 1u);
-    umma_bf16(tmem_d, da[0], db[2], idesc, 1u);
-    umma_bf16(tmem_d, da[2], db[0], idesc, 1u);
 }
 
 template <int MODE>
@@ -192,9 +200,9 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
 
     const uint32_t sBlob = base + L::kOffBlob;
     const uint32_t sWhi = sBlob, sWlo = sBlob + L::kPiece;
-    const float* par = reinterpret_cast<const float*>(sm + L::kOffBlob + 2 * L::kPiece);
-    const uint32_t sX0h = base + L::kOffX0, sX0l = sX0h + L::kAx0;
-    const uint32_t sX1h = base + L::kOffX1, sX1l = sX1h + L::kAx1;
+    const float* par = reinterpret_cast<const float*>(sm + L::kOffBlob + L::kOffPar);
+    const uint32_t sX0[3] = {base + L::kOffX0, base + L::kOffX0 + L::kAx0, base + L::kOffX0 + 2 * L::kAx0};   // obs: three pieces
+    const uint32_t sX1h = base + L::kOffX1, sX1l = sX1h + L::kAx1, sX1c = sX1l + L::kAx1;   // sX1c: recurrent actor only
     const uint32_t sHh = base + L::kOffH, sHl = sHh + L::kAh;
     const uint32_t sBar = base + L::kOffBar;
     const uint32_t bar_w = sBar, bar_a0 = sBar + 8, bar_m0 = sBar + 16, bar_a1 = sBar + 24, bar_m2 = sBar + 32, bar_ax = sBar + 40,
@@ -248,7 +256,10 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
             // layer 0 (obs -> kN0) and the hidden half of the GRU (h -> gh): both operands are staged at a0
             mbar_wait(bar_a0, ph);
             tc_fence_after();
-            mma_split(tmem + 0, sX0h, sX0l, sWhi + L::kOffW0, sWlo + L::kOffW0, 1, L::kN0, leader);
+            {
+                const uint32_t w0[3] = {sWhi + L::kOffW0, sWlo + L::kOffW0, sBlob + L::kOffW0c};
+                mma_split3(tmem + 0, sX0, w0, 1, L::kN0, leader);
+            }
             if (leader) umma_commit(bar_m0);
             mma_split(tmem + L::kColGh, sHh, sHl, sWhi + L::kOffWhh, sWlo + L::kOffWhh, kHx / 16, kG, leader);
             __syncwarp();
@@ -262,7 +273,13 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
             // input half of the GRU: x -> gi (overwrites the consumed first-layer columns)
             mbar_wait(bar_ax, ph);
             tc_fence_after();
-            mma_split(tmem + L::kColGi, sX1h, sX1l, sWhi + L::kOffWih, sWlo + L::kOffWih, kHx / 16, kG, leader);
+            if (kVdn) {
+                mma_split(tmem + L::kColGi, sX1h, sX1l, sWhi + L::kOffWih, sWlo + L::kOffWih, kHx / 16, kG, leader);
+            } else {
+                const uint32_t xa[3] = {sX1h, sX1l, sX1c};
+                const uint32_t wb[3] = {sWhi + L::kOffWih, sWlo + L::kOffWih, sBlob + L::kOffWihc};
+                mma_split3(tmem + L::kColGi, xa, wb, kHx / 16, kG, leader);
+            }
             if (leader) umma_commit(bar_m3);          // covers gh as well
             __syncwarp();
             if (kVdn) {
@@ -274,9 +291,11 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
             }
         }
     } else {
-        // ---- epilogue warps: thread = env row = TMEM lane ----
-        const int row = threadIdx.x;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        // ---- epilogue warps: two threads per env row (= TMEM lane); `half` selects the columns / K groups a thread owns.
+        // A warp may only touch TMEM lanes 32 * (warp % 4) .. + 31, so warps w and w + 4 share a lane group.
+        const int row = threadIdx.x & (kRows - 1);
+        const int half = threadIdx.x >> 7;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         int prev_agent = -1;
         uint32_t w_loads = 0;
         for (int item = item0, it = 0; item < item1; ++item, ++it) {
@@ -285,31 +304,33 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
             const int env = tile * kRows + row;
             const bool valid = env < a.E;
             const size_t ea = (size_t)(valid ? env : 0) * a.A + agent;
-            // stage 0: this row's observation and hidden state as split A operands
-            float hold[kHx];
+            // stage 0: this row's observation and hidden state as split A operands (half h: obs elements 8h .. 8h + 7,
+            // hidden units 16h .. 16h + 15 -- the units whose gates this thread evaluates below)
+            float hold[kHx / 2];
             {
-                float x[kObsPad];
+                float v[8];
 #pragma unroll
-                for (int i = 0; i < kObsPad; ++i) x[i] = (valid && i < a.n_obs) ? a.obs[ea * a.n_obs + i] : 0.0f;
-#pragma unroll
-                for (int kg = 0; kg < kObsPad / 8; ++kg) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = x[kg * 8 + i];
-                    store_k8(sX0h + (kg * kRows + row) * 16, sX0l + (kg * kRows + row) * 16, v);
+                for (int i = 0; i < 8; ++i) {
+                    const int c = half * 8 + i;
+                    v[i] = (valid && c < a.n_obs) ? a.obs[ea * a.n_obs + c] : 0.0f;
                 }
-                const float4* h4 = reinterpret_cast<const float4*>(a.hidden_in + ea * kHx);
+                {
+                    const uint32_t o = (uint32_t)(half * kRows + row) * 16;
+                    store_k8_3(sX0[0] + o, sX0[1] + o, sX0[2] + o, v);
+                }
+                const float4* h4 = reinterpret_cast<const float4*>(a.hidden_in + ea * kHx + half * (kHx / 2));
 #pragma unroll
-                for (int kg = 0; kg < kHx / 8; ++kg) {
+                for (int g = 0; g < 2; ++g) {
                     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
                     if (valid) {
-                        p = h4[2 * kg];
-                        q = h4[2 * kg + 1];
+                        p = h4[2 * g];
+                        q = h4[2 * g + 1];
                     }
-                    const float v[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+                    const float w[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) hold[kg * 8 + i] = v[i];
-                    store_k8(sHh + (kg * kRows + row) * 16, sHl + (kg * kRows + row) * 16, v);
+                    for (int i = 0; i < 8; ++i) hold[g * 8 + i] = w[i];
+                    const int kg = half * 2 + g;
+                    store_k8(sHh + (kg * kRows + row) * 16, sHl + (kg * kRows + row) * 16, w);
                 }
             }
             fence_proxy_async();
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
             mbar_wait(bar_m0, ph);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < L::kN0; c0 += 16) {
+            for (int c0 = half * (L::kN0 / 2); c0 < (half + 1) * (L::kN0 / 2); c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16_issue(trow + c0, r);
                 tmem_ld16_wait(r);
@@ -337,9 +358,14 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
                         v1[i] = fmaxf(v1[i], 0.0f);
                     }
                 }
-                const int kg = c0 >> 3;
-                store_k8(sX1h + (kg * kRows + row) * 16, sX1l + (kg * kRows + row) * 16, v0);
-                store_k8(sX1h + ((kg + 1) * kRows + row) * 16, sX1l + ((kg + 1) * kRows + row) * 16, v1);
+                const uint32_t o0 = (uint32_t)((c0 >> 3) * kRows + row) * 16, o1 = o0 + kRows * 16;
+                if (kVdn) {
+                    store_k8(sX1h + o0, sX1l + o0, v0);
+                    store_k8(sX1h + o1, sX1l + o1, v1);
+                } else {
+                    store_k8_3(sX1h + o0, sX1l + o0, sX1c + o0, v0);
+                    store_k8_3(sX1h + o1, sX1l + o1, sX1c + o1, v1);
+                }
             }
             fence_proxy_async();
             tc_fence_before();
@@ -348,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
                 // second feature layer: bias + ReLU -> x (same place: the layer-2 MMA has consumed H1)
                 mbar_wait(bar_m2, ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < kHx; c0 += 16) {
+                {
+                    const int c0 = half * 16;
                     uint32_t r[16];
                     tmem_ld16_issue(trow + L::kColH2 + c0, r);
                     tmem_ld16_wait(r);
@@ -367,12 +393,12 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
                 tc_fence_before();
             }
             mbar_arrive(bar_ax);
-            // GRU gates (torch.nn.GRUCell, gate order r | z | n): h' = (1 - z) n + z h
+            // GRU gates (torch.nn.GRUCell, gate order r | z | n): h' = (1 - z) n + z h, units 16 * half .. + 15
             mbar_wait(bar_m3, ph);
             tc_fence_after();
-            float hnew[kHx];
-#pragma unroll
-            for (int u0 = 0; u0 < kHx; u0 += 16) {      // fully unrolled: hnew / hold keep static register indices
+            float hnew[kHx / 2];
+            {
+                const int u0 = half * 16;
                 float rg[16], zg[16];
                 uint32_t gi[16], gh[16];
                 tmem_ld16_issue(trow + L::kColGi + u0, gi);
@@ -398,60 +424,63 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
                 for (int i = 0; i < 16; ++i) {
                     const float n = tanh_((__uint_as_float(gi[i]) + par[L::kPbih + 2 * kHx + u0 + i]) +
                                           rg[i] * (__uint_as_float(gh[i]) + par[L::kPbhh + 2 * kHx + u0 + i]));
-                    hnew[u0 + i] = (1.0f - zg[i]) * n + zg[i] * hold[u0 + i];
+                    hnew[i] = (1.0f - zg[i]) * n + zg[i] * hold[i];
                 }
             }
             if (valid && a.hidden_out != nullptr) {
-                float4* o4 = reinterpret_cast<float4*>(a.hidden_out + ea * kHx);
+                float4* o4 = reinterpret_cast<float4*>(a.hidden_out + ea * kHx + half * (kHx / 2));
 #pragma unroll
-                for (int j = 0; j < kHx / 4; ++j) o4[j] = make_float4(hnew[4 * j], hnew[4 * j + 1], hnew[4 * j + 2], hnew[4 * j + 3]);
+                for (int j = 0; j < kHx / 8; ++j) o4[j] = make_float4(hnew[4 * j], hnew[4 * j + 1], hnew[4 * j + 2], hnew[4 * j + 3]);
             }
             if (kVdn) {
                 // h' as the head's A operand (same place as h: the gh MMAs completed with m3)
 #pragma unroll
-                for (int kg = 0; kg < kHx / 8; ++kg) {
+                for (int g = 0; g < 2; ++g) {
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = hnew[kg * 8 + i];
+                    for (int i = 0; i < 8; ++i) v[i] = hnew[g * 8 + i];
+                    const int kg = half * 2 + g;
                     store_k8(sHh + (kg * kRows + row) * 16, sHl + (kg * kRows + row) * 16, v);
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar_ah);
-                mbar_wait(bar_m4, ph);
-                tc_fence_after();
-                uint32_t qr[16];
-                tmem_ld16_issue(trow + L::kColQ, qr);
-                tmem_ld16_wait(qr);
-                float q[kActPad];
+                mbar_wait(bar_m4, ph);     // every thread: the head MMA reads h', which the next item's stage 0 overwrites
+                if (half == 0) {      // the head is 16 columns: one thread per row finishes it
+                    tc_fence_after();
+                    uint32_t qr[16];
+                    tmem_ld16_issue(trow + L::kColQ, qr);
+                    tmem_ld16_wait(qr);
+                    float q[kActPad];
 #pragma unroll
-                for (int j = 0; j < kActPad; ++j) q[j] = __uint_as_float(qr[j]) + par[L::kPbq + j];
-                if (valid) {
-                    if (a.q_out != nullptr) {
+                    for (int j = 0; j < kActPad; ++j) q[j] = __uint_as_float(qr[j]) + par[L::kPbq + j];
+                    if (valid) {
+                        if (a.q_out != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < kActPad; ++j)
-                            if (j < a.n_act) a.q_out[ea * a.n_act + j] = q[j];
-                    }
-                    if (a.actions != nullptr) {
-                        // greedy: first maximum, like torch.argmax; exploration: one decision per env (net.py:54), then a
-                        // uniform action id per agent (net.py:56) -- same Philox stream as flock_qnet_kernel
-                        int best = 0;
-                        float bv = q[0];
-#pragma unroll
-                        for (int j = 1; j < kActPad; ++j)
-                            if (j < a.n_act && q[j] > bv) {
-                                bv = q[j];
-                                best = j;
-                            }
-                        const uint32_t ge = (uint32_t)(a.env_offset + env);
-                        const uint32_t c2 = a.step + (a.env_step != nullptr ? (uint32_t)a.env_step[env] : 0u);
-                        const uint32_t ep = a.env_epoch != nullptr ? (a.env_epoch[env] << 4) : 0u;
-                        const uint4 re = philox4x32_10(ge, 0xffffffffu, c2, kTagExplore + ep, a.seed_lo, a.seed_hi);
-                        if (u24(re.x) <= a.epsilon && a.epsilon > 0.0f) {
-                            const uint4 ra = philox4x32_10(ge, (uint32_t)agent, c2, kTagRandAct + ep, a.seed_lo, a.seed_hi);
-                            best = (int)(((unsigned long long)ra.x * (unsigned long long)a.n_act) >> 32);
+                            for (int j = 0; j < kActPad; ++j)
+                                if (j < a.n_act) a.q_out[ea * a.n_act + j] = q[j];
                         }
-                        a.actions[ea] = (float)best;
+                        if (a.actions != nullptr) {
+                            // greedy: first maximum, like torch.argmax; exploration: one decision per env (net.py:54), then a
+                            // uniform action id per agent (net.py:56) -- same Philox stream as flock_qnet_kernel
+                            int best = 0;
+                            float bv = q[0];
+#pragma unroll
+                            for (int j = 1; j < kActPad; ++j)
+                                if (j < a.n_act && q[j] > bv) {
+                                    bv = q[j];
+                                    best = j;
+                                }
+                            const uint32_t ge = (uint32_t)(a.env_offset + env);
+                            const uint32_t c2 = a.step + (a.env_step != nullptr ? (uint32_t)a.env_step[env] : 0u);
+                            const uint32_t ep = a.env_epoch != nullptr ? (a.env_epoch[env] << 4) : 0u;
+                            const uint4 re = philox4x32_10(ge, 0xffffffffu, c2, kTagExplore + ep, a.seed_lo, a.seed_hi);
+                            if (u24(re.x) <= a.epsilon && a.epsilon > 0.0f) {
+                                const uint4 ra = philox4x32_10(ge, (uint32_t)agent, c2, kTagRandAct + ep, a.seed_lo, a.seed_hi);
+                                best = (int)(((unsigned long long)ra.x * (unsigned long long)a.n_act) >> 32);
+                            }
+                            a.actions[ea] = (float)best;
+                        }
                     }
                 }
             }
@@ -507,11 +536,33 @@ __global__ void flock_gru_tc_pack_kernel(PackArgs p, uint8_t* __restrict__ blobs
         for (int u = threadIdx.x; u < units; u += blockDim.x) pack_unit(hi + off, lo + off, W, K, N, Npad, u);
     };
     pack(L::kOffW0, p.w0 + (size_t)agent * p.n_obs * L::kN0, p.n_obs, kObsPad, L::kN0, L::kN0);
+    // third pieces: w - bf16(w) - bf16(w - bf16(w)); unit u = 8 K elements of column n, as in pack_unit
+    auto pack3 = [&](int off, const float* W, int K, int Kpad, int N) {
+        for (int u = threadIdx.x; u < (Kpad / 8) * N; u += blockDim.x) {
+            const int n = u % N, sg = u / N;
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                w[i] = 0u;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k = sg * 8 + 2 * i + j;
+                    float r = k < K ? W[(size_t)k * N + n] : 0.0f;
+                    r -= __bfloat162float(__float2bfloat16_rn(r));
+                    r -= __bfloat162float(__float2bfloat16_rn(r));
+                    w[i] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r)) << (16 * j);
+                }
+            }
+            reinterpret_cast<uint4*>(blob + off)[u] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+    pack3(L::kOffW0c, p.w0 + (size_t)agent * p.n_obs * L::kN0, p.n_obs, kObsPad, L::kN0);
+    if (!L::kVdn) pack3(L::kOffWihc, p.w_ih + (size_t)agent * kHx * kG, kHx, kHx, kG);
     if (L::kVdn) pack(L::kOffW2, p.w2 + (size_t)agent * kH1 * kHx, kH1, kH1, kHx, kHx);
     pack(L::kOffWih, p.w_ih + (size_t)agent * kHx * kG, kHx, kHx, kG, kG);
     pack(L::kOffWhh, p.w_hh + (size_t)agent * kHx * kG, kHx, kHx, kG, kG);
     if (L::kVdn) pack(L::kOffWq, p.wq + (size_t)agent * kHx * p.n_act, kHx, kHx, p.n_act, kActPad);
-    float* par = reinterpret_cast<float*>(blob + 2 * L::kPiece);
+    float* par = reinterpret_cast<float*>(blob + L::kOffPar);
     for (int i = threadIdx.x; i < L::kParamFloats; i += blockDim.x) {
         float v;
         if (i < L::kPb2) v = p.b0[(size_t)agent * L::kN0 + i];
