@@ -48,6 +48,8 @@ struct flock_env {
     int* tile_inv;                // its inverse (agent -> slot)
     float* sorted_xy;             // pruned path: per-env staging record (positions by slot, boxes, ids)
     unsigned short* hint_slots;   // pruned path: last step's neighbour slots per row
+    float* env_sums;              // tiled path, uw / uwd: per-env sums behind the centre of mass / mean heading
+    uint8_t* far_rows;            // pruned path: rows that left their spatial neighbourhood (wrap-around) since the last refresh
     uint32_t perm_age;            // steps since the row order was refreshed
     unsigned long long* pair_counter;   // device counter of row x neighbour pairs evaluated by the pruned kernel
     const void* zc_host[5];       // last host buffers seen by flock_step_host and their device aliases
@@ -129,6 +131,8 @@ Params make_params(const flock_env* e, float dt) {
     p.inv = e->tile_inv;
     p.sorted_xy = e->sorted_xy;
     p.hint_slots = e->hint_slots;
+    p.env_sums = e->env_sums;
+    p.far_rows = e->far_rows;
     return p;
 }
 
@@ -332,6 +336,10 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         if (err == cudaSuccess) err = cudaMalloc(&e->hint_slots, flock::pruned_hint_bytes(cfg->num_agents, cfg->num_envs));
         if (err == cudaSuccess)
             err = cudaMemset(e->hint_slots, 0xff, flock::pruned_hint_bytes(cfg->num_agents, cfg->num_envs));
+        if (err == cudaSuccess && cfg->variant != FLOCK_V2)
+            err = cudaMalloc(&e->env_sums, (size_t)cfg->num_envs * 2 * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&e->far_rows, flock::pruned_hint_bytes(cfg->num_agents, cfg->num_envs) / 16);
+        if (err == cudaSuccess) err = cudaMemset(e->far_rows, 0, flock::pruned_hint_bytes(cfg->num_agents, cfg->num_envs) / 16);
         if (err == cudaSuccess)
             err = flock::launch_perm_identity(e->tile_perm, e->tile_inv, cfg->num_agents, cfg->num_envs, nullptr);
         if (err == cudaSuccess) err = cudaDeviceSynchronize();
@@ -343,6 +351,8 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         cudaFree(e->tile_inv);
         cudaFree(e->sorted_xy);
         cudaFree(e->hint_slots);
+        cudaFree(e->env_sums);
+        cudaFree(e->far_rows);
         cudaFree(e->pair_counter);
         cudaFree(e->stage_actions);
         cudaFree(e->stage_noise);
@@ -364,6 +374,8 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->tile_inv);
     cudaFree(e->sorted_xy);
     cudaFree(e->hint_slots);
+    cudaFree(e->env_sums);
+    cudaFree(e->far_rows);
     cudaFree(e->pair_counter);
     if (e->host_event_live) cudaEventDestroy(e->host_event);
     delete e;

@@ -61,6 +61,8 @@ struct Params {
     const int* inv;               // inverse of perm (agent -> slot)
     float* sorted_xy;             // pruned path: per env x | y by slot, boxes, agent ids (3 * PS floats)
     unsigned short* hint_slots;   // pruned path: [E][PS][8] slots of last step's neighbours (0xffff: none)
+    uint8_t* far_rows;            // pruned path: [E][PS] rows (by slot) that wrapped around the world since the last row-order refresh
+    float* env_sums;              // tiled path, uw / uwd: [E][2] sequential (agent order) sums of the NEW x, y (uw) or h (uwd)
     // host-call path: device-visible HOST mirrors of the step results (zero-copy), nullable
     float* m_obs;
     float* m_reward;

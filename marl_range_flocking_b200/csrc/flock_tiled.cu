@@ -63,6 +63,10 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 
 __host__ __device__ __forceinline__ int padded_agents(int N) { return ((N + 3) & ~3) + 4; }
 
+// warp-shuffle bitonic top-k merge of 32 per-lane sorted lists (defined with the warp-per-row kernel below)
+template <int K>
+__device__ __forceinline__ void warp_bitonic_topk(unsigned long long (&key)[K]);
+
 // shared-memory carve-up: sx | sy | [sh] | candidate buffer. sh (headings) exists only where the
 // kernel needs every agent's heading afterwards (uwd mean heading, reset).
 size_t tiled_smem_bytes(int num_agents, int rows, bool need_sh) {
@@ -220,7 +224,23 @@ __device__ __forceinline__ void write_obs_t(const Params& p, int env, int a, siz
         return;
     }
     float* o = p.obs + idx * (size_t)(p.H * k);
-    for (int t = (p.H - 1) * k - 1; t >= 0; --t) o[t + k] = fresh ? 0.0f : o[t];
+    if (p.H == 4) {
+        // the reference's history depth: all old rows are loaded into registers BEFORE the first store (the compiler must
+        // keep a load behind every earlier store to this overlapping window, which made the element-wise shift nine
+        // serialised memory round trips per agent: 147 -> 118 us for the sensing kernel at 64 x 2048)
+        float old[3 * K];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < K; ++s) old[r * K + s] = (s < k && !fresh) ? o[r * k + s] : 0.0f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                if (s < k) o[(r + 1) * k + s] = old[r * K + s];
+    } else {
+        for (int t = (p.H - 1) * k - 1; t >= 0; --t) o[t + k] = fresh ? 0.0f : o[t];
+    }
 #pragma unroll
     for (int s = 0; s < K; ++s)
         if (s < k) o[s] = dist[s];
@@ -234,7 +254,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
     const int N = p.N, k = p.k;
     const int env = blockIdx.y, tile = blockIdx.x;
     const int rows = blockDim.x;
-    const TileSmem sm = carve(smem, N, V == FLOCK_UWD);
+    const TileSmem sm = carve(smem, N, false);
     const size_t base = (size_t)env * N;
     // Row assignment. With a row order (p.perm, refreshed every few steps by
     // flock_perm_refresh_kernel) the 32 rows of a warp are spatial neighbours, so their k-NN
@@ -249,8 +269,6 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
     for (int s = 0; s < K; ++s) hint[s] = (p.nn != nullptr && has_row && s < k) ? p.nn[(base + i) * k + s] : -1;
     // the state was integrated in place by the pre-pass (flock_integrate_kernel): stage the NEW positions
     stage_xy(p, sm, &bar, env);
-    if (V == FLOCK_UWD)
-        for (int a = threadIdx.x; a < N; a += rows) sm.sh[a] = p.h[base + a];
     if (threadIdx.x < padded_agents(N) - N) {
         sm.sx[N + threadIdx.x] = kInf;
         sm.sy[N + threadIdx.x] = 0.0f;
@@ -263,21 +281,13 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
         h = p.h[base + i];
     }
 
+    // per-env sums of the new state, formed once by the integrate pre-pass (see flock_integrate_kernel)
     float comx = 0.f, comy = 0.f, hmean = 0.f;
     if (V == FLOCK_UW) {
-        float sx_ = 0.f, sy_ = 0.f;
-        for (int j = 0; j < N; ++j) {
-            sx_ = sx_ + sm.sx[j];
-            sy_ = sy_ + sm.sy[j];
-        }
-        comx = mean_of_sum(p, sx_);
-        comy = mean_of_sum(p, sy_);
+        comx = mean_of_sum(p, p.env_sums[2 * env]);
+        comy = mean_of_sum(p, p.env_sums[2 * env + 1]);
     }
-    if (V == FLOCK_UWD) {
-        float sh_ = 0.f;
-        for (int j = 0; j < N; ++j) sh_ = sh_ + sm.sh[j];
-        hmean = mean_of_sum(p, sh_);
-    }
+    if (V == FLOCK_UWD) hmean = mean_of_sum(p, p.env_sums[2 * env]);
 
     long long fx = 0;
     bool coll = false;
@@ -398,15 +408,16 @@ constexpr int kPrunedCandCap = 16;   // deferred candidates (slots) per row betw
 // per env: x by slot | y by slot | one (x0, x1, y0, y1) box per 8 slots | agent id (u16) by slot
 __host__ __device__ __forceinline__ size_t sorted_record_floats(int PS) { return (size_t)PS * 3; }
 
+constexpr int kSumChunk = 2048;   // agents per shared-memory chunk of the per-env sequential sums
+
 template <int V, bool SORTED>
 __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_constant__ Params p) {
     const int N = p.N, env = blockIdx.y;
     const int PS = ((N + 31) / 32) * 32;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= PS) return;                       // PS is a multiple of 32: whole warps leave together
     const size_t base = (size_t)env * N;
     const bool real = slot < N;
-    if (!SORTED && !real) return;
+    const bool in_record = SORTED && slot < PS;   // PS is a multiple of 32: whole warps are in or out
     float x = kInf, y = 0.0f;                     // padding slots: never selected, never collide
     int agent = 0;
     if (real) {
@@ -416,6 +427,7 @@ __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_const
         float h = p.h[i], vx, vy;
         x = p.x[i];
         y = p.y[i];
+        const float x_old = x, y_old = y;
         float a0, a1 = 0.0f, nzu = 0.f, nzw = 0.f;
         if (V == FLOCK_UWD) {
             a0 = p.actions[i];
@@ -439,8 +451,12 @@ __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_const
             p.vx[i] = vx;
             p.vy[i] = vy;
         }
+        // wrap-around (check_boundary): the agent is now a world away from the rows it shares a warp with until the next
+        // row-order refresh; the pruned kernel scans such rows on their own (see there)
+        if (SORTED && p.far_rows != nullptr && (fabsf(x - x_old) > 0.5f * p.B || fabsf(y - y_old) > 0.5f * p.B))
+            p.far_rows[(size_t)env * PS + slot] = 1;
     }
-    if (SORTED) {
+    if (in_record) {
         float* rec = p.sorted_xy + (size_t)env * sorted_record_floats(PS);
         rec[slot] = x;
         rec[PS + slot] = y;
@@ -456,6 +472,57 @@ __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_const
             reinterpret_cast<float4*>(rec + 2 * (size_t)PS)[slot / kBoxSlots] = make_float4(x0, x1, y0, y1);
         reinterpret_cast<unsigned short*>(rec + 2 * (size_t)PS + PS / 2)[slot] = (unsigned short)(real ? agent : 0xffff);
     }
+    if (V != FLOCK_V2 && p.env_sums != nullptr) {
+        // uw: torch.mean(positions, 0) (gym_flock_uw.py:193); uwd: sum(headings) / N (gym_flock_uw_discrete.py:256). The
+        // canonical float32 sum is sequential in agent order, so it is formed ONCE per env -- by the env's last CTA to
+        // finish integrating (arrival counter), two threads running the two serial chains over shared-memory chunks --
+        // instead of by every row of the sensing kernel.
+        __shared__ __align__(16) float cs[2][kSumChunk];
+        __shared__ bool last;
+        unsigned int* arrive = p.tile_scratch + env;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = atomicAdd(arrive, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            float acc = 0.0f;
+            for (int c0 = 0; c0 < N; c0 += kSumChunk) {
+                const int n = min(kSumChunk, N - c0);
+                for (int j = threadIdx.x; j < n; j += blockDim.x) {     // L2 loads: other CTAs wrote these values
+                    if (V == FLOCK_UW) {
+                        cs[0][j] = __ldcg(p.xo + base + c0 + j);
+                        cs[1][j] = __ldcg(p.yo + base + c0 + j);
+                    } else {
+                        cs[0][j] = __ldcg(p.ho + base + c0 + j);
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0 || (V == FLOCK_UW && threadIdx.x == 32)) {
+                    const float* v = cs[threadIdx.x >> 5];
+                    const float4* v4 = reinterpret_cast<const float4*>(v);
+                    const int n4 = n >> 2;
+#pragma unroll 8
+                    for (int j4 = 0; j4 < n4; ++j4) {      // 128-bit loads run ahead of the serial add chain
+                        const float4 q = v4[j4];
+                        acc = acc + q.x;
+                        acc = acc + q.y;
+                        acc = acc + q.z;
+                        acc = acc + q.w;
+                    }
+                    for (int j = n4 << 2; j < n; ++j) acc = acc + v[j];
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                p.env_sums[2 * env] = acc;
+                *arrive = 0u;                     // the sensing kernel of this step counts its CTAs from zero again
+            }
+            if (V == FLOCK_UW && threadIdx.x == 32) p.env_sums[2 * env + 1] = acc;
+        }
+    }
 }
 
 template <int V, bool SORTED>
@@ -465,7 +532,7 @@ static cudaError_t launch_integrate(const Params& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <int K, bool PER>
+template <int V, int K, bool PER>
 __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -530,6 +597,24 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     mbar_wait(&bar, 0);
 
     const float x = has_row ? ss_x[slot] : 0.f, y = has_row ? ss_y[slot] : 0.f;
+    // uw / uwd: the epilogue's read-modify-write operands (heading, previous heading, the three older rows of the uw
+    // observation window) are fetched now, so their DRAM round trip runs under the scan instead of after it
+    float h_row = 0.f, prev_h_row = 0.f;
+    float win[(V == FLOCK_UW) ? 3 * K : 1];
+    const bool pre_win = V == FLOCK_UW && p.H == 4 && p.obs_head == nullptr;
+    if (V != FLOCK_V2 && has_row) {
+        h_row = p.h[base + i];
+        if (V == FLOCK_UW) {
+            prev_h_row = p.prev_h[base + i];
+            if (pre_win) {
+                const float* o = p.obs + (base + i) * (size_t)(4 * k);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int s = 0; s < K; ++s) win[r * K + s] = s < k ? o[r * k + s] : 0.0f;
+            }
+        }
+    }
     // per-row threshold: the largest CURRENT distance to last step's neighbours bounds the k-th best
     float thr = -1.0f;                                     // lanes without a row accept nothing
     if (has_row) {
@@ -539,8 +624,23 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
             if (s < k) bound = fmaxf(bound, pair_d2<PER>(x, y, ss_x[hslot[s]], ss_y[hslot[s]], p.B));
         thr = hint_ok ? bound : kFltMax;
     }
-    const float wx0 = warp_min(has_row ? x : kFltMax), wx1 = warp_max(has_row ? x : -kFltMax);
-    const float wy0 = warp_min(has_row ? y : kFltMax), wy1 = warp_max(has_row ? y : -kFltMax);
+    // Far rows (Euclidean worlds only: the min-image metric does not notice a wrap): an agent that wrapped around since
+    // the last row-order refresh sits a world away from the other rows of its warp. Left in, it would stretch the warp's
+    // bounding box over the whole world (every box passes the gap test) and, on the step of the wrap itself, bring a
+    // threshold of ~B^2 -- one such row made its warp 13x slower, and the kernel as slow as its slowest warp
+    // (118 vs 40 us at 64 x 2048). They are taken out of the shared pass and scanned one at a time by the whole warp below.
+    bool far = false;
+    if (!PER && p.far_rows != nullptr && has_row) far = p.far_rows[(size_t)env * PS + slot] != 0;
+    unsigned far_mask = __ballot_sync(kFull, far);
+    if (__popc(far_mask) > 8) {        // a warp of strays (dense wrap-around, stale order after a masked reset): shared pass
+        far_mask = 0u;
+        far = false;
+    }
+    const float thr_hint = thr;
+    const bool main_row = has_row && !far;
+    if (far) thr = -1.0f;
+    const float wx0 = warp_min(main_row ? x : kFltMax), wx1 = warp_max(main_row ? x : -kFltMax);
+    const float wy0 = warp_min(main_row ? y : kFltMax), wy1 = warp_max(main_row ? y : -kFltMax);
     // thresholds are non-negative floats: their bit patterns order like unsigned integers
     float thr_max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fmaxf(thr, 0.0f))));
     const float slack = p.B * 1.0e-6f + 1.0e-30f;
@@ -568,7 +668,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     const int ngroups = (nbox + 31) / 32;
     const int own_g = slot / (kBoxSlots * 32);            // group of 32 boxes holding this warp's first row
     unsigned long long evaluated = 0;
-    if (__any_sync(kFull, has_row)) {
+    if (__any_sync(kFull, main_row)) {
         for (int o = 0; o < ngroups; ++o) {
             int g = __shfl_sync(kFull, own_g, 0) + o;
             if (g >= ngroups) g -= ngroups;
@@ -609,6 +709,53 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         }
         merge();
     }
+    // far rows, one at a time, all 32 lanes on the same row: lanes split the 8-slot boxes, a box is opened when its gap to
+    // the row's POINT does not exceed the row's threshold, and the 32 private lists are merged by the warp-shuffle bitonic
+    // top-k on (d2, agent id) keys. Threshold: the smaller of the hint bound and a bound from the boxes themselves -- a
+    // complete box other than the row's own holds 8 >= k other agents, all within the largest distance from the point to
+    // the box's corners -- so the step of the wrap (hint bound ~B^2) is pruned as well. Exact like the shared pass.
+    while (far_mask != 0u) {
+        const int r = __ffs(far_mask) - 1;
+        far_mask &= far_mask - 1u;
+        const float xq = __shfl_sync(kFull, x, r), yq = __shfl_sync(kFull, y, r);
+        const int sq = __shfl_sync(kFull, slot, r);
+        float tb = __shfl_sync(kFull, thr_hint, r);
+        const int nfull = N / kBoxSlots;
+        for (int bl = lane; bl < nfull; bl += 32) {
+            if (bl == sq / kBoxSlots) continue;
+            const float4 q = bb[bl];
+            const float ddx = fmaxf(fabsf(xq - q.x), fabsf(xq - q.y)), ddy = fmaxf(fabsf(yq - q.z), fabsf(yq - q.w));
+            tb = fminf(tb, fmaf(ddy, ddy, ddx * ddx) * 1.0001f + 1.0e-30f);
+        }
+        tb = warp_min(tb);
+        TopK<K> tq;
+        tq.init();
+        for (int bl = lane; bl < nbox; bl += 32) {
+            const float4 q = bb[bl];
+            const float gx = axis_gap<PER>(xq, xq, q.x, q.y, p.B, slack);
+            const float gy = axis_gap<PER>(yq, yq, q.z, q.w, p.B, slack);
+            if ((gx * gx + gy * gy) * 0.9999f <= tb) {
+                evaluated += 1;
+#pragma unroll
+                for (int u = 0; u < kBoxSlots; ++u) {
+                    const int sj = bl * kBoxSlots + u;
+                    const float d = pair_d2<PER>(xq, yq, ss_x[sj], ss_y[sj], p.B);
+                    if (sj != sq && d <= tb) tq.insert_lex(d, ((int)sid[sj] << 16) | sj);
+                }
+            }
+        }
+        unsigned long long key[K];
+#pragma unroll
+        for (int s = 0; s < K; ++s) key[s] = ((unsigned long long)__float_as_uint(tq.d[s]) << 32) | (unsigned)tq.idx[s];
+        warp_bitonic_topk<K>(key);       // every lane ends with the merged list
+        if (lane == r) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                t.d[s] = __uint_as_float((unsigned)(key[s] >> 32));
+                t.idx[s] = (int)(unsigned)key[s];
+            }
+        }
+    }
 
     long long fx = 0;
     bool coll = false;
@@ -616,9 +763,37 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         float dist[K];
         coll = finish_row<K, TopK<K>>(t, k, p.sensor_range, p.cd, dist);
         const size_t idx = base + i;
-        const float rew = reward_from_flags<FLOCK_V2>(coll, false, false);
+        float rew;
+        if (V == FLOCK_V2) {
+            rew = reward_from_flags<FLOCK_V2>(coll, false, false);
+        } else {
+            // uw: centre of mass + heading change (gym_flock_uw.py:186-221); uwd: alignment with the mean heading
+            // (gym_flock_uw_discrete.py:234-276); the per-env sums come from the integrate pre-pass
+            float comx = 0.f, comy = 0.f, hmean = 0.f;
+            const float h = h_row, prev_h = prev_h_row;
+            if (V == FLOCK_UW) {
+                comx = mean_of_sum(p, p.env_sums[2 * env]);
+                comy = mean_of_sum(p, p.env_sums[2 * env + 1]);
+            } else {
+                hmean = mean_of_sum(p, p.env_sums[2 * env]);
+            }
+            rew = agent_reward<V>(p, coll, x, y, h, prev_h, comx, comy, hmean);
+            if (V == FLOCK_UW && !(prev_h == h)) p.prev_h[idx] = h;
+        }
         fx = reward_fx(rew);
-        write_obs_t<K>(p, env, 0, idx, dist, false);   // v2: H == 1
+        if (V == FLOCK_UW && pre_win) {     // window shifted by one row (gym_flock_uw.py:120-123), old rows from registers
+            float* o = p.obs + idx * (size_t)(4 * k);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int s = 0; s < K; ++s)
+                    if (s < k) o[(r + 1) * k + s] = win[r * K + s];
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                if (s < k) o[s] = dist[s];
+        } else {
+            write_obs_t<K>(p, env, i, idx, dist, false);
+        }
         // list entries are (agent id << 16 | slot): ids go to the neighbour list, slots to next step's hints
         int ids[K];
         unsigned hw[4] = {~0u, ~0u, ~0u, ~0u};
@@ -674,15 +849,15 @@ static int pruned_rows_override() {   // FLOCK_PRUNED_ROWS=64|128|256: rows per 
     return v;
 }
 
-template <int K, bool PER>
+template <int V, int K, bool PER>
 static cudaError_t launch_pruned(const Params& p, int sm_count, cudaStream_t s) {
     {   // launch 1 of 2: integrate every agent once, in slot order
-        cudaError_t e = launch_integrate<FLOCK_V2, true>(p, s);
+        cudaError_t e = launch_integrate<V, true>(p, s);
         if (e != cudaSuccess) return e;
     }
     const int rows = pruned_rows_override() ? pruned_rows_override() : choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);
-    flock_step_pruned_kernel<K, PER><<<grid, rows, pruned_smem_bytes(p.N, rows), s>>>(p);
+    flock_step_pruned_kernel<V, K, PER><<<grid, rows, pruned_smem_bytes(p.N, rows), s>>>(p);
     return cudaGetLastError();
 }
 
@@ -766,6 +941,10 @@ __global__ void __launch_bounds__(256) flock_perm_refresh_kernel(const __grid_co
         const int PS = ((N + 31) / 32) * 32;
         uint4* hs = reinterpret_cast<uint4*>(p.hint_slots) + (size_t)env * PS;
         for (int t = threadIdx.x; t < PS; t += blockDim.x) hs[t] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    if (p.far_rows != nullptr) {     // every row is back among its spatial neighbours
+        const int PS = ((N + 31) / 32) * 32;
+        for (int t = threadIdx.x; t < PS; t += blockDim.x) p.far_rows[(size_t)env * PS + t] = 0;
     }
 }
 
@@ -852,21 +1031,13 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_rowwarp_kernel(con
     for (int a = threadIdx.x; a < N; a += blockDim.x) sm.sh[a] = p.h[base + a];
     __syncthreads();
 
+    // per-env sums of the new state, formed once by the integrate pre-pass (see flock_integrate_kernel)
     float comx = 0.f, comy = 0.f, hmean = 0.f;
     if (V == FLOCK_UW) {
-        float sx_ = 0.f, sy_ = 0.f;
-        for (int j = 0; j < N; ++j) {
-            sx_ = sx_ + sm.sx[j];
-            sy_ = sy_ + sm.sy[j];
-        }
-        comx = mean_of_sum(p, sx_);
-        comy = mean_of_sum(p, sy_);
+        comx = mean_of_sum(p, p.env_sums[2 * env]);
+        comy = mean_of_sum(p, p.env_sums[2 * env + 1]);
     }
-    if (V == FLOCK_UWD) {
-        float sh_ = 0.f;
-        for (int j = 0; j < N; ++j) sh_ = sh_ + sm.sh[j];
-        hmean = mean_of_sum(p, sh_);
-    }
+    if (V == FLOCK_UWD) hmean = mean_of_sum(p, p.env_sums[2 * env]);
 
     long long fx_acc = 0;
     bool coll_any = false;
@@ -1232,15 +1403,14 @@ static bool prune_enabled() {   // FLOCK_PRUNE=0: plain all-pairs scan (same res
     }();
     return prune;
 }
-static bool use_pruned(int variant, const Params& p, int sm_count, int tiled_mode) {
-    return variant == FLOCK_V2 && prune_enabled() && p.perm != nullptr && p.sorted_xy != nullptr &&
-           !use_rowwarp(p, sm_count, tiled_mode);
+static bool use_pruned(int /*variant*/, const Params& p, int sm_count, int tiled_mode) {
+    return prune_enabled() && p.perm != nullptr && p.sorted_xy != nullptr && !use_rowwarp(p, sm_count, tiled_mode);
 }
 int tiled_step_launches(int, const Params&, int, int) { return 2; }   // integrate pre-pass + sensing kernel
 
 template <int V, int K, bool PER>
 static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, int tiled_mode, cudaStream_t s) {
-    if (use_pruned(V, p, sm_count, tiled_mode)) return launch_pruned<(K < 4 ? 4 : K), PER>(p, sm_count, s);
+    if (use_pruned(V, p, sm_count, tiled_mode)) return launch_pruned<V, (K < 4 ? 4 : K), PER>(p, sm_count, s);
     {   // launch 1 of 2: integrate every agent once, in place
         cudaError_t e = launch_integrate<V, false>(p, s);
         if (e != cudaSuccess) return e;
@@ -1248,7 +1418,7 @@ static cudaError_t launch_tiled_vkp(const Params& p, int sm_count, int tiled_mod
     if (use_rowwarp(p, sm_count, tiled_mode)) return launch_rowwarp<V, (K < 4 ? 4 : K), PER>(p, sm_count, s);
     const int rows = choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);
-    flock_step_tiled_kernel<V, K, PER><<<grid, rows, tiled_smem_bytes(p.N, rows, V == FLOCK_UWD), s>>>(p);
+    flock_step_tiled_kernel<V, K, PER><<<grid, rows, tiled_smem_bytes(p.N, rows, false), s>>>(p);
     return cudaGetLastError();
 }
 template <int V, bool PER>
@@ -1322,10 +1492,14 @@ cudaError_t tiled_configure(int /*num_agents*/) {
     {
         const size_t bp = pruned_smem_bytes(num_agents, kMaxTileThreads);
         if (bp > 47 * 1024) {
-            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<4, true>, bp);
-            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<8, true>, bp);
-            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<4, false>, bp);
-            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<8, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_V2, 4, true>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_V2, 8, true>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_V2, 4, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_V2, 8, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_UW, 4, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_UW, 8, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_UWD, 4, false>, bp);
+            if (e == cudaSuccess) e = opt_in(flock_step_pruned_kernel<FLOCK_UWD, 8, false>, bp);
         }
         const int G = order_grid_side(num_agents);
         const size_t br = (size_t)G * G * sizeof(int) + (size_t)num_agents * 2 * sizeof(unsigned short);

@@ -80,6 +80,8 @@ TILED = [
     ("v2", 2, 300, 8, 0.3, (0, 400), 50.0),      # 3 tiles per env, ragged last tile
     ("uw", 4, 48, 3, 0.5, (0, 300), 7.0),
     ("uwd", 3, 40, 4, 0.5, (0, 300), 7.0),
+    ("uw", 2, 301, 3, 0.3, (0, 400), 7.0),       # pruned Euclidean path, ragged last tile, N not a power of two (true division)
+    ("uwd", 2, 260, 4, 0.3, (0, 400), 7.0),
     ("v2", 2, 33, 3, 0.5, (0, 200), 30.0),
 ]
 
@@ -356,6 +358,32 @@ def test_large_swarm_config5_bit_exact(mode, auto_reset):
     assert bool((d[..., 1:] >= d[..., :-1]).all()) and bool((d >= 0).all()) and bool((d <= 100.0).all())
     assert not bool((nn == torch.arange(2048, device=nn.device)[None, :, None]).any())
     assert bool(((nn >= 0) & (nn < 2048)).all())
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["thread-per-row-pruned", "warp-per-row-bitonic"])
+@pytest.mark.parametrize("variant,k,cd", [("uw", 3, 0.05), ("uwd", 4, 0.05)])
+def test_large_swarm_uw_uwd_bit_exact(variant, k, cd, mode):
+    """2048-agent uw / uwd swarms (Euclidean metric, gym_flock_uw.py:125-144): the spatially pruned thread-per-row kernel
+    and the warp-per-row kernel against the oracle over 40 steps = two row-order refreshes, with a masked reset in
+    between. The centre of mass / mean heading behind the rewards is the canonical sequential sum, formed once per env
+    by the integrate pre-pass."""
+    env, orc = make_pair(variant, 4, 2048, k, cd, (0, 2000), 7.0, seed=0xFACE, tiled_mode=mode)
+    env.reset()
+    orc.reset(max_attempts=64)
+    compare_all(env, orc, tag="reset:")
+    for t in range(40):
+        a = orc.random_actions()
+        dt = 0.1 if t % 5 else 0.5
+        orc.step(a, dt)
+        env.step(torch.from_numpy(a).cuda(), dt)
+        if t < 3 or t % 4 == 3 or t in (16, 17, 25, 26, 32, 33):
+            compare_all(env, orc, tag=f"step{t}:")
+        if t == 24:
+            mask = np.array([0, 1, 0, 1], np.uint8)
+            orc.reset(mask=mask)
+            env.reset(mask=torch.from_numpy(mask).cuda().bool())
+            compare_all(env, orc, tag="masked reset:")
+    compare_all(env, orc, tag="final:")
 
 
 def test_two_large_swarm_envs_of_different_size_share_a_device():
