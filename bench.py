@@ -509,6 +509,88 @@ def timed_e2e_pipelined(pipe, steps, warmup, device):
     return wall
 
 
+def policy_closed_loops(device, rank):
+    """Compact closed-loop legs for the default line: one fused policy launch + one env launch per step under CUDA-graph
+    replay, one env batch (SURVEY 8f-2 / BASELINE configs[2], configs[3] and the reference's main.py loop)."""
+    import torch
+    from marl_range_flocking_b200 import VecEnv
+    from marl_range_flocking_b200.policies import BatchedActors, BatchedQNet, BatchedRnnActors
+
+    def graph_time(step, inner=50, reps=10):
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                step()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(inner):
+                    step()
+            g.replay()
+            side.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(side)
+            for _ in range(reps):
+                g.replay()
+            ev1.record(side)
+            side.synchronize()
+        torch.cuda.current_stream(device).wait_stream(side)
+        return ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
+
+    def make(name, **over):
+        w = WORKLOADS[name]
+        kw = dict(w.get("env_kw", {}))
+        kw.update(over)
+        env = VecEnv(w["variant"], w["E"] if name != "cfg4" else 4096, w["N"], w["k"], w["cd"], range_start=w["rs"], sensor_range=w["sr"],
+                     seed=0xB0B, env_offset=rank * w["E"], device=device, **w["kw"], **kw)
+        env.reset()
+        return env
+
+    out = {}
+    # recurrent MADDPG actors of main.py on the v2 env (cfg2 shape)
+    env = make("cfg2")
+    E, N = env.num_envs, env.num_particles
+    net = BatchedRnnActors(N, env.k, device=device)
+    net.pack_fused()
+    hidden, abuf = net.init_hidden(E), torch.empty(E, N, 2, device=device)
+
+    def rnn_step():
+        net.forward_fused(env.observation, hidden, out=abuf, hidden_out=hidden)
+        env.step(abuf, DT)
+    t = graph_time(rnn_step)
+    out["rnn_actor_v2_4096x10"] = {"us_per_step": t * 1e6, "agent_steps_per_s": E * N / t,
+                                   "policy": "recurrent MADDPG actors (fce + GRUCell on tcgen05 with split fp16 operands, MLP on tcgen05 bf16)"}
+    del env, net
+    # shared-critic DDPG actors on the uw env (cfg3 shape, window layout: the faster closed loop)
+    env = make("cfg3", obs_layout="window")
+    E, N = env.num_envs, env.num_particles
+    actors = BatchedActors(N, env.obs_hist * env.k, 400, 300, 2, device=device)
+    actors.pack_fused()
+    abuf2 = torch.empty(E, N, 2, device=device)
+
+    def actor_step():
+        actors.forward_fused(env.observation, out=abuf2)
+        env.step(abuf2, DT)
+    t = graph_time(actor_step)
+    out["ddpg_actor_uw_4096x32"] = {"us_per_step": t * 1e6, "agent_steps_per_s": E * N / t,
+                                    "policy": "shared-critic DDPG actors 12-400-300-2 (tcgen05 bf16, LayerNorm / ReLU / tanh fused)"}
+    del env, actors
+    # VDN recurrent Q networks + epsilon-greedy on the discrete env (cfg4 variant at 4096 x 16)
+    env = make("cfg4")
+    E, N = env.num_envs, env.num_particles
+    qn = BatchedQNet(N, env.k, env.k, recurrent=True, device=device)
+    hidden, abuf3 = qn.init_hidden(E), torch.empty(E, N, device=device)
+
+    def vdn_step():
+        qn.sample_action_fused(env.observation, hidden, 0.1, step=0, seed=11, out=abuf3, hidden_out=hidden, counters=env.noise_counters)
+        env.step(abuf3, DT)
+    t = graph_time(vdn_step)
+    out["vdn_qnet_uwd_4096x16"] = {"us_per_step": t * 1e6, "agent_steps_per_s": E * N / t,
+                                   "policy": "recurrent VDN Q networks + per-env epsilon-greedy (tcgen05, split fp16 operands)"}
+    return out
+
+
 def hbm_roofline(w, E, N, per_launch_s, name):
     peak, peak_src = _peaks()
     alg_bytes = E * N * w["bytes"]
@@ -759,6 +841,7 @@ def run_gpu(args, name, w):
             del oenvs, oacts
         if rank == 0:
             extra["configs"] = others
+            extra["policies"] = policy_closed_loops(device, rank)
 
     # optional: closed-loop rollout with the batched per-agent actors of the shared-critic DDPG learner
     # (BASELINE configs[2] "MADDPG actor rollout"; SURVEY 8f-2: the policy, not the env, bounds it)
@@ -833,7 +916,7 @@ def run_gpu(args, name, w):
             extra["actor_rollout"][f"fused_tcgen05_{label}"] = best
 
     # the reference's default main.py loop: v2 env + recurrent MADDPG actors (learners/maddpg_official_rnn/net.py);
-    # closed loop policy + env step with the fused kernels (fp32 GRU front end + tcgen05 MLP) under CUDA-graph replay,
+    # closed loop policy + env step with the fused kernels (GRU front end + tcgen05 MLP) under CUDA-graph replay,
     # next to the same networks as PyTorch baddbmm's
     if rank == 0 and args.policy == "actor" and w["variant"] == "v2":
         from marl_range_flocking_b200.policies import BatchedRnnActors
@@ -857,37 +940,39 @@ def run_gpu(args, name, w):
         net.pack_fused()
         hidden = net.init_hidden(E)
         abuf = torch.empty(E, N, 2, device=device)
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                net.forward_fused(env.observation, hidden, out=abuf, hidden_out=hidden)
-                env.step(abuf, DT)
-            side.synchronize()
-            g = torch.cuda.CUDAGraph()
-            reps, inner = 20, 50
-            with torch.cuda.graph(g, stream=side):
-                for _ in range(inner):
-                    net.forward_fused(env.observation, hidden, out=abuf, hidden_out=hidden)
+        for impl, key, what in (("tc", "fused_closed_loop", "GRU front end on the tensor cores (tcgen05, split fp16 operands)"),
+                                ("fp32", "fused_closed_loop_fp32_front", "fp32 CUDA-core GRU front kernel")):
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    net.forward_fused(env.observation, hidden, out=abuf, hidden_out=hidden, impl=impl)
                     env.step(abuf, DT)
-            g.replay()
-            side.synchronize()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(side)
-            for _ in range(reps):
+                side.synchronize()
+                g = torch.cuda.CUDAGraph()
+                reps, inner = 20, 50
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(inner):
+                        net.forward_fused(env.observation, hidden, out=abuf, hidden_out=hidden, impl=impl)
+                        env.step(abuf, DT)
                 g.replay()
-            ev1.record(side)
-            side.synchronize()
-        torch.cuda.current_stream(device).wait_stream(side)
-        t = ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
-        extra["rnn_actor_rollout"]["fused_closed_loop"] = {
-            "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
-            "policy": f"{N} per-agent recurrent actors {k_obs}-32-GRU32-400-300-2: flock_rnn_actor_forward (fp32 GRU front kernel + "
-                      "tcgen05 MLP kernel) + one env launch per step, CUDA-graph replay"}
+                side.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(side)
+                for _ in range(reps):
+                    g.replay()
+                ev1.record(side)
+                side.synchronize()
+            torch.cuda.current_stream(device).wait_stream(side)
+            t = ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
+            extra["rnn_actor_rollout"][key] = {
+                "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
+                "policy": f"{N} per-agent recurrent actors {k_obs}-32-GRU32-400-300-2: {what} + tcgen05 MLP kernel + one env "
+                          "launch per step, CUDA-graph replay"}
 
     # VDN action selection next to the discrete env (BASELINE configs[3]): the per-agent Q networks of
     # learners/vdn/net.py (recurrent, as the reference trains them) + per-env epsilon-greedy, closed loop with the
-    # env step; fused fp32 kernel (flock_qnet_forward) under CUDA-graph replay (the exploration draws take their step
+    # env step; fused kernels (flock_qnet_forward_tc / flock_qnet_forward) under CUDA-graph replay (the exploration draws take their step
     # from a device counter, so replays do not repeat them) vs the same networks as PyTorch baddbmm's (eager)
     if rank == 0 and w["variant"] == "uwd":
         from marl_range_flocking_b200.policies import BatchedQNet
@@ -899,33 +984,35 @@ def run_gpu(args, name, w):
         abuf = torch.empty(E, N, device=device)
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side), torch.no_grad():
-            def fused_step():
-                qn.sample_action_fused(env.observation, hidden, 0.1, step=0, seed=11, out=abuf, hidden_out=hidden,
-                                       counters=env.noise_counters)
-                env.step(abuf, DT)
-            for _ in range(3):
-                fused_step()
-            side.synchronize()
-            g = torch.cuda.CUDAGraph()
-            reps, inner = 10, 50
-            with torch.cuda.graph(g, stream=side):
-                for _ in range(inner):
+        for impl, key, what in (("tc", "fused_tc", "one fused tensor-core launch (flock_qnet_forward_tc: tcgen05, split fp16 operands, fp32-level accuracy)"),
+                                ("fp32", "fused_fp32", "one fused fp32 CUDA-core launch (flock_qnet_forward)")):
+            with torch.cuda.stream(side), torch.no_grad():
+                def fused_step():
+                    qn.sample_action_fused(env.observation, hidden, 0.1, step=0, seed=11, out=abuf, hidden_out=hidden,
+                                           counters=env.noise_counters, impl=impl)
+                    env.step(abuf, DT)
+                for _ in range(3):
                     fused_step()
-            g.replay()
-            side.synchronize()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(side)
-            for _ in range(reps):
+                side.synchronize()
+                g = torch.cuda.CUDAGraph()
+                reps, inner = 10, 50
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(inner):
+                        fused_step()
                 g.replay()
-            ev1.record(side)
-            side.synchronize()
+                side.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(side)
+                for _ in range(reps):
+                    g.replay()
+                ev1.record(side)
+                side.synchronize()
+            t = ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
+            extra["vdn_rollout"][key] = {
+                "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
+                "policy": f"{N} per-agent recurrent Q networks {k_obs}-64-32-GRU32-{k_obs} + per-env epsilon-greedy, {what}",
+                "launch": "CUDA graph replay (policy launch + env launch per step)"}
         torch.cuda.current_stream(device).wait_stream(side)
-        t = ev0.elapsed_time(ev1) * 1e-3 / (reps * inner)
-        extra["vdn_rollout"]["fused_fp32"] = {
-            "ms_per_step": t * 1e3, "agent_steps_per_s": E * N / t,
-            "policy": f"{N} per-agent recurrent Q networks {k_obs}-64-32-GRU32-{k_obs} + per-env epsilon-greedy, one fused "
-                      "fp32 launch (flock_qnet_forward)", "launch": "CUDA graph replay (policy launch + env launch per step)"}
         if args.policy == "actor":
             state = {"hidden": qn.init_hidden(E)}
 

@@ -24,5 +24,7 @@ for path in sys.argv[1:]:
               "vdn_rollout", "rnn_actor_rollout"):
         if k in d:
             print(k, json.dumps(d[k])[:700])
+    for n, c in d.get("policies", {}).items():
+        print(n, "us %.1f" % c["us_per_step"], "value %.3e" % c["agent_steps_per_s"])
     for n, c in d.get("configs", {}).items():
         print(n, "ms %.5f" % c["ms_per_step"], "value %.3e" % c["value"], "frac %.4f" % c["roofline"]["frac"], "repeats", c["repeats"])
