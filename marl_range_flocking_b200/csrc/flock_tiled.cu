@@ -624,13 +624,13 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
             if (s < k) bound = fmaxf(bound, pair_d2<PER>(x, y, ss_x[hslot[s]], ss_y[hslot[s]], p.B));
         thr = hint_ok ? bound : kFltMax;
     }
-    // Far rows (Euclidean worlds only: the min-image metric does not notice a wrap): an agent that wrapped around since
-    // the last row-order refresh sits a world away from the other rows of its warp. Left in, it would stretch the warp's
-    // bounding box over the whole world (every box passes the gap test) and, on the step of the wrap itself, bring a
-    // threshold of ~B^2 -- one such row made its warp 13x slower, and the kernel as slow as its slowest warp
-    // (118 vs 40 us at 64 x 2048). They are taken out of the shared pass and scanned one at a time by the whole warp below.
+    // Far rows: an agent that wrapped around since the last row-order refresh sits a world away (in coordinates) from
+    // the other rows of its warp. Left in, it stretches the warp's bounding box over the whole world (every box passes the
+    // gap test along that axis) and, in a Euclidean world, brings a threshold of ~B^2 on the step of the wrap -- one such
+    // row made its warp up to 13x slower, and the kernel as slow as its slowest warp (uwd 64 x 2048: 82 vs 42 us).
+    // They are taken out of the shared pass and scanned one at a time by the whole warp below.
     bool far = false;
-    if (!PER && p.far_rows != nullptr && has_row) far = p.far_rows[(size_t)env * PS + slot] != 0;
+    if (p.far_rows != nullptr && has_row) far = p.far_rows[(size_t)env * PS + slot] != 0;
     unsigned far_mask = __ballot_sync(kFull, far);
     if (__popc(far_mask) > 8) {        // a warp of strays (dense wrap-around, stale order after a masked reset): shared pass
         far_mask = 0u;
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         const float xq = __shfl_sync(kFull, x, r), yq = __shfl_sync(kFull, y, r);
         const int sq = __shfl_sync(kFull, slot, r);
         float tb = __shfl_sync(kFull, thr_hint, r);
-        const int nfull = N / kBoxSlots;
+        const int nfull = PER ? 0 : N / kBoxSlots;     // min-image worlds: the hint bound survives a wrap, no need
         for (int bl = lane; bl < nfull; bl += 32) {
             if (bl == sq / kBoxSlots) continue;
             const float4 q = bb[bl];
