@@ -133,6 +133,17 @@ def test_actor_and_qnet_entry_points_validate_arguments_without_a_gpu():
     assert lib.flock_actor_forward(None, None, None, 128, 2, 12, None) == -1
     assert lib.flock_qnet_forward(null10, 1, None, None, None, None, None, 8, 2, 4, 4, 0.1, 0, 0, 0, None, None) == -1
     assert lib.flock_wait_host(None) == -1
+    # tensor-core GRU front ends (flock_gru_tc.cu)
+    assert lib.flock_gru_tc_packed_bytes(0, 5) == 5 * lib.flock_gru_tc_packed_bytes(0, 1) > 0
+    assert lib.flock_gru_tc_packed_bytes(1, 5) > lib.flock_gru_tc_packed_bytes(0, 5)         # the VDN image also holds W2 and the head
+    assert lib.flock_gru_tc_packed_bytes(2, 5) == 0 and lib.flock_gru_tc_packed_bytes(1, 0) == 0
+    assert lib.flock_gru_tc_pack(2, 4, 4, 4, null10, None, None) == -1 and b"mode" in lib.flock_last_error()
+    assert lib.flock_gru_tc_pack(1, 4, 17, 4, null10, None, None) == -1 and b"n_obs" in lib.flock_last_error()
+    assert lib.flock_gru_tc_pack(1, 4, 4, 17, null10, None, None) == -1 and b"n_actions" in lib.flock_last_error()
+    assert lib.flock_gru_tc_pack(0, 4, 4, 0, null10, None, None) == -1                       # NULL parameters / image
+    assert lib.flock_qnet_forward_tc(None, None, None, None, None, None, 8, 2, 4, 4, 0.1, 0, 0, 0, None, None) == -1
+    assert lib.flock_rnn_actor_forward_tc(None, None, None, None, None, None, 8, 2, 4, None, 0.15, 0.0, 0.2, 0.01, 0, 0, 0,
+                                          None, None) == -1
 
 
 class _RnnActor(nn.Module):                                # layer names = the reference's state_dict keys (net.py:32-38)
