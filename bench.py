@@ -761,6 +761,47 @@ def run_gpu(args, name, w):
         torch.cuda.synchronize(device)
         return ev0.elapsed_time(ev1) * 1e-3 / reps
 
+    # independent env batches in flight on several streams (informational: what a trainer with several replicas per GPU
+    # gets -- the 4096-env launch fills 0.23 waves of the machine, so launches of different batches overlap; the headline
+    # above is ONE stream). Same ring, same kernels, S graphs replayed concurrently, each over its own part of the ring.
+    if rank == 0 and not envs[0].tiled and len(envs) >= 8:
+        S = 4
+        per = len(envs) // S
+        streams = [torch.cuda.Stream(device=device) for _ in range(S)]
+        graphs = []
+        n_steps = max(per, (256 // per) * per)
+        for si, st in enumerate(streams):
+            sub_e, sub_a = envs[si * per:(si + 1) * per], acts[si * per:(si + 1) * per]
+            st.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(st):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    for s_ in range(n_steps):
+                        sub_e[s_ % per].step(sub_a[s_ % per][(s_ // per) & 1], DT)
+                g.replay()
+            graphs.append(g)
+        torch.cuda.synchronize(device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 8
+        ev0.record()
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream(device))
+        for _ in range(reps):
+            for st, g in zip(streams, graphs):
+                with torch.cuda.stream(st):
+                    g.replay()
+        for st in streams:
+            torch.cuda.current_stream(device).wait_stream(st)
+        ev1.record()
+        torch.cuda.synchronize(device)
+        tc_ = ev0.elapsed_time(ev1) * 1e-3 / (reps * S * n_steps)
+        gb = E * N * w["bytes"] / tc_ / 1e9
+        extra["concurrent_batches"] = {"streams": S, "ms_per_step": tc_ * 1e3, "agent_steps_per_s_per_gpu": E * N / tc_,
+                                       "achieved_GBps": gb, "frac_of_hbm_peak": gb / peak_hbm,
+                                       "note": f"{S} independent env batches in flight ({S} streams, one CUDA graph each over its own "
+                                               "quarter of the ring > L2); per-step time = region / all steps; not the headline"}
+        del graphs
+
     # what a real rollout sees: ONE env batch stepped over and over, its state resident in L2 (informational: the
     # headline above cycles over a ring larger than L2, as the timing rules require)
     if rank == 0:

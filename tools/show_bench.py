@@ -20,7 +20,7 @@ for path in sys.argv[1:]:
         print("e2e %.3e" % e["value"], e.get("value_is"), "sync %.3e" % e.get("sync_per_step", {}).get("value", 0), "pipe %.3e" % e.get("pipelined", {}).get("value", 0))
     if "cpu_baseline" in d:
         print("cpu", json.dumps(d["cpu_baseline"])[:1200])
-    for k in ("l2_resident_single_batch", "step_n_persistent", "rollout_n_streamed", "large_batch", "stats_allreduce", "clocks", "actor_rollout",
+    for k in ("concurrent_batches", "l2_resident_single_batch", "step_n_persistent", "rollout_n_streamed", "large_batch", "stats_allreduce", "clocks", "actor_rollout",
               "vdn_rollout", "rnn_actor_rollout"):
         if k in d:
             print(k, json.dumps(d[k])[:700])
