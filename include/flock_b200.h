@@ -323,7 +323,7 @@ FLOCK_API int flock_qnet_forward(const float *const *params, int recurrent, cons
                        const flock_noise_counters_t *counters, void *stream);
 
 /* The recurrent front ends of the two policies above ON THE TENSOR CORES (csrc/flock_gru_tc.cu): every layer is a
- * tcgen05.mma over tiles of 128 env rows with split bf16 operands (v = hi + lo, four MMAs per product: fp32-level
+ * tcgen05.mma over tiles of 128 env rows with split fp16 operands (v = hi + lo, three MMAs per product: fp32-level
  * accuracy, hidden state and Q-values within 1e-5 of the fp32 modules), accumulators in TMEM, activations never leave
  * the SM. `mode` 0 = recurrent MADDPG actor front (fce + GRUCell, net.py:53-58), 1 = recurrent VDN QNet (net.py:27-58).
  *   flock_gru_tc_packed_bytes / flock_gru_tc_pack: packed parameter image; `params` as in flock_rnn_actor_forward

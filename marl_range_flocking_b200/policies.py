@@ -209,7 +209,7 @@ class BatchedRnnActors(torch.nn.Module):
         front = [t.detach().float().contiguous() for t in (self.we, self.be, self.w_ih, self.b_ih, self.w_hh, self.b_hh)]
         self._packed, self._packed_srcs = packed, srcs
         self._front, self._front_ptrs = front, (ctypes.c_void_p * 6)(*[t.data_ptr() for t in front])
-        # the same front end for the tensor-core kernel (flock_gru_tc.cu): split-bf16 weight images
+        # the same front end for the tensor-core kernel (flock_gru_tc.cu): split-fp16 weight images
         self._front_packed = None
         if self.hidden_rnn == 32 and self.input_dims <= 16:
             fp = torch.empty(lib.flock_gru_tc_packed_bytes(0, self.num_agents), dtype=torch.uint8, device=self.we.device)
@@ -226,7 +226,7 @@ class BatchedRnnActors(torch.nn.Module):
                       step: int = 0, env_offset: int = 0, counters=None, impl: str = "tc") -> Tuple[torch.Tensor, torch.Tensor]:
         """`forward` in two kernel launches: fce + GRUCell, then the 32-400-300-2 MLP on the tensor cores (bf16
         operands, fp32 accumulation). `impl="tc"` (default): the front end runs on the tensor cores too, with split
-        bf16 operands (fp32-level accuracy, hidden state within 1e-5 of the fp32 module; csrc/flock_gru_tc.cu);
+        fp16 operands (fp32-level accuracy, hidden state within 1e-5 of the fp32 module; csrc/flock_gru_tc.cu);
         `impl="fp32"`: the CUDA-core front kernel. `hidden_out` may be `hidden`.
         With `ou_state` ((E, N, 2) float32, zeros after a reset) the learner's Ornstein-Uhlenbeck exploration noise
         (agent.py:61, utils.py:43-47) is added in the same launch, one process per (env, agent, action). Pass
@@ -377,7 +377,7 @@ class BatchedQNet(torch.nn.Module):
             ptrs = (ctypes.c_void_p * 10)(*([t.data_ptr() for t in srcs] + [None] * (10 - len(srcs))))
             packed = None
             if self.recurrent and self.hx_size == 32 and n_obs <= 16 and A <= 16 and self.w1.shape[2] == 64:
-                # tensor-core path (csrc/flock_gru_tc.cu): split-bf16 weight images, re-packed after every update
+                # tensor-core path (csrc/flock_gru_tc.cu): split-fp16 weight images, re-packed after every update
                 packed = torch.empty(lib.flock_gru_tc_packed_bytes(1, N), dtype=torch.uint8, device=x.device)
                 with torch.cuda.device(x.device):
                     _lib.check(lib.flock_gru_tc_pack(1, N, n_obs, A, ptrs, packed.data_ptr(), torch.cuda.current_stream().cuda_stream))
@@ -405,7 +405,7 @@ class BatchedQNet(torch.nn.Module):
         return q, h_out, act
 
     def forward_fused(self, obs: torch.Tensor, hidden: Optional[torch.Tensor] = None, impl: str = "tc") -> Tuple[torch.Tensor, torch.Tensor]:
-        """`forward` in one kernel launch. `impl="tc"` (default, recurrent nets): tcgen05 MMAs with split bf16 operands
+        """`forward` in one kernel launch. `impl="tc"` (default, recurrent nets): tcgen05 MMAs with split fp16 operands
         (fp32-level accuracy: within 1e-5 of the fp32 module); `impl="fp32"`: the CUDA-core kernel (same arithmetic as
         PyTorch up to summation order; also what non-recurrent nets use)."""
         q, h, _ = self._fused(obs, hidden, True, False, 0.0, 0, 0, 0, impl=impl)

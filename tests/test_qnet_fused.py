@@ -18,7 +18,7 @@ def _net(N, n_obs, A, rec, seed, dev):
     return BatchedQNet(N, n_obs, A, recurrent=rec, device=dev)
 
 
-@pytest.mark.parametrize("impl", ["tc", "fp32"])      # tensor-core kernel with split bf16 operands / fp32 CUDA-core kernel
+@pytest.mark.parametrize("impl", ["tc", "fp32"])      # tensor-core kernel with split fp16 operands / fp32 CUDA-core kernel
 @pytest.mark.parametrize("E,N,n_obs,A,rec", [(8192, 16, 4, 4, True), (8192, 16, 4, 4, False), (300, 5, 8, 8, True),
                                              (257, 3, 3, 5, False), (1, 2, 4, 4, True), (100, 7, 16, 16, True),
                                              (129, 4, 1, 2, True)])

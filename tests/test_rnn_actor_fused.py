@@ -37,7 +37,7 @@ def _emulate(a, obs, hidden):
     return torch.cat([lin, ang], dim=-1).transpose(0, 1).contiguous(), h
 
 
-@pytest.mark.parametrize("impl", ["tc", "fp32"])      # front end: tensor cores with split bf16 operands / fp32 CUDA cores
+@pytest.mark.parametrize("impl", ["tc", "fp32"])      # front end: tensor cores with split fp16 operands / fp32 CUDA cores
 @pytest.mark.parametrize("E,N,n_obs", [(128, 1, 4), (300, 5, 4), (4096, 10, 4), (77, 3, 8), (1, 2, 12), (4096, 32, 16)])
 def test_fused_rnn_actor_matches_pytorch(E, N, n_obs, impl):
     dev = torch.device("cuda:0")
