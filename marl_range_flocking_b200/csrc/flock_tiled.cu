@@ -631,6 +631,33 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     // They are taken out of the shared pass and scanned one at a time by the whole warp below.
     bool far = false;
     if (p.far_rows != nullptr && has_row) far = p.far_rows[(size_t)env * PS + slot] != 0;
+    {
+        // ... and rows whose THRESHOLD is an outlier in their warp (more than 4x the warp's smallest in radius): the old
+        // neighbours of an agent that has just wrapped (their hint bound jumps to ~B^2 in a Euclidean world), rows without a
+        // valid hint, and genuinely isolated agents (uw draws its swarm in a quarter of the world: whoever wraps sits alone on
+        // the far side, 1000 away from everyone; after a refresh such agents collect in the first / last slots). In the
+        // shared pass one such row makes all 32 lanes evaluate every box (measured: uw 64 x 2048, 1-5 isolated rows in the
+        // last tile of each env: that CTA 190 k cycles against a mean of 33 k, the kernel 95 instead of 50 us).
+        // The yardstick is the warp's MEDIAN threshold (radix select on sign | exponent | two mantissa bits with ballots,
+        // ~70 instructions per warp): the smallest threshold of a warp is no yardstick -- k-th-neighbour distances of
+        // uniformly scattered agents spread over more than 10x in d2 within 32 rows for k = 3 or 4 -- while 8x the median
+        // is exceeded by a normal row with probability ~1e-7.
+        const bool cand_row = has_row && !far;
+        const unsigned tkey = __float_as_uint(fmaxf(thr, 0.0f)) >> 21;       // 11 bits, monotone in thr
+        const unsigned act = __ballot_sync(kFull, cand_row);
+        int need = (__popc(act) + 1) >> 1;
+        unsigned prefix = 0u;
+#pragma unroll
+        for (int b = 10; b >= 0; --b) {
+            const unsigned zero = __ballot_sync(kFull, cand_row && (tkey >> (b + 1)) == (prefix >> (b + 1)) && ((tkey >> b) & 1u) == 0u);
+            const int c0 = __popc(zero);
+            if (need > c0) {
+                need -= c0;
+                prefix |= 1u << b;
+            }
+        }
+        far = far || (cand_row && act != 0u && tkey > prefix + 12u);          // 12 quarter-octaves = 8x in d2
+    }
     unsigned far_mask = __ballot_sync(kFull, far);
     if (__popc(far_mask) > 8) {        // a warp of strays (dense wrap-around, stale order after a masked reset): shared pass
         far_mask = 0u;
@@ -720,11 +747,15 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         const float xq = __shfl_sync(kFull, x, r), yq = __shfl_sync(kFull, y, r);
         const int sq = __shfl_sync(kFull, slot, r);
         float tb = __shfl_sync(kFull, thr_hint, r);
-        const int nfull = PER ? 0 : N / kBoxSlots;     // min-image worlds: the hint bound survives a wrap, no need
+        const int nfull = N / kBoxSlots;
         for (int bl = lane; bl < nfull; bl += 32) {
             if (bl == sq / kBoxSlots) continue;
             const float4 q = bb[bl];
-            const float ddx = fmaxf(fabsf(xq - q.x), fabsf(xq - q.y)), ddy = fmaxf(fabsf(yq - q.z), fabsf(yq - q.w));
+            float ddx = fmaxf(fabsf(xq - q.x), fabsf(xq - q.y)), ddy = fmaxf(fabsf(yq - q.z), fabsf(yq - q.w));
+            if (PER) {      // a min-image distance never exceeds the direct one, nor B/2
+                ddx = fminf(ddx, 0.5f * p.B);
+                ddy = fminf(ddy, 0.5f * p.B);
+            }
             tb = fminf(tb, fmaf(ddy, ddy, ddx * ddx) * 1.0001f + 1.0e-30f);
         }
         tb = warp_min(tb);
