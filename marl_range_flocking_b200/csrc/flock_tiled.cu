@@ -657,6 +657,21 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
             }
         }
         far = far || (cand_row && act != 0u && tkey > prefix + 12u);          // 12 quarter-octaves = 8x in d2
+        // ... and rows that lie far from the warp's patch without having wrapped: agents that diffused out of the swarm's
+        // bulk are sorted into distant cells of the row order and end up among unrelated rows (measured, uw: two such rows in
+        // the last warp of an env stretched its bounding box over the whole swarm -> every box opened, 119 k cycles against
+        // a mean of 39 k). Yardstick: distance from the warp's mean position against 20 median neighbour radii (a patch of
+        // 32 rows is 4-6 such radii across).
+        float sx = cand_row ? x : 0.0f, sy = cand_row ? y : 0.0f;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            sx += __shfl_xor_sync(kFull, sx, m);
+            sy += __shfl_xor_sync(kFull, sy, m);
+        }
+        const float inv_cnt = 1.0f / (float)max(__popc(act), 1);
+        const float ddx = x - sx * inv_cnt, ddy = y - sy * inv_cnt;
+        const float med_thr = fmaxf(__uint_as_float(prefix << 21), 1.0e-6f * p.B * p.B);
+        far = far || (cand_row && (ddx * ddx + ddy * ddy) > 400.0f * med_thr);
     }
     unsigned far_mask = __ballot_sync(kFull, far);
     if (__popc(far_mask) > 8) {        // a warp of strays (dense wrap-around, stale order after a masked reset): shared pass
