@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     bool far = false;
     if (p.far_rows != nullptr && has_row) far = p.far_rows[(size_t)env * PS + slot] != 0;
     {
-        // ... and rows whose THRESHOLD is an outlier in their warp (more than 4x the warp's smallest in radius): the old
+        // ... and rows whose THRESHOLD is an outlier in their warp (more than 8x the warp's median d2): the old
         // neighbours of an agent that has just wrapped (their hint bound jumps to ~B^2 in a Euclidean world), rows without a
         // valid hint, and genuinely isolated agents (uw draws its swarm in a quarter of the world: whoever wraps sits alone on
         // the far side, 1000 away from everyone; after a refresh such agents collect in the first / last slots). In the
