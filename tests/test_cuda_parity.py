@@ -386,6 +386,32 @@ def test_large_swarm_uw_uwd_bit_exact(variant, k, cd, mode):
     compare_all(env, orc, tag="final:")
 
 
+@pytest.mark.parametrize("variant,N,k,layout", [("uw", 301, 3, "window"), ("uw", 301, 3, "ring"), ("uwd", 260, 4, "window")])
+def test_dense_euclidean_swarm_with_auto_reset_bit_exact(variant, N, k, layout):
+    """Large uw / uwd swarms in a small world: constant wrap-around (far-row flags, poisoned hints), collisions that end
+    episodes, in-launch sequence step -> masked auto-reset (hints and flags of the restarted envs dropped), 48 steps =
+    three row-order refreshes; uw on both observation layouts. Pruned thread-per-row kernel against the oracle."""
+    kw = dict(obs_layout=layout) if variant == "uw" else {}
+    env, orc = make_pair(variant, 3, N, k, 0.6, (0, 120), 7.0, seed=0xD0D0, tiled_mode=1, auto_reset=True, max_reset_attempts=8, **kw)
+    env.reset()
+    orc.reset(max_attempts=8)
+    restarted = 0
+    for t in range(48):
+        a = orc.random_actions()
+        dt = 0.1 if t % 4 else 0.4
+        orc.step(a, dt)
+        restarted += int(orc.env_done.sum())
+        orc.reset(mask=orc.env_done.copy(), keep_outputs=True, max_attempts=8)
+        env.step(torch.from_numpy(a).cuda(), dt)
+        torch.cuda.synchronize()
+        assert_same(f"step{t}:x", env.x, orc.x)
+        assert_same(f"step{t}:reward", env.reward[..., 0], orc.reward)
+        assert_same(f"step{t}:env_done", env.dones[1].to(torch.uint8), orc.env_done)
+        obs = env.observation
+        assert_same(f"step{t}:obs", obs, orc.obs.reshape(obs.shape))
+    assert restarted > 0 and env.stats()["episodes"] == int(orc.stats[0]) > 0
+
+
 def test_two_large_swarm_envs_of_different_size_share_a_device():
     """The dynamic shared-memory opt-in is per FUNCTION, not per handle: a smaller large-swarm env created after
     a bigger one must not lower the limit under it (8192 agents need > 48 KB). Both are stepped alternately and
@@ -408,7 +434,8 @@ def test_two_large_swarm_envs_of_different_size_share_a_device():
     assert bool(torch.isfinite(d).all()) and bool((d[..., 1:] >= d[..., :-1]).all())
 
 
-@pytest.mark.parametrize("variant,E,N,k", [("v2", 64, 10, 4), ("uw", 32, 32, 3), ("uwd", 48, 16, 4), ("v2", 2, 96, 8)])
+@pytest.mark.parametrize("variant,E,N,k", [("v2", 64, 10, 4), ("uw", 32, 32, 3), ("uwd", 48, 16, 4), ("v2", 2, 96, 8),
+                                           ("uw", 3, 200, 3), ("uwd", 3, 130, 4)])   # tiled Euclidean: stale hints / far-row flags after the restore
 def test_get_state_set_state_round_trip_continues_bit_equal(variant, E, N, k):
     """Checkpoint / restore: a twin env that receives `get_state()` of a running env must continue
     with identical bits -- state, observation window, episode counters, Philox epochs, statistics."""
