@@ -272,8 +272,12 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     float* sx = s_stage[wib][0];
     float* sy = s_stage[wib][1];
     float* sh = s_stage[wib][2];
-    const int N = p.N, G = p.G, k = p.k, sstride = p.sstride;
-    const LaneMap m = lane_map(lane, N, G, p.g_magic);
+    // The unrolled instantiations serve the BASELINE swarm sizes EXACTLY (NJ4 = 3: N = 10, 4: N = 16, 8: N = 32; other sizes
+    // take the generic loop, NJ4 = 0): N, the envs per warp, the stride and the lane map are compile-time constants there,
+    // which removes ~40 instructions of the one-task-per-warp preamble and the tail guards of the pair loop.
+    constexpr int NX = NJ4 == 3 ? 10 : NJ4 == 4 ? 16 : NJ4 == 8 ? 32 : 0;
+    const int N = NX > 0 ? NX : p.N, G = NX > 0 ? 32 / NX : p.G, k = p.k, sstride = NX > 0 ? 4 * NJ4 : p.sstride;
+    const LaneMap m = lane_map(lane, N, G, NX > 0 ? (65536 + NX - 1) / NX : p.g_magic);
     const int num_tasks = p.num_tasks;
     const int warps_total = gridDim.x * kSmallWarps;
     const int nsteps = MULTI ? p.num_steps : 1;
@@ -704,15 +708,16 @@ cudaError_t launch_step_small_vkpni(const Params& p, int mode, int sm_count, cud
     return cudaLaunchKernelEx(&cfg, flock_step_small_kernel<V, K, PER, kModeStep, NJ4, IDX>, p);
 }
 
-// unrolled pair loops for the strides of the BASELINE configs (N = 9..12, 13..16, 29..32)
+// unrolled pair loops for the swarm sizes of the BASELINE configs (N = 10, 16, 32), the generic loop for all others
 template <int V, int K, bool PER, bool IDX>
 cudaError_t launch_step_small_vkpi(const Params& p, int mode, int sm_count, cudaStream_t s) {
     switch (p.sstride) {
-        case 12: return launch_step_small_vkpni<V, K, PER, 3, IDX>(p, mode, sm_count, s);
-        case 16: return launch_step_small_vkpni<V, K, PER, 4, IDX>(p, mode, sm_count, s);
-        case 32: return launch_step_small_vkpni<V, K, PER, 8, IDX>(p, mode, sm_count, s);
-        default: return launch_step_small_vkpni<V, K, PER, 0, IDX>(p, mode, sm_count, s);
+        case 12: if (p.N == 10 && p.G == 3) return launch_step_small_vkpni<V, K, PER, 3, IDX>(p, mode, sm_count, s); break;
+        case 16: if (p.N == 16 && p.G == 2) return launch_step_small_vkpni<V, K, PER, 4, IDX>(p, mode, sm_count, s); break;
+        case 32: if (p.N == 32 && p.G == 1) return launch_step_small_vkpni<V, K, PER, 8, IDX>(p, mode, sm_count, s); break;
+        default: break;
     }
+    return launch_step_small_vkpni<V, K, PER, 0, IDX>(p, mode, sm_count, s);
 }
 
 // one explicit instantiation of this per translation unit (flock_small_<variant>.cu)

@@ -73,6 +73,8 @@ SMALL = [
     ("uwd", 64, 16, 4, 0.5, (0, 100), 7.0),      # BASELINE config 4 parameters
     ("uwd", 33, 8, 4, 3.0, (0, 50), 7.0),        # VDN trainer parameters
     ("uwd", 20, 25, 6, 0.5, (0, 100), 7.0),
+    ("uw", 20, 30, 3, 0.5, (0, 200), 7.0),       # stride 32 but N < 32: the generic loop, not the unrolled N == 32 kernel
+    ("v2", 9, 31, 8, 0.5, (0, 100), 30.0),
 ]
 TILED = [
     ("v2", 5, 64, 8, 0.5, (0, 200), 30.0),       # TMA path (N % 4 == 0)
