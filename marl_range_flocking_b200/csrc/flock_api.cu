@@ -50,6 +50,7 @@ struct flock_env {
     unsigned short* hint_slots;   // pruned path: last step's neighbour slots per row
     float* env_sums;              // tiled path, uw / uwd: per-env sums behind the centre of mass / mean heading
     uint8_t* far_rows;            // pruned path: rows that left their spatial neighbourhood (wrap-around) since the last refresh
+    unsigned long long* timeline; // -DFLOCK_TIMELINE developer builds only
     uint32_t perm_age;            // steps since the row order was refreshed
     unsigned long long* pair_counter;   // device counter of row x neighbour pairs evaluated by the pruned kernel
     const void* zc_host[5];       // last host buffers seen by flock_step_host and their device aliases
@@ -133,6 +134,9 @@ Params make_params(const flock_env* e, float dt) {
     p.hint_slots = e->hint_slots;
     p.env_sums = e->env_sums;
     p.far_rows = e->far_rows;
+#ifdef FLOCK_TIMELINE
+    p.timeline = e->timeline;
+#endif
     return p;
 }
 
@@ -323,6 +327,13 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
     err = cudaMalloc(&e->stage_actions, e->action_floats * sizeof(float));
     if (err == cudaSuccess && cfg->variant == FLOCK_UWD)
         err = cudaMalloc(&e->stage_noise, (size_t)cfg->num_envs * cfg->num_agents * 2 * sizeof(float));
+#ifdef FLOCK_TIMELINE
+    if (err == cudaSuccess) {
+        const size_t bytes = (size_t)flock::kTimelineSlots * flock::kTimelineCtas * sizeof(unsigned long long);
+        err = cudaMalloc(&e->timeline, bytes);
+        if (err == cudaSuccess) err = cudaMemset(e->timeline, 0, bytes);
+    }
+#endif
     if (err == cudaSuccess && e->path == 1) err = flock::tiled_configure(cfg->num_agents);
     if (err == cudaSuccess && e->path == 1) {
         err = cudaMalloc(&e->tile_scratch, (size_t)cfg->num_envs * 2 * sizeof(unsigned int));
@@ -353,6 +364,7 @@ int flock_create(const flock_cfg_t* cfg, int device, flock_env_t** out) {
         cudaFree(e->hint_slots);
         cudaFree(e->env_sums);
         cudaFree(e->far_rows);
+        cudaFree(e->timeline);
         cudaFree(e->pair_counter);
         cudaFree(e->stage_actions);
         cudaFree(e->stage_noise);
@@ -376,6 +388,7 @@ void flock_destroy(flock_env_t* e) {
     cudaFree(e->hint_slots);
     cudaFree(e->env_sums);
     cudaFree(e->far_rows);
+    cudaFree(e->timeline);
     cudaFree(e->pair_counter);
     if (e->host_event_live) cudaEventDestroy(e->host_event);
     delete e;
@@ -880,6 +893,19 @@ int flock_rnn_actor_forward_tc(const void* packed_mlp, const void* packed_front,
                                           ou_state, theta, mu, sigma, dt, seed, step, env_offset, noise_counters(counters), s);
     return err == cudaSuccess ? FLOCK_OK : cuda_fail(err, "rnn actor MLP kernel launch");
 }
+
+#ifdef FLOCK_TIMELINE
+// developer build only (tools/cta_timeline.py): copies the first n CTA records of the handle's timeline out and clears it
+extern "C" __attribute__((visibility("default"))) int flock_debug_timeline(flock_env* e, unsigned long long* out, int n) {
+    if (e == nullptr || e->timeline == nullptr || out == nullptr || n < 1 || n > flock::kTimelineCtas) return FLOCK_E_INVALID;
+    const size_t bytes = (size_t)flock::kTimelineSlots * flock::kTimelineCtas * sizeof(unsigned long long);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err == cudaSuccess)
+        err = cudaMemcpy(out, e->timeline, (size_t)n * flock::kTimelineSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess) err = cudaMemset(e->timeline, 0, bytes);
+    return err == cudaSuccess ? FLOCK_OK : FLOCK_E_CUDA;
+}
+#endif
 
 int flock_debug_sincos(const float* h, int n, float* sn, float* cs, void* stream) {
     cudaError_t err = flock::launch_debug_sincos(h, n, sn, cs, static_cast<cudaStream_t>(stream));

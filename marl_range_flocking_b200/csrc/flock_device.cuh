@@ -62,6 +62,9 @@ struct Params {
     float* sorted_xy;             // pruned path: per env x | y by slot, boxes, agent ids (3 * PS floats)
     unsigned short* hint_slots;   // pruned path: [E][PS][8] slots of last step's neighbours (0xffff: none)
     uint8_t* far_rows;            // pruned path: [E][PS] rows (by slot) that wrapped around the world since the last row-order refresh
+#ifdef FLOCK_TIMELINE
+    unsigned long long* timeline; // developer build: per-CTA timeline records (see below)
+#endif
     float* env_sums;              // tiled path, uw / uwd: [E][2] sequential (agent order) sums of the NEW x, y (uw) or h (uwd)
     // host-call path: device-visible HOST mirrors of the step results (zero-copy), nullable
     float* m_obs;
@@ -93,6 +96,25 @@ __device__ __forceinline__ float* ring_row(const Params& p, int env, int slot, i
 // the programmatic-serialization attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+
+// Developer instrumentation (compiled in only with -DFLOCK_TIMELINE, see tools/cta_timeline.py): per-CTA wall-clock
+// timeline of a kernel -- %globaltimer at entry / after griddepcontrol.wait / at exit, SM id, and a few per-kernel
+// counters -- written to Params::timeline (allocated by flock_create in such a build) and read back through
+// flock_debug_timeline().
+#ifdef FLOCK_TIMELINE
+constexpr int kTimelineSlots = 8, kTimelineCtas = 65536;      // Params::timeline: [kTimelineCtas][kTimelineSlots]
+__device__ __forceinline__ unsigned long long timeline_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned timeline_smid() {
+    unsigned s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Canonical transcendental functions (same DEFINITION as oracle/flock_oracle.c, separate code).

@@ -267,6 +267,9 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     constexpr bool MIRROR = MODE == kModeMirror;
     constexpr bool AUTORESET = MODE == kModeAutoReset;
     constexpr bool NOISE = MODE == kModeNoise;
+#ifdef FLOCK_TIMELINE
+    const unsigned long long tl_entry = timeline_now();
+#endif
     __shared__ __align__(16) float s_stage[kSmallWarps][3][kSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* sx = s_stage[wib][0];
@@ -282,6 +285,9 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     const int warps_total = gridDim.x * kSmallWarps;
     const int nsteps = MULTI ? p.num_steps : 1;
     pdl_wait_prior_grid();
+#ifdef FLOCK_TIMELINE
+    const unsigned long long tl_go = timeline_now();
+#endif
 
     const int GN = G * N;
     const unsigned EN = (unsigned)p.E * (unsigned)N;
@@ -547,6 +553,15 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             if (__any_sync(0xffffffffu, want)) reset_groups<K>(p, m, sx, sy, env, idx, want, true);
         }
     }
+#ifdef FLOCK_TIMELINE
+    if (threadIdx.x == 0 && blockIdx.x < kTimelineCtas) {
+        unsigned long long* d = p.timeline + (size_t)blockIdx.x * kTimelineSlots;
+        d[0] = tl_entry;
+        d[1] = tl_go;
+        d[2] = timeline_now();
+        d[3] = timeline_smid();
+    }
+#endif
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -65,7 +65,8 @@ __host__ __device__ __forceinline__ int padded_agents(int N) { return ((N + 3) &
 
 // warp-shuffle bitonic top-k merge of 32 per-lane sorted lists (defined with the warp-per-row kernel below)
 template <int K>
-__device__ __forceinline__ void warp_bitonic_topk(unsigned long long (&key)[K]);
+__device__ __forceinline__ void warp_bitonic_topk(unsigned long long (&key)[K], int width = 32);
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src);
 
 // shared-memory carve-up: sx | sy | [sh] | candidate buffer. sh (headings) exists only where the
 // kernel needs every agent's heading afterwards (uwd mean heading, reset).
@@ -533,8 +534,13 @@ static cudaError_t launch_integrate(const Params& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// (min 4 CTAs of 256 threads per SM = at most 64 registers: the rare multi-row pass below must not cost the common path its occupancy)
 template <int V, int K, bool PER>
-__global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kMaxTileThreads, 4) flock_step_pruned_kernel(const __grid_constant__ Params p) {
+#ifdef FLOCK_TIMELINE
+    const unsigned long long tl_entry = timeline_now();
+    const long long tl_c0 = clock64();
+#endif
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
     constexpr unsigned kFull = 0xffffffffu;
@@ -762,14 +768,37 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
     // top-k on (d2, agent id) keys. Threshold: the smaller of the hint bound and a bound from the boxes themselves -- a
     // complete box other than the row's own holds 8 >= k other agents, all within the largest distance from the point to
     // the box's corners -- so the step of the wrap (hint bound ~B^2) is pruned as well. Exact like the shared pass.
+#ifdef FLOCK_TIMELINE
+    const long long tl_c1 = clock64();
+    const int tl_nfar = __popc(far_mask);
+#endif
+    // Up to four such rows are scanned at a time, one per group of 32 / 16 / 8 lanes (a row costs ~1000 warp-instructions
+    // of mostly fixed work -- box tests, the butterfly merge -- so a warp with six of them spent 40 k cycles here).
     while (far_mask != 0u) {
-        const int r = __ffs(far_mask) - 1;
+        const int left = __popc(far_mask);
+        // lanes per row (k > 4: one row at a time -- the 8-entry lists make the grouped form cost registers and time, and
+        // measured on cfg5, which has few such rows, it lost 2 us)
+        const int gs = K > 4 ? 32 : (left >= 4 ? 8 : (left >= 2 ? 16 : 32));
+        const int ngroups = 32 / gs, grp = lane / gs, li = lane - grp * gs;
+        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;                              // scalars, not an array: no local memory
+        r0 = __ffs(far_mask) - 1;
         far_mask &= far_mask - 1u;
+        if (ngroups >= 2) {
+            r1 = __ffs(far_mask) - 1;
+            far_mask &= far_mask - 1u;
+        }
+        if (ngroups >= 4) {
+            r2 = __ffs(far_mask) - 1;
+            far_mask &= far_mask - 1u;
+            r3 = __ffs(far_mask) - 1;
+            far_mask &= far_mask - 1u;
+        }
+        const int r = grp == 0 ? r0 : (grp == 1 ? r1 : (grp == 2 ? r2 : r3));   // the row this lane works for
         const float xq = __shfl_sync(kFull, x, r), yq = __shfl_sync(kFull, y, r);
         const int sq = __shfl_sync(kFull, slot, r);
         float tb = __shfl_sync(kFull, thr_hint, r);
         const int nfull = N / kBoxSlots;
-        for (int bl = lane; bl < nfull; bl += 32) {
+        for (int bl = li; bl < nfull; bl += gs) {
             if (bl == sq / kBoxSlots) continue;
             const float4 q = bb[bl];
             float ddx = fmaxf(fabsf(xq - q.x), fabsf(xq - q.y)), ddy = fmaxf(fabsf(yq - q.z), fabsf(yq - q.w));
@@ -779,10 +808,14 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
             }
             tb = fminf(tb, fmaf(ddy, ddy, ddx * ddx) * 1.0001f + 1.0e-30f);
         }
-        tb = warp_min(tb);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {                              // minimum over the row's lane group
+            const float o = __shfl_xor_sync(kFull, tb, m);
+            if (m < gs) tb = fminf(tb, o);
+        }
         TopK<K> tq;
         tq.init();
-        for (int bl = lane; bl < nbox; bl += 32) {
+        for (int bl = li; bl < nbox; bl += gs) {
             const float4 q = bb[bl];
             const float gx = axis_gap<PER>(xq, xq, q.x, q.y, p.B, slack);
             const float gy = axis_gap<PER>(yq, yq, q.z, q.w, p.B, slack);
@@ -799,16 +832,45 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         unsigned long long key[K];
 #pragma unroll
         for (int s = 0; s < K; ++s) key[s] = ((unsigned long long)__float_as_uint(tq.d[s]) << 32) | (unsigned)tq.idx[s];
-        warp_bitonic_topk<K>(key);       // every lane ends with the merged list
-        if (lane == r) {
+        warp_bitonic_topk<K>(key, gs);   // every lane of a group ends with the group's merged list
+        if (K > 4) {
+            if (lane == r0) {
 #pragma unroll
-            for (int s = 0; s < K; ++s) {
-                t.d[s] = __uint_as_float((unsigned)(key[s] >> 32));
-                t.idx[s] = (int)(unsigned)key[s];
+                for (int s = 0; s < K; ++s) {
+                    t.d[s] = __uint_as_float((unsigned)(key[s] >> 32));
+                    t.idx[s] = (int)(unsigned)key[s];
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {    // hand each list to the lane that owns the row (it may sit in another group)
+            if (g < ngroups) {
+                const int owner = g == 0 ? r0 : (g == 1 ? r1 : (g == 2 ? r2 : r3));
+#pragma unroll
+                for (int s = 0; s < K; ++s) {
+                    const unsigned long long kk = shfl_u64(key[s], g * gs);
+                    if (lane == owner) {
+                        t.d[s] = __uint_as_float((unsigned)(kk >> 32));
+                        t.idx[s] = (int)(unsigned)kk;
+                    }
+                }
             }
         }
     }
 
+#ifdef FLOCK_TIMELINE
+    if (lane == 0) {      // slowest warp of the CTA: shared pass, one-at-a-time pass (SM clocks); rows taken out, boxes opened
+        const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        if (cta < (size_t)kTimelineCtas) {
+            unsigned long long* d = p.timeline + cta * kTimelineSlots;
+            atomicMax(&d[4], (unsigned long long)(tl_c1 - tl_c0));
+            atomicMax(&d[5], (unsigned long long)(clock64() - tl_c1));
+            atomicAdd(&d[6], (unsigned long long)tl_nfar);
+            atomicAdd(&d[7], evaluated);
+        }
+    }
+#endif
     long long fx = 0;
     bool coll = false;
     if (has_row) {
@@ -890,6 +952,18 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_pruned_kernel(cons
         }
     }
     (void)wid;
+#ifdef FLOCK_TIMELINE
+    if (threadIdx.x == 0) {
+        const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        if (cta < (size_t)kTimelineCtas) {
+            unsigned long long* d = p.timeline + cta * kTimelineSlots;
+            d[0] = tl_entry;
+            d[1] = tl_entry;
+            d[2] = timeline_now();
+            d[3] = timeline_smid();
+        }
+    }
+#endif
 }
 
 static int pruned_rows_override() {   // FLOCK_PRUNED_ROWS=64|128|256: rows per CTA of the pruned kernel (tuning knob)
@@ -1054,11 +1128,19 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return ((unsigned long long)hi << 32) | lo;
 }
 
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// `width` (32, 16 or 8, warp-uniform): merge within aligned groups of that many lanes only
 template <int K>
-__device__ __forceinline__ void warp_bitonic_topk(unsigned long long (&key)[K]) {
+__device__ __forceinline__ void warp_bitonic_topk(unsigned long long (&key)[K], int width) {
     static_assert((K & (K - 1)) == 0, "K must be a power of two");
 #pragma unroll
     for (int m = 1; m < 32; m <<= 1) {
+        if (m >= width) break;
         unsigned long long other[K];
 #pragma unroll
         for (int s = 0; s < K; ++s) other[s] = shfl_xor_u64(key[s], m);
