@@ -55,6 +55,10 @@ if what in bench.WORKLOADS and not what == "cfg5":
     print("  work phase per CTA (us)   ", pct((a[:, 2] - a[:, 1]) / 1e3))
     per_sm = np.bincount(a[:, 3], minlength=148)
     print("  CTAs per SM: min %d max %d" % (per_sm.min(), per_sm.max()))
+    last_exit = np.array([((a[a[:, 3] == s, 2] - t0) / 1e3).max() if per_sm[s] else 0.0 for s in range(len(per_sm))])
+    for c in sorted(set(per_sm[per_sm > 0])):
+        sel = last_exit[per_sm == c]
+        print("  SMs with %2d CTAs: %3d, last exit mean %.2f max %.2f us" % (c, len(sel), sel.mean(), sel.max()))
 else:
     variant, k = {"uw2048": ("uw", 3), "uwd2048": ("uwd", 4), "v22048": ("v2", 8), "cfg5": ("v2", 8)}[what]
     env = VecEnv(variant, 64, 2048, k, 0.05, range_start=(0, 2000), sensor_range=100.0, seed=3, reset_collision_distance=0.05)
