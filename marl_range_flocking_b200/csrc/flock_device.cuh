@@ -95,6 +95,7 @@ __device__ __forceinline__ float* ring_row(const Params& p, int env, int slot, i
 // previous kernel's memory before the first global access. No-ops when the launch does not carry
 // the programmatic-serialization attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 

@@ -9,6 +9,10 @@
 #include "flock_device.cuh"
 #include "flock_launch.h"
 
+#ifndef FLOCK_PDL_PREFETCH
+#define FLOCK_PDL_PREFETCH 1      // 0: developer A/B build without the pre-wait L2 prefetch
+#endif
+
 namespace flock {
 
 constexpr int kSmallThreads = 64;    // 64-thread CTAs measured best (8.27 vs 8.43 us on cfg3, 7.57 vs 7.89 on cfg4)
@@ -284,13 +288,35 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
     const int num_tasks = p.num_tasks;
     const int warps_total = gridDim.x * kSmallWarps;
     const int nsteps = MULTI ? p.num_steps : 1;
+    const int GN = G * N;
+    const unsigned EN = (unsigned)p.E * (unsigned)N;
+#if FLOCK_PDL_PREFETCH
+    if (!MULTI) {
+        // Launched as a programmatic dependent, the CTA sits in griddepcontrol.wait for 0.3-0.5 us while the previous kernel
+        // of the stream drains (tools/cta_timeline.py). Loads must wait -- the previous kernel may be the one that writes
+        // our inputs -- but an L2 PREFETCH of the lines this warp is about to read is always safe (L2 is the point of
+        // coherence: a later write by the previous kernel lands in the same line) and turns the DRAM round trip after the
+        // wait into L2 hits when the state is cold.
+        const int task0 = blockIdx.x * kSmallWarps + wib;
+        const unsigned flat0 = (unsigned)task0 * (unsigned)GN + (unsigned)lane;
+        if (task0 < num_tasks && lane < GN && flat0 < EN) {
+            prefetch_l2(p.x + flat0);
+            prefetch_l2(p.y + flat0);
+            prefetch_l2(p.h + flat0);
+            if (V == FLOCK_UWD) {
+                prefetch_l2(p.actions + flat0);
+                if (p.noise != nullptr) prefetch_l2(p.noise + 2 * (size_t)flat0);
+            } else {
+                prefetch_l2(p.actions + 2 * (size_t)flat0);
+            }
+        }
+    }
+#endif
     pdl_wait_prior_grid();
 #ifdef FLOCK_TIMELINE
     const unsigned long long tl_go = timeline_now();
 #endif
 
-    const int GN = G * N;
-    const unsigned EN = (unsigned)p.E * (unsigned)N;
     const bool ring = (V == FLOCK_UW) && p.obs_head != nullptr;
     for (int task = blockIdx.x * kSmallWarps + wib; task < num_tasks; task += warps_total) {
         // the warp's agents are one contiguous run: index = task*G*N + lane, so the loads below can
