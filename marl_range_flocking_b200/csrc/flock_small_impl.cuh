@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     for (int s = 0; s < K; ++s) hist[s] = dist[s];
                 }
                 knn_small<K, PER, NJ4, V == FLOCK_UW, List>(sxg, syg, m.a, N, sstride, x, y, p.B, t, sumx, sumy);
+                if (V != FLOCK_UW && !MULTI) pdl_launch_dependents();   // the next kernel may start launching (and prefetching)
                 if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
                     comx = mean_of_sum(p, sumx);
                     comy = mean_of_sum(p, sumy);
@@ -506,7 +507,10 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
             }
         }
 
-        pdl_launch_dependents();   // the next kernel may start launching while we store the results
+        // Programmatic dependent launch trigger: v2 / uwd fire it right after the pair loop (see there), uw here, before
+        // the result stores (measured with the pre-wait prefetch in place: the early trigger gives cfg2 2.86 -> 2.78 us and
+        // cfg4 4.97 -> 4.88 us, but cfg3 5.22 -> 5.40 us: the uw epilogue is long and the waiting dependents get in its way)
+        if (V == FLOCK_UW || MULTI) pdl_launch_dependents();
         if (live) {
             p.xo[idx] = x;
             p.yo[idx] = y;
