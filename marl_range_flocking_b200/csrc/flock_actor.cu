@@ -172,6 +172,9 @@ flock_actor_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // launched as a programmatic dependent (launch_pdl): TMEM allocation and barrier set-up above overlap the previous
+    // kernel of the stream (usually the env step); nothing an earlier kernel wrote is read before this point
+    pdl_wait_prior_grid();
     if (threadIdx.x == 0) stamp(1);
 
     // The two single-thread roles run warp-uniformly (all 32 lanes execute the control flow and the
@@ -738,9 +741,8 @@ cudaError_t launch_actor_forward(const void* blobs, const float* obs, float* act
             return e;
         }
     }
-    actor::flock_actor_kernel<<<grid, actor::kThreads, actor::kSmemBytes, s>>>(bl, obs, actions, E, N, in_dims, tiles, per_cta,
-                                                                           ou, nullptr);
-    return cudaGetLastError();
+    return launch_pdl(actor::flock_actor_kernel, dim3(grid), dim3(actor::kThreads), actor::kSmemBytes, s, bl, obs, actions, E, N, in_dims,
+                      tiles, per_cta, ou, static_cast<long long*>(nullptr));
 }
 
 }  // namespace flock

@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // launched as a programmatic dependent (launch_pdl): TMEM allocation and barrier set-up above overlap the previous
+    // kernel of the stream (usually the env step); nothing an earlier kernel wrote is read before this point
+    pdl_wait_prior_grid();
 
     if (warp == kMmaWarp) {
         // ---- weight loader + MMA issuer (warp-uniform control flow, one elected lane issues) ----
@@ -451,6 +454,7 @@ __global__ void __launch_bounds__(kThreads, 2) flock_gru_tc_kernel(const __grid_
             stamp(it, 11);
         }
     }
+    pdl_launch_dependents();     // the next kernel of the stream (recurrent actor: the MLP kernel; the env step) may start launching
     tc_fence_before();
     __syncthreads();
     stamp(1, 12);
@@ -573,9 +577,9 @@ cudaError_t launch_gru_tc_forward(int mode, const void* blobs, const float* obs,
         cudaMemsetAsync(dbg, 0, (size_t)grid * 32 * sizeof(long long), s);
         a.dbg = dbg;
     }
-    if (mode == 1) grutc::flock_gru_tc_kernel<1><<<grid, grutc::kThreads, grutc::Layout<1>::kSmemBytes, s>>>(a);
-    else grutc::flock_gru_tc_kernel<0><<<grid, grutc::kThreads, grutc::Layout<0>::kSmemBytes, s>>>(a);
-    const cudaError_t launched = cudaGetLastError();
+    const cudaError_t launched =
+        mode == 1 ? launch_pdl(grutc::flock_gru_tc_kernel<1>, dim3(grid), dim3(grutc::kThreads), grutc::Layout<1>::kSmemBytes, s, a)
+                  : launch_pdl(grutc::flock_gru_tc_kernel<0>, dim3(grid), dim3(grutc::kThreads), grutc::Layout<0>::kSmemBytes, s, a);
     if (dbg != nullptr) {
         timing = false;
         cudaStreamSynchronize(s);

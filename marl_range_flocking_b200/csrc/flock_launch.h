@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 namespace flock {
 struct Params;
 
@@ -32,6 +34,27 @@ struct DeviceOnce {
         return cudaSuccess;
     }
 };
+
+// Launch `kernel` as a programmatic dependent of the previous kernel of the stream (FLOCK_PDL=0 disables): it may start
+// while that kernel drains and must execute griddepcontrol.wait before it reads anything an earlier kernel wrote.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    static const bool use_pdl = [] {
+        const char* v = getenv("FLOCK_PDL");
+        return v == nullptr || v[0] != '0';
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // device-side step counters of the fused exploration noise (flock_noise_counters_t)
 struct NoiseCounters {

@@ -130,6 +130,9 @@ flock_rnn_mlp_kernel(const uint8_t* __restrict__ blobs, const float* __restrict_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // launched as a programmatic dependent (launch_pdl): TMEM allocation and barrier set-up above overlap the previous
+    // kernel of the stream (usually the env step); nothing an earlier kernel wrote is read before this point
+    pdl_wait_prior_grid();
 
     // roles, barriers and parities exactly as in flock_actor_kernel
     if (warp == kTmaWarp) {
@@ -553,9 +556,8 @@ cudaError_t launch_rnn_actor_forward(const void* blobs, const float* const* fron
     const int total = tiles * N;
     const int per_cta = (total + sm_count - 1) / sm_count;
     const int grid = (total + per_cta - 1) / per_cta;
-    rnn::flock_rnn_mlp_kernel<<<grid, rnn::kThreads, rnn::kSmemBytes, s>>>(static_cast<const uint8_t*>(blobs), hidden_out,
-                                                                         actions, E, N, tiles, per_cta, ou);
-    return cudaGetLastError();
+    return launch_pdl(rnn::flock_rnn_mlp_kernel, dim3(grid), dim3(rnn::kThreads), rnn::kSmemBytes, s, static_cast<const uint8_t*>(blobs),
+                      static_cast<const float*>(hidden_out), actions, E, N, tiles, per_cta, ou);
 }
 
 }  // namespace flock
