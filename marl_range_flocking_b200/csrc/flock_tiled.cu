@@ -419,7 +419,6 @@ __global__ void __launch_bounds__(256) flock_integrate_kernel(const __grid_const
     const size_t base = (size_t)env * N;
     const bool real = slot < N;
     const bool in_record = SORTED && slot < PS;   // PS is a multiple of 32: whole warps are in or out
-    pdl_launch_dependents();      // the sensing kernel may start launching: it waits (griddepcontrol.wait) before it reads our results
     float x = kInf, y = 0.0f;                     // padding slots: never selected, never collide
     int agent = 0;
     if (real) {
@@ -556,19 +555,13 @@ __global__ void __launch_bounds__(kMaxTileThreads, 4) flock_step_pruned_kernel(c
     const size_t base = (size_t)env * N;
     const int slot = tile * rows + threadIdx.x;
     const bool has_row = slot < N;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    // Programmatic dependent launch: this kernel is launched while the integrate pre-pass still runs. What does not depend
-    // on it -- the row order and the hint rows (last step's neighbours) -- is requested first; everything the pre-pass
-    // writes (the staging record, the far-row flags, headings) is touched only after griddepcontrol.wait.
-    const int i = has_row ? p.perm[base + slot] : N;    // this thread's agent
-    uint4 hv_pre = make_uint4(~0u, ~0u, ~0u, ~0u);
-    if (has_row) hv_pre = reinterpret_cast<const uint4*>(p.hint_slots)[(size_t)env * PS + slot];
-    pdl_wait_prior_grid();
     if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
         const uint32_t bytes = (uint32_t)(sorted_record_floats(PS) * sizeof(float));
         mbar_expect_tx(&bar, bytes);
         tma_load_1d(smem, p.sorted_xy + (size_t)env * sorted_record_floats(PS), bytes, &bar);
     }
+    const int i = has_row ? p.perm[base + slot] : N;    // this thread's agent
     // Threshold hints: the slots of last step's k neighbours, kept by this kernel in slot order (one
     // coalesced 16-byte row per agent). Any k distinct other slots bound the k-th distance, so stale
     // rows are harmless; rows invalidated by a row-order refresh or a reset (0xffff) fall back to the
@@ -576,7 +569,8 @@ __global__ void __launch_bounds__(kMaxTileThreads, 4) flock_step_pruned_kernel(c
     int hslot[K];
     bool hint_ok = has_row;
     {
-        const uint4 hv = hv_pre;
+        uint4 hv = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (has_row) hv = reinterpret_cast<const uint4*>(p.hint_slots)[(size_t)env * PS + slot];
         const unsigned w[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
         for (int s = 0; s < K; ++s) {
@@ -983,23 +977,10 @@ static cudaError_t launch_pruned(const Params& p, int sm_count, cudaStream_t s) 
     }
     const int rows = pruned_rows_override() ? pruned_rows_override() : choose_rows(p.N, p.E, sm_count);
     const dim3 grid((p.N + rows - 1) / rows, p.E);
-    // launch 2 of 2 as a programmatic dependent of the pre-pass (FLOCK_PDL=0 disables): its launch latency and its hint
-    // loads overlap the pre-pass, which triggers its dependents at entry
-    static const bool use_pdl = [] {
-        const char* v = getenv("FLOCK_PDL");
-        return v == nullptr || v[0] != '0';
-    }();
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(rows);
-    cfg.dynamicSmemBytes = pruned_smem_bytes(p.N, rows);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, flock_step_pruned_kernel<V, K, PER>, p);
+    // (launching this kernel as a programmatic dependent of the pre-pass was measured: +2 us at 64 envs when launched
+    // eagerly, nothing under graph replay, and a LOSS of 5-14 us per step at 16-48 envs -- plain stream order it is)
+    flock_step_pruned_kernel<V, K, PER><<<grid, rows, pruned_smem_bytes(p.N, rows), s>>>(p);
+    return cudaGetLastError();
 }
 
 // Row order for the thread-per-row kernels: agents sorted by the Hilbert index of their cell on a
