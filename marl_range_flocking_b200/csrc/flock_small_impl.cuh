@@ -9,6 +9,9 @@
 #include "flock_device.cuh"
 #include "flock_launch.h"
 
+#ifndef FLOCK_LATE_TRIGGER
+#define FLOCK_LATE_TRIGGER 0        // 1: developer A/B build with the dependents' trigger before the result stores for every variant
+#endif
 #ifndef FLOCK_PDL_PREFETCH
 #define FLOCK_PDL_PREFETCH 1      // 0: developer A/B build without the pre-wait L2 prefetch
 #endif
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
                     for (int s = 0; s < K; ++s) hist[s] = dist[s];
                 }
                 knn_small<K, PER, NJ4, V == FLOCK_UW, List>(sxg, syg, m.a, N, sstride, x, y, p.B, t, sumx, sumy);
-                if (V != FLOCK_UW && !MULTI) pdl_launch_dependents();   // the next kernel may start launching (and prefetching)
+                if (V != FLOCK_UW && !MULTI && !FLOCK_LATE_TRIGGER) pdl_launch_dependents();   // the next kernel may start launching (and prefetching)
                 if (V == FLOCK_UW) {  // torch.mean(positions, 0), gym_flock_uw.py:193
                     comx = mean_of_sum(p, sumx);
                     comy = mean_of_sum(p, sumy);
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(kSmallThreads) flock_step_small_kernel(const _
         // Programmatic dependent launch trigger: v2 / uwd fire it right after the pair loop (see there), uw here, before
         // the result stores (measured with the pre-wait prefetch in place: the early trigger gives cfg2 2.86 -> 2.78 us and
         // cfg4 4.97 -> 4.88 us, but cfg3 5.22 -> 5.40 us: the uw epilogue is long and the waiting dependents get in its way)
-        if (V == FLOCK_UW || MULTI) pdl_launch_dependents();
+        if (V == FLOCK_UW || MULTI || FLOCK_LATE_TRIGGER) pdl_launch_dependents();
         if (live) {
             p.xo[idx] = x;
             p.yo[idx] = y;
