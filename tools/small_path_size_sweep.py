@@ -1,4 +1,5 @@
-"""Step time of the small path over a range of batch sizes (four L2-resident env batches, graph replay): developer A/B of\nbuild variants (FLOCK_LIBRARY_PATH), e.g. trigger placement / pre-wait prefetch. usage: python tools/small_path_size_sweep.py"""
+"""Step time of the small path over a range of batch sizes (four L2-resident env batches, graph replay): developer A/B of
+build variants (FLOCK_LIBRARY_PATH), e.g. trigger placement / pre-wait prefetch. usage: python tools/small_path_size_sweep.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
