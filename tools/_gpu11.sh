@@ -1,5 +1,5 @@
 set -x
-O=gpurun_out/r02g
+O=gpurun_out/r02h
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=12 -p no:cacheprovider > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 tail -3 $O/pytest.log
