@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kMaxTileThreads) flock_step_tiled_kernel(const
 }
 
 // -------------------------------------------------------------------------------------------------
-// v2, many envs x large swarm: thread-per-row kernel with EXACT spatial pruning.
+// Many envs x large swarm (all three variants): thread-per-row kernel with EXACT spatial pruning.
 //
 // The env is staged in the spatially sorted row order (p.perm: Morton cells), so both the 32 rows of a
 // warp and every block of 32 consecutive neighbour slots are compact in space. For each block the
@@ -393,7 +393,7 @@ __device__ __forceinline__ float axis_gap(float a0, float a1, float b0, float b1
 }
 
 // -------------------------------------------------------------------------------------------------
-// Pruned path for v2 large swarms. Two launches per step:
+// Pruned path for large swarms (v2: min-image metric; uw / uw_discrete: Euclidean). Two launches per step:
 //  1. flock_integrate_kernel<V2, SORTED>: one thread per sorted SLOT integrates its agent ONCE (same code
 //     as everywhere else), writes the new state at the agent's index and, per env, a staging record
 //     [x by slot | y by slot | bounding boxes of every 8 consecutive slots] that is contiguous in memory.
